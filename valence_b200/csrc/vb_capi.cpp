@@ -1,0 +1,225 @@
+// C-ABI of libvalence_b200.so (see include/valence_b200.h for the contract and the reference
+// lines each entry point replaces).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+
+#include "../../include/valence_b200.h"
+#include "vb_engine.h"
+
+struct vb_engine {
+    std::unique_ptr<vb::Engine> eng;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+void to_c(const vb::EnergyResult& r, vb_energy_result* o)
+{
+    o->energy = r.energy; o->enucrep = r.enucrep; o->numerator = r.numerator; o->wfnorm = r.wfnorm; o->e1 = r.e1; o->e2 = r.e2;
+    for (int i = 0; i < VB_CNT_N; ++i) o->counters[i] = r.counters[i];
+    o->n_entries = r.n_entries; o->n_groups = r.n_groups; o->n_pairgroups = r.n_pairgroups; o->n_tiles = r.n_tiles;
+    o->n_tiles_mine = r.n_tiles_mine; o->n_ao_quartets = r.n_ao_quartets; o->n_prim_quartets = r.n_prim_quartets;
+    o->flops_model = r.flops_model; o->ref_shell_quartets = r.ref_shell_quartets;
+    o->t_total_ms = r.t_total; o->t_host_setup_ms = r.t_host_setup; o->t_1e_ms = r.t_1e; o->t_density_ms = r.t_density;
+    o->t_diag_ms = r.t_diag; o->t_tiles_ms = r.t_tiles; o->launches = r.launches; o->diag_launches = r.diag_launches;
+    o->tile_launches = r.tile_launches; o->min_pivot_ratio = r.min_pivot_ratio;
+}
+
+template <class F>
+int guarded(F&& f)
+{
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return 1;
+    } catch (...) {
+        g_err = "unknown error";
+        return 1;
+    }
+}
+
+// one live instance per process, like the reference's module globals (valence_finalize_module.F90:23-52)
+std::unique_ptr<vb::Engine> g_api;
+vb::EnergyResult g_last;   // kept for resume across calculate calls
+
+// xm_abort (xm_module.F90:942-950): `error` line from this rank, then stop
+[[noreturn]] void api_abort(const std::string& msg)
+{
+    std::printf("%-40s from rank %8d\n", msg.c_str(), 0);
+    std::fflush(stdout);
+    std::exit(1);
+}
+
+std::string host_argv1()
+{
+    if (const char* env = std::getenv("VALENCE_INPUT")) return env;
+    std::ifstream f("/proc/self/cmdline", std::ios::binary);
+    std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    size_t z = all.find('\0');
+    if (z == std::string::npos || z + 1 >= all.size()) return "";
+    return std::string(all.c_str() + z + 1);
+}
+
+// xm_output 'save' (xm_module.F90:464-577): orbitals + energy, formats :571-576
+void write_orbitals_file(const vb::Input& in, const std::vector<std::vector<double>>* coeff, double energy)
+{
+    FILE* fh = std::fopen("orbitals", "w");
+    if (!fh) return;
+    const int nval = in.norbs() - in.ndf;
+    for (int o = 0; o < in.norbs(); ++o) {
+        if (o == nval) std::fprintf(fh, "\n");
+        const vb::OrbitalDef& od = in.orbitals[o];
+        std::fprintf(fh, "     %2d     ", (int)od.atoms.size());
+        for (int a : od.atoms) std::fprintf(fh, "%4d", a);
+        std::fprintf(fh, "%4d\n", (int)od.xp.size());
+        for (size_t k = 0; k < od.xp.size(); ++k) {
+            double c = coeff ? (*coeff)[o][k] : od.coeff[k];
+            std::fprintf(fh, "%4d %13.8f", od.xp[k], c);
+            if (k % 4 == 3 || k + 1 == od.xp.size()) std::fprintf(fh, "\n");
+        }
+    }
+    if (in.ndf == 0) std::fprintf(fh, "\n");
+    std::fprintf(fh, "\n total energy in atomic units %32.16f\n\n", energy);
+    std::fclose(fh);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vb_last_error(void) { return g_err.c_str(); }
+
+int vb_engine_create(const char* input_path, int device, vb_engine** out)
+{
+    *out = nullptr;
+    return guarded([&] {
+        vb::Input in = vb::parse_input_file(input_path);
+        std::unique_ptr<vb_engine> h(new vb_engine);
+        h->eng.reset(new vb::Engine(in, device));
+        *out = h.release();
+    });
+}
+
+void vb_engine_destroy(vb_engine* e) { delete e; }
+int vb_engine_natom(const vb_engine* e) { return e->eng->input().natom; }
+int vb_engine_nelec(const vb_engine* e) { return e->eng->input().nelec(); }
+
+int vb_engine_set_coords(vb_engine* e, const double* x)
+{
+    return guarded([&] { e->eng->set_coords_angstrom(x); });
+}
+
+int vb_engine_energy(vb_engine* e, vb_energy_result* out)
+{
+    return guarded([&] {
+        vb::EnergyResult r;
+        e->eng->energy(&r);
+        to_c(r, out);
+    });
+}
+
+int vb_engine_energy_partial(vb_engine* e, int rank, int nranks, vb_energy_result* out)
+{
+    return guarded([&] {
+        if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("bad rank / nranks");
+        vb::EnergyResult r;
+        e->eng->energy_partial(rank, nranks, &r);
+        to_c(r, out);
+    });
+}
+
+int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out)
+{
+    return guarded([&] {
+        vb::EnergyResult r;
+        // carry the partial's workload fields through
+        r.n_entries = out->n_entries; r.n_groups = out->n_groups; r.n_pairgroups = out->n_pairgroups; r.n_tiles = out->n_tiles;
+        r.n_tiles_mine = out->n_tiles_mine; r.n_ao_quartets = out->n_ao_quartets; r.n_prim_quartets = out->n_prim_quartets;
+        r.flops_model = out->flops_model; r.t_host_setup = out->t_host_setup_ms; r.t_1e = out->t_1e_ms; r.t_density = out->t_density_ms;
+        r.t_diag = out->t_diag_ms; r.t_tiles = out->t_tiles_ms; r.diag_launches = out->diag_launches; r.tile_launches = out->tile_launches;
+        r.min_pivot_ratio = out->min_pivot_ratio; r.enucrep = out->enucrep; r.e1 = out->e1; r.wfnorm = out->wfnorm;
+        e->eng->energy_finish(&r);
+        to_c(r, out);
+    });
+}
+
+double* vb_engine_accum_device(const vb_engine* e) { return e->eng->accum_device(); }
+int vb_engine_accum_len(const vb_engine* e) { return e->eng->accum_len(); }
+void* vb_engine_stream(const vb_engine* e) { return e->eng->stream(); }
+
+/* ---- reference-compatible layer ------------------------------------------------------------- */
+void valence_api_initialize_(int* info, int* call_mpi_init, int* comm)
+{
+    (void)call_mpi_init; (void)comm;   // single process per GPU; no MPI inside the engine
+    std::string path = host_argv1();
+    if (path.empty()) api_abort("must have one input file");            // valence_initialize_module.F90:50
+    try {
+        vb::Input in = vb::parse_input_file(path);
+        int dev = 0;
+        if (const char* lr = std::getenv("LOCAL_RANK")) dev = std::atoi(lr);
+        g_api.reset(new vb::Engine(in, dev));
+    } catch (const vb::InputError& ex) {
+        api_abort(ex.what());
+    } catch (const std::exception& ex) {
+        api_abort(ex.what());
+    }
+    *info = 0;                                                           // valence_api.F90:31
+}
+
+void valence_api_calculate_energy_(double* x, double* v)
+{
+    if (!g_api) api_abort("valence_api_calculate_energy before valence_api_initialize");
+    try {
+        g_api->set_coords_angstrom(x);                                   // valence_api.F90:57-63
+        vb::EnergyResult r;
+        g_api->energy(&r);
+        g_last = r;
+        if (g_api->input().natom > 1) std::printf(" %-32s  %24.16f\n", "nuclear repulsion", r.enucrep);   // valence.F90:92
+        std::printf(" %-32s  %24.16f\n", "guess energy", r.energy);                                      // valence.F90:191
+        std::fflush(stdout);
+        write_orbitals_file(g_api->input(), nullptr, r.energy);                                          // valence.F90:192
+        if (g_api->input().max_iter > 0)
+            api_abort("orbital optimisation is not available in this build");
+        *v = r.energy;
+    } catch (const std::exception& ex) {
+        api_abort(ex.what());
+    }
+}
+
+const double* vb_api_input_coords(void) { return g_api ? g_api->input().coords.data() : nullptr; }
+
+void valence_api_finalize_(int* call_mpi_finalize)
+{
+    (void)call_mpi_finalize;
+    g_api.reset();
+}
+
+void init_(int* info)
+{
+    int one = 1, dummy = 0;
+    valence_api_initialize_(info, &one, &dummy);                         // valence_api_nitrogen.F90:4-9
+}
+void getn_(int* n)
+{
+    if (!g_api) api_abort("getn before init");
+    *n = g_api->input().natom;                                           // valence_api_nitrogen.F90:11-21
+}
+void calcsurface_(double* x, double* v)
+{
+    valence_api_calculate_energy_(x, v);
+    *v = *v * 219474.631;                                                // valence_api_nitrogen.F90:23-32
+}
+void finalize_(void)
+{
+    int one = 1;
+    valence_api_finalize_(&one);                                         // valence_api_nitrogen.F90:34-36
+}
+
+}  // extern "C"

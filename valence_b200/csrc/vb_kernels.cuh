@@ -1,0 +1,319 @@
+// CUDA kernels of the VSVB energy engine (sm_100a).
+//
+//   k_ao_1e        AO overlap and core-Hamiltonian matrices (replaces the SIMINT
+//                  overlap/ke/potential calls of ovint/int1e, valence.F90:2988,3132,3151)
+//   k_orb_1e       orbital-level <bra_s|ket_t>, <bra_s|h|ket_t> (ovint/int1e, :2891-3176)
+//   k_gather_block / k_gj_inverse / k_entry_density
+//                  spin-block overlap matrices, their inverses and determinants
+//                  (replaces density/det/givdr, :1535-2144, by the inverse form,
+//                  SURVEY.md appendix B)
+//   k_tile         fused shell-quartet ERI generation + transformation to the
+//                  orbital-pair basis + contraction with the cofactor densities
+//                  (replaces int2e :3184-3438 and the 2e loop of vsvb_energy :1153-1433)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vb_eri.cuh"
+#include "vb_setup.h"
+
+namespace vb {
+
+enum { CNT_SCHWARZ_EREP = 0, CNT_SCHWARZ_EXCH, CNT_VALUE_EREP, CNT_VALUE_EXCH, CNT_INT2E, CNT_SHELLQ, CNT_SHORTCUT,
+       CNT_ENTRIES, CNT_N };
+
+struct DevShell {          // global shell on the device
+    double x, y, z;
+    int l, nprim, prim_off, ao_off;
+};
+
+struct TileArgs {
+    const PGDesc* pgs;
+    const int* pg_pairs;
+    const SPRec* sps;
+    const Item* items;
+    const PrimPair* pps;
+    const double* dmat;
+    const double* boys;
+    const int2* tiles;
+    int ntiles;
+    int tile_first, tile_stride;     // static block-cyclic shard of this rank; work stealing inside
+    unsigned int* counter;
+    int mode;                        // 0 = diagonal (Schwarz) pass, 1 = energy, 2 = export G
+    int nso, nnd, sym, subject;
+    int dq_cap;                      // doubles reserved for the staged ket density
+    double* diag;                    // mode 0: (s,t) -> (st|st)
+    const double* sch;               // mode 1: Schwarz table as the reference indexes it, nso*nso
+    double itol;
+    const double* Pa;                // entry-level alpha / beta densities, nso*nso
+    const double* Pb;
+    double c0;                       // det(alpha block) * det(beta block) * coupling weights
+    const int* nsh_bra;              // # shells passing the weight screen, per entry (bra / ket orbital)
+    const int* nsh_ket;
+    double* tileE;                   // mode 1: per-tile energy partial (deterministic reduction later)
+    unsigned long long* counters;    // CNT_N
+    double* gfull;                   // mode 2: dense G over ordered pairs
+    const int* pair_index;           // mode 2: (s*nso+t) -> dense pair index, or -1
+    int npairs_total;
+    double* gen_scratch;             // generic (d-shell) path scratch, GEN_SCRATCH doubles per thread
+};
+
+// ------------------------------------------------------------------------------------------------
+// one-electron AO matrices
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dev_binom(int n, int k)
+{
+    double r = 1.0;
+    for (int i = 0; i < k; ++i) r = r * (n - i) / (i + 1);
+    return r;
+}
+
+__global__ void k_ao_1e(const DevShell* __restrict__ sh, int nshell, const double* __restrict__ exps,
+                        const double* __restrict__ coefs, const double* __restrict__ nuc /* x,y,z,Z per atom */, int natom,
+                        const double* __restrict__ boys_tab, int nao, double* __restrict__ S, double* __restrict__ H)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long npair = (long long)nshell * (nshell + 1) / 2;
+    if (idx >= npair) return;
+    int i = (int)floor(sqrt(2.0 * (double)idx + 0.25) - 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
+    while ((long long)i * (i + 1) / 2 > idx) --i;
+    int j = (int)(idx - (long long)i * (i + 1) / 2);
+    DevShell A = sh[i], B = sh[j];
+    if (A.l < B.l) { DevShell t = A; A = B; B = t; }   // A carries la >= lb
+    const int la = A.l, lb = B.l, L = la + lb, na = ncart(la), nb = ncart(lb);
+    double AB[3] = {A.x - B.x, A.y - B.y, A.z - B.z};
+    double AB2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+    double Sb[36], Hb[36];
+    for (int n = 0; n < na * nb; ++n) { Sb[n] = 0.0; Hb[n] = 0.0; }
+    for (int ia = 0; ia < A.nprim; ++ia)
+        for (int ib = 0; ib < B.nprim; ++ib) {
+            double a = exps[A.prim_off + ia], b = exps[B.prim_off + ib], p = a + b, ip = 1.0 / p, h2p = 0.5 * ip;
+            double K = coefs[A.prim_off + ia] * coefs[B.prim_off + ib] * exp(-a * b * ip * AB2);
+            if (K == 0.0) continue;
+            double P[3] = {(a * A.x + b * B.x) * ip, (a * A.y + b * B.y) * ip, (a * A.z + b * B.z) * ip};
+            double PA[3] = {P[0] - A.x, P[1] - A.y, P[2] - A.z};
+            double PB[3] = {P[0] - B.x, P[1] - B.y, P[2] - B.z};
+            // 1D overlap tables s[d][i][j], i <= la, j <= lb + 2
+            double s[3][3][5];
+            for (int d = 0; d < 3; ++d) {
+                s[d][0][0] = 1.0;
+                for (int ii = 1; ii <= la; ++ii) s[d][ii][0] = PA[d] * s[d][ii - 1][0] + (ii > 1 ? (ii - 1) * h2p * s[d][ii - 2][0] : 0.0);
+                for (int jj = 1; jj <= lb + 2; ++jj)
+                    for (int ii = 0; ii <= la; ++ii) {
+                        double v = PB[d] * s[d][ii][jj - 1];
+                        if (ii > 0) v += ii * h2p * s[d][ii - 1][jj - 1];
+                        if (jj > 1) v += (jj - 1) * h2p * s[d][ii][jj - 2];
+                        s[d][ii][jj] = v;
+                    }
+            }
+            double pref = K * pow(PI * ip, 1.5);
+            for (int ca = 0; ca < na; ++ca) {
+                int c1 = coff(la) + ca, al[3] = {c_lx(c1), c_ly(c1), c_lz(c1)};
+                for (int cb = 0; cb < nb; ++cb) {
+                    int c2 = coff(lb) + cb, bl[3] = {c_lx(c2), c_ly(c2), c_lz(c2)};
+                    double sx[3], tx[3];
+                    for (int d = 0; d < 3; ++d) {
+                        int ii = al[d], jj = bl[d];
+                        sx[d] = s[d][ii][jj];
+                        tx[d] = -2.0 * b * b * s[d][ii][jj + 2] + b * (2.0 * jj + 1.0) * s[d][ii][jj];
+                        if (jj >= 2) tx[d] -= 0.5 * jj * (jj - 1) * s[d][ii][jj - 2];
+                    }
+                    Sb[ca * nb + cb] += pref * sx[0] * sx[1] * sx[2];
+                    Hb[ca * nb + cb] += pref * (tx[0] * sx[1] * sx[2] + sx[0] * tx[1] * sx[2] + sx[0] * sx[1] * tx[2]);
+                }
+            }
+            // nuclear attraction: [e|C]^(m), e <= L, bra-only vertical recurrence, then HRR by binomials
+            for (int c = 0; c < natom; ++c) {
+                double Z = nuc[4 * c + 3];
+                if (!(fabs(Z) > 1.0e-12)) continue;     // valence.F90:3149
+                double PC[3] = {P[0] - nuc[4 * c], P[1] - nuc[4 * c + 1], P[2] - nuc[4 * c + 2]};
+                double U = p * (PC[0] * PC[0] + PC[1] * PC[1] + PC[2] * PC[2]);
+                double F[EMAX + 1];
+                boys_rt(L, boys_tab, U, F);
+                double R[EMAX + 1][ncum(EMAX)];
+                double pv = -Z * K * 2.0 * PI * ip;
+                for (int m = 0; m <= L; ++m) R[m][0] = pv * F[m];
+                for (int e = 1; e < ncum(L); ++e) {
+                    int d = c_dir(e), e1 = c_dec(e, d), n1 = c_l(e1, d), Le = c_L(e);
+                    int e2 = n1 > 0 ? c_dec(e1, d) : 0;
+                    for (int m = 0; m <= L - Le; ++m) {
+                        double v = PA[d] * R[m][e1] - PC[d] * R[m + 1][e1];
+                        if (n1 > 0) v += n1 * h2p * (R[m][e2] - R[m + 1][e2]);
+                        R[m][e] = v;
+                    }
+                }
+                for (int ca = 0; ca < na; ++ca) {
+                    int c1 = coff(la) + ca, ax = c_lx(c1), ay = c_ly(c1), az = c_lz(c1);
+                    for (int cb = 0; cb < nb; ++cb) {
+                        int c2 = coff(lb) + cb, bx = c_lx(c2), by = c_ly(c2), bz = c_lz(c2);
+                        double v = 0.0;
+                        for (int kx = 0; kx <= bx; ++kx)
+                            for (int ky = 0; ky <= by; ++ky)
+                                for (int kz = 0; kz <= bz; ++kz)
+                                    v += dev_binom(bx, kx) * dev_binom(by, ky) * dev_binom(bz, kz) * pow(AB[0], (double)(bx - kx)) *
+                                         pow(AB[1], (double)(by - ky)) * pow(AB[2], (double)(bz - kz)) * R[0][cidx(ax + kx, ay + ky, az + kz)];
+                        Hb[ca * nb + cb] += v;
+                    }
+                }
+            }
+        }
+    for (int ca = 0; ca < na; ++ca)
+        for (int cb = 0; cb < nb; ++cb) {
+            size_t r = (size_t)A.ao_off + ca, c = (size_t)B.ao_off + cb;
+            S[r * nao + c] = Sb[ca * nb + cb]; S[c * nao + r] = Sb[ca * nb + cb];
+            H[r * nao + c] = Hb[ca * nb + cb]; H[c * nao + r] = Hb[ca * nb + cb];
+        }
+}
+
+// orbital-level one-electron integrals: out_s[k], out_h[k] for the pair list (x_k, y_k) of orbital ids.
+// Orbitals are CSR lists of (AO, weight * angn).
+__global__ void k_orb_1e(const int* __restrict__ optr, const int* __restrict__ oao, const double* __restrict__ oc,
+                         const int2* __restrict__ pairs, int npairs, int nao, const double* __restrict__ S,
+                         const double* __restrict__ H, double* __restrict__ out_s, double* __restrict__ out_h)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npairs) return;
+    int x = pairs[k].x, y = pairs[k].y;
+    double ss = 0.0, hh = 0.0;
+    for (int i = optr[x]; i < optr[x + 1]; ++i) {
+        const double ci = oc[i];
+        const size_t row = (size_t)oao[i] * nao;
+        double ts = 0.0, th = 0.0;
+        for (int j = optr[y]; j < optr[y + 1]; ++j) {
+            ts += oc[j] * S[row + oao[j]];
+            if (H) th += oc[j] * H[row + oao[j]];
+        }
+        ss += ci * ts;
+        hh += ci * th;
+    }
+    out_s[k] = ss;
+    if (out_h) out_h[k] = hh;
+}
+
+// M[r][c] = Se[entry_of_slot(bra_list[r])][entry_of_slot(ket_list[c])]   (row-major n x n)
+__global__ void k_gather_block(const double* __restrict__ Se, int nso, const int* __restrict__ bra_entry,
+                               const int* __restrict__ ket_entry, int n, double* __restrict__ M)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    int r = idx / n, c = idx % n;
+    M[idx] = Se[(size_t)bra_entry[r] * nso + ket_entry[c]];
+}
+
+// In-place Gauss-Jordan inverse with partial pivoting, one CTA per matrix (row-major, n x n).
+// out[0] = determinant, out[1] = smallest |pivot| / largest |pivot| seen.
+__global__ void k_gj_inverse(double* __restrict__ Ms, const int* __restrict__ ns, const long long* __restrict__ offs,
+                             int* __restrict__ piv_ws, const long long* __restrict__ piv_offs, double* __restrict__ outs)
+{
+    const int b = blockIdx.x, n = ns[b];
+    double* A = Ms + offs[b];
+    int* piv = piv_ws + piv_offs[b];
+    double* out = outs + 2 * b;
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_piv, s_det, s_min, s_max;
+    __shared__ int s_row;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { s_det = 1.0; s_min = 1e300; s_max = 0.0; }
+    if (n == 0) { if (tid == 0) { out[0] = 1.0; out[1] = 1.0; } return; }
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        // pivot search in column k, rows k..n-1
+        double best = -1.0; int bi = k;
+        for (int r = k + tid; r < n; r += nt) { double v = fabs(A[(size_t)r * n + k]); if (v > best) { best = v; bi = r; } }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, best, o); int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double bv = -1.0; int br = k;
+            for (int w = 0; w < (nt + 31) / 32; ++w) if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < br)) { bv = s_val[w]; br = s_idx[w]; }
+            s_row = br; piv[k] = br;
+            double pv = A[(size_t)br * n + k];
+            s_piv = pv;
+            s_det *= (br != k) ? -pv : pv;
+            s_min = fmin(s_min, fabs(pv)); s_max = fmax(s_max, fabs(pv));
+        }
+        __syncthreads();
+        const int pr = s_row; const double pv = s_piv;
+        if (pv == 0.0) { if (tid == 0) { out[0] = 0.0; out[1] = 0.0; } return; }
+        if (pr != k) for (int c = tid; c < n; c += nt) { double t = A[(size_t)k * n + c]; A[(size_t)k * n + c] = A[(size_t)pr * n + c]; A[(size_t)pr * n + c] = t; }
+        __syncthreads();
+        const double ipv = 1.0 / pv;
+        for (int c = tid; c < n; c += nt) A[(size_t)k * n + c] = (c == k) ? ipv : A[(size_t)k * n + c] * ipv;
+        __syncthreads();
+        // eliminate column k from every other row: one warp per row strip
+        for (int r = (tid >> 5); r < n; r += (nt >> 5)) {
+            if (r == k) continue;
+            double f = A[(size_t)r * n + k];
+            if (f == 0.0) continue;
+            for (int c = (tid & 31); c < n; c += 32) {
+                double v = A[(size_t)r * n + c];
+                A[(size_t)r * n + c] = (c == k) ? -f * A[(size_t)k * n + k] : v - f * A[(size_t)k * n + c];
+            }
+        }
+        __syncthreads();
+    }
+    // undo the row interchanges as column interchanges, last first
+    for (int k = n - 1; k >= 0; --k) {
+        int pr = piv[k];
+        if (pr != k) for (int r = tid; r < n; r += nt) { double t = A[(size_t)r * n + k]; A[(size_t)r * n + k] = A[(size_t)r * n + pr]; A[(size_t)r * n + pr] = t; }
+        __syncthreads();
+    }
+    if (tid == 0) { out[0] = s_det; out[1] = s_max > 0.0 ? s_min / s_max : 0.0; }
+}
+
+// entry-level density of one spin block: P[s][t] = Minv[pos_ket(t)][pos_bra(s)], 0 when an entry has no slot of this spin
+__global__ void k_entry_density(const double* __restrict__ Minv, int n, const int* __restrict__ pos_bra,
+                                const int* __restrict__ pos_ket, int nso, double* __restrict__ P)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nso * nso) return;
+    int s = idx / nso, t = idx % nso;
+    int r = pos_bra[s], c = pos_ket[t];
+    P[idx] = (r >= 0 && c >= 0) ? Minv[(size_t)c * n + r] : 0.0;
+}
+
+// deterministic two-level sum of n doubles (fixed tree; same result on every run and for every grid)
+__global__ void k_sum(const double* __restrict__ x, long long n, double* __restrict__ out)
+{
+    __shared__ double sh[1024];
+    double acc = 0.0, comp = 0.0;   // Kahan per thread over a fixed stride pattern
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        double y = x[i] - comp, t = acc + y;
+        comp = (t - acc) - y;
+        acc = t;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// E1 = sum_st h[s][t] (Pa+Pb)[s][t],  N1 = sum_st S[s][t] (Pa+Pb)[s][t]   (valence.F90:1072-1106)
+__global__ void k_one_electron_energy(const double* __restrict__ Se, const double* __restrict__ He,
+                                      const double* __restrict__ Pa, const double* __restrict__ Pb, int n2,
+                                      double* __restrict__ out /* [2] */)
+{
+    __shared__ double sh[2][1024];
+    double e = 0.0, w = 0.0;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        double p = Pa[i] + Pb[i];
+        e += He[i] * p;
+        w += Se[i] * p;
+    }
+    sh[0][threadIdx.x] = e; sh[1][threadIdx.x] = w;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sh[0][0]; out[1] = sh[1][0]; }
+}
+
+}  // namespace vb

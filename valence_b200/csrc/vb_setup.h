@@ -1,0 +1,98 @@
+// Host-side set-up of one VSVB energy evaluation: normalised basis, expanded
+// orbitals, wavefunction entry lists, orbital-pair groups, shell-pair /
+// primitive-pair tables and HRR-folded pair densities for the GPU kernels.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "vb_eri.cuh"
+#include "vb_input.h"
+
+namespace vb {
+
+constexpr double ANGS2BOHR = 1.889725987722;   // /root/reference/src/tools_module.F90:11
+
+struct GShell {
+    int l, atom, nprim, ao_off, prim_off, type_shell;   // type_shell: index into the per-type shell tables
+    double r[3];
+};
+
+struct Basis {
+    std::vector<GShell> shells;
+    std::vector<int> atom_first_shell;          // natom + 1
+    std::vector<double> exps, coefs;            // normalised contraction weights (norm_prim)
+    std::vector<double> angn;                   // per cumulative cartesian index, l <= LMAX_SHELL
+    int nao = 0;
+};
+
+// An orbital expanded over global shells.  c = scattered LCAO weights without
+// the angular factor (what the reference holds in coeffi(:), valence.F90:3221-3237)
+struct OrbShell {
+    int gshell;
+    double c[6];
+};
+struct ExpOrb {
+    std::vector<OrbShell> sh;
+};
+
+// Device-friendly tables ----------------------------------------------------
+struct SPRec {          // one oriented shell pair of a pair group (whole contraction)
+    int type;           // ptype(la, lb)
+    int eoff;           // first [e0| component of this shell pair inside the group's e-space
+    int pp_beg, pp_cnt; // range in the primitive-pair array
+};
+struct Item {           // ket work item: a chunk of one shell pair's primitive pairs
+    int eoff, pp_beg, pp_cnt, pad;
+};
+struct PGDesc {
+    int sp_beg[NPTYPE + 1];     // shell pairs sorted by type
+    int item_beg[NPTYPE + 1];   // items sorted by type
+    long long d_off;            // offset of the folded density block [ne][np]
+    int ne, np;                 // # e-components, # orbital pairs
+    int pair_beg;               // offset into the pair list (s,t)
+    int g, h;                   // entry groups
+    double smax;                // max Schwarz value over the pairs (filled after the diagonal pass)
+};
+
+struct EntryGroup {
+    std::vector<int> entries;   // wavefunction entries (0-based)
+    std::vector<int> shells;    // global shells spanned
+    int nao = 0;
+};
+
+struct Wavefunction {           // bra/ket orbital lists (valence.F90:324-336, 557-605)
+    std::vector<int> bra, ket;  // orbital id per electron slot (0-based ids)
+    int nnd = 0, nso = 0;       // # single-slot entries, # entries
+    bool sym = true;            // bra == ket (ijkl symmetry enabled)
+    int subject = -1;           // entry index of the subject orbital slot (first_order_opt), or -1
+    // entry -> slots
+    int nslots(int s) const { return s < nnd ? 1 : 2; }
+    int slot(int s, int k) const { return s < nnd ? s : 2 * s - nnd + k; }   // 0-based
+};
+
+struct TileSetup {
+    std::vector<EntryGroup> groups;
+    std::vector<PGDesc> pgs;
+    std::vector<int> pg_pairs;      // 2 ints (s,t) per pair
+    std::vector<SPRec> sps;
+    std::vector<Item> items;
+    std::vector<PrimPair> pps;
+    std::vector<double> dmat;       // folded densities, per pair group [e][p]
+    int max_ne = 0, max_np = 0;
+    int lmax = 0;
+};
+
+double dblfac(int n);
+void norm_prim(int l, int n, const double* exps, const double* raw, double* out);   // valence.F90:2264-2305
+Basis build_basis(const Input& in, const std::vector<double>& xyz_bohr);
+double nuclear_repulsion(const Input& in, const std::vector<double>& xyz_bohr);      // tools_module.F90:19-40
+
+// scatter of one orbital's weights over its OBS (valence.F90:2919-2932, ndf2obs :2191-2247)
+ExpOrb expand_orbital(const Input& in, const Basis& bas, const std::vector<std::vector<double>>& coeff, int orb);
+// global shell and component of OBS position `pos` (1-based) of orbital `orb`
+bool obs_position(const Input& in, const Basis& bas, int orb, int pos, int* gshell, int* comp);
+
+void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs2e,
+                 int chunk, TileSetup* out);
+
+}  // namespace vb

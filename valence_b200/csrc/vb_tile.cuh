@@ -1,0 +1,291 @@
+// The fused hot kernel: for one tile (bra pair group P, ket pair group Q)
+//   1. every contracted shell quartet of the AO block (P-support | Q-support) is generated once
+//      (Obara-Saika VRR per angular-momentum class; warp = one bra shell pair, lanes = ket
+//      primitive-pair chunks of one class),
+//   2. half-transformed on the fly with the staged ket pair densities (lanes = ket orbital pairs,
+//      integrals broadcast by warp shuffles), then with the bra pair densities,
+//   3. the resulting orbital-level integrals (st|uv) are screened exactly as the reference
+//      screens them (valence.F90:1189-1190, 1213-1216, 1286-1287) and contracted with the
+//      cofactor densities; nothing but one double per tile reaches HBM.
+#pragma once
+#include "vb_kernels.cuh"
+
+namespace vb {
+
+__device__ __forceinline__ int tri_index(int a, int c) { return a * (a + 1) / 2 + c; }   // a >= c, 0-based
+
+// W(s,t,u,v) = P[s,t] P[u,v] - sum_sigma P^s[s,v] P^s[u,t]   (times c0 outside)
+__device__ __forceinline__ double w_term(const double* __restrict__ Pa, const double* __restrict__ Pb, int nso, int s, int t, int u, int v)
+{
+    double ast = Pa[s * nso + t], bst = Pb[s * nso + t], auv = Pa[u * nso + v], buv = Pb[u * nso + v];
+    double asv = Pa[s * nso + v], bsv = Pb[s * nso + v], aut = Pa[u * nso + t], but = Pb[u * nso + t];
+    return (ast + bst) * (auv + buv) - asv * aut - bsv * but;
+}
+
+template <int TB, int TK>
+__device__ __forceinline__ void eri_batch(const TileArgs& A, const SPRec& sp, const Item& it, bool active,
+                                          const PrimPair* __restrict__ kpps, double* __restrict__ acc)
+{
+    constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
+    const int nq = active ? it.pp_cnt : 0;
+    for (int ip = 0; ip < sp.pp_cnt; ++ip) {
+        const PrimPair a = A.pps[sp.pp_beg + ip];
+        for (int iq = 0; iq < nq; ++iq) {
+            const PrimPair b = kpps[it.pp_beg + iq];
+            QuartetGeom g;
+            double T, pref;
+            quartet_geom(a, b, g, T, pref);
+            double F[M + 1];
+            boys<M>(A.boys, T, F);
+#pragma unroll
+            for (int m = 0; m <= M; ++m) F[m] *= pref;
+            if constexpr (M == 0) acc[0] += F[0];
+            else vrr_unrolled<LA, EA, LC, EC>(g, F, acc);
+        }
+    }
+}
+
+// first half transformation: H[e] (lane = ket orbital pair q) += sum_src sum_f acc_src[e][f] * Dq[(eoff_src+f)][q]
+template <int NE, int NF>
+__device__ __forceinline__ void half_transform(const double* __restrict__ acc, int eoff, int cnt, int lane, int npq,
+                                               const double* __restrict__ Dq, double* __restrict__ H)
+{
+    for (int src = 0; src < cnt; ++src) {
+        const int eo = __shfl_sync(0xffffffffu, eoff, src);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const double dq = (lane < npq) ? Dq[(eo + f) * npq + lane] : 0.0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double v = __shfl_sync(0xffffffffu, acc[e * NF + f], src);
+                H[e] += v * dq;
+            }
+        }
+    }
+}
+
+template <int TB, int TK>
+__device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& sp, const PGDesc& Q, int base, int nit, int lane,
+                                               const PrimPair* __restrict__ kpps, const double* __restrict__ Dq, double* __restrict__ H)
+{
+    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    double acc[NE * NF];
+#pragma unroll
+    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+    const bool active = base + lane < nit;
+    Item it = {0, 0, 0, 0};
+    if (active) it = A.items[Q.item_beg[TK] + base + lane];
+    eri_batch<TB, TK>(A, sp, it, active, kpps, acc);
+    half_transform<NE, NF>(acc, it.eoff, min(32, nit - base), lane, Q.np, Dq, H);
+}
+
+// generic path (any class with a d shell): runtime loops, scratch in global memory
+__device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, const SPRec& sp, const PGDesc& Q, int base, int nit,
+                                           int lane, const PrimPair* __restrict__ kpps, const double* __restrict__ Dq,
+                                           double* __restrict__ H, double* __restrict__ scratch)
+{
+    const int LA = pt_la(tb), EA = pt_E(tb), LC = pt_la(tk), EC = pt_E(tk), M = EA + EC;
+    const int NE = pt_ne(tb), NF = pt_ne(tk);
+    double* T = scratch;                       // GEN_SCRATCH
+    double* acc = scratch + GEN_SCRATCH;       // up to 31*31
+    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+    const bool active = base + lane < nit;
+    Item it = {0, 0, 0, 0};
+    if (active) it = A.items[Q.item_beg[tk] + base + lane];
+    const int nq = active ? it.pp_cnt : 0;
+    for (int ip = 0; ip < sp.pp_cnt; ++ip) {
+        const PrimPair a = A.pps[sp.pp_beg + ip];
+        for (int iq = 0; iq < nq; ++iq) {
+            const PrimPair b = kpps[it.pp_beg + iq];
+            QuartetGeom g;
+            double Tt, pref, F[MTOP + 1];
+            quartet_geom(a, b, g, Tt, pref);
+            boys_rt(M, A.boys, Tt, F);
+            for (int m = 0; m <= M; ++m) F[m] *= pref;
+            vrr_generic(LA, EA, LC, EC, g, F, T, acc);
+        }
+    }
+    const int cnt = min(32, nit - base);
+    for (int src = 0; src < cnt; ++src) {
+        const int eo = __shfl_sync(0xffffffffu, it.eoff, src);
+        for (int f = 0; f < NF; ++f) {
+            const double dq = (lane < Q.np) ? Dq[(eo + f) * Q.np + lane] : 0.0;
+            for (int e = 0; e < NE; ++e) {
+                const double v = __shfl_sync(0xffffffffu, acc[e * NF + f], src);
+                H[e] += v * dq;
+            }
+        }
+    }
+}
+
+constexpr int TILE_THREADS = 256;
+constexpr int HMAX_UNR = 9;                      // pt_ne(pp)
+constexpr int HMAX_GEN = 31;                     // pt_ne(dd)
+constexpr int GEN_PER_THREAD = GEN_SCRATCH + HMAX_GEN * HMAX_GEN;
+
+template <bool GEN>
+__global__ void __launch_bounds__(TILE_THREADS) k_tile(const TileArgs A)
+{
+    extern __shared__ double smem[];
+    double* Dq = smem;                            // [Q.ne][Q.np]
+    double* Gt = smem + A.dq_cap;                 // [32][32]
+    __shared__ int s_tile;
+    __shared__ double s_red[TILE_THREADS / 32];
+    __shared__ unsigned long long s_cnt[CNT_N];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = TILE_THREADS / 32;
+    constexpr int HM = GEN ? HMAX_GEN : HMAX_UNR;
+    double* scratch = nullptr;
+    if constexpr (GEN) scratch = A.gen_scratch + ((size_t)blockIdx.x * TILE_THREADS + tid) * GEN_PER_THREAD;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
+        if (tid < CNT_N) s_cnt[tid] = 0ull;
+        __syncthreads();
+        const long long tl = (long long)A.tile_first + (long long)s_tile * A.tile_stride;
+        if (tl >= A.ntiles) break;
+        const int2 tq = A.tiles[tl];
+        const PGDesc P = A.pgs[tq.x];
+        const PGDesc Q = A.pgs[tq.y];
+        for (int i = tid; i < Q.ne * Q.np; i += TILE_THREADS) Dq[i] = A.dmat[Q.d_off + i];
+        for (int i = tid; i < 32 * 32; i += TILE_THREADS) Gt[i] = 0.0;
+        __syncthreads();
+
+        const int nsp = P.sp_beg[NPTYPE] - P.sp_beg[0];
+        for (int isp = warp; isp < nsp; isp += nw) {
+            const SPRec sp = A.sps[P.sp_beg[0] + isp];
+            double H[HM];
+#pragma unroll
+            for (int e = 0; e < HM; ++e) H[e] = 0.0;
+            for (int tk = 0; tk < (GEN ? NPTYPE : 3); ++tk) {
+                const int nit = Q.item_beg[tk + 1] - Q.item_beg[tk];
+                for (int base = 0; base < nit; base += 32) {
+                    const int cls = sp.type * NPTYPE + tk;
+                    switch (cls) {
+#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, Q, base, nit, lane, A.pps, Dq, H); break;
+                        VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
+                        VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
+                        VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
+#undef VB_CASE
+                        default:
+                            if constexpr (GEN) batch_generic(A, sp.type, tk, sp, Q, base, nit, lane, A.pps, Dq, H, scratch);
+                            break;
+                    }
+                }
+            }
+            // second half transformation: G[p][q] += sum_e Dp[eoff+e][p] H[e]
+            if (lane < Q.np) {
+                const double* Dp = A.dmat + P.d_off + (size_t)sp.eoff * P.np;
+                const int ne = pt_ne(sp.type);
+                for (int p = 0; p < P.np; ++p) {
+                    double g = 0.0;
+#pragma unroll
+                    for (int e = 0; e < HM; ++e)
+                        if (e < ne) g += Dp[e * P.np + p] * H[e];
+                    atomicAdd(&Gt[p * 32 + lane], g);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- contraction with the cofactor densities --------------------------------------
+        double epart = 0.0;
+        unsigned long long cnt[CNT_N];
+#pragma unroll
+        for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
+        const bool diag_tile = tq.x == tq.y;
+        const int nso = A.nso;
+        for (int idx = tid; idx < P.np * Q.np; idx += TILE_THREADS) {
+            const int p = idx / Q.np, q = idx % Q.np;
+            if (diag_tile && q > p) continue;
+            const double G = Gt[p * 32 + q];
+            const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
+            const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
+            if (A.mode == 0) {
+                if (diag_tile && p == q) {
+                    A.diag[(size_t)s * nso + t] = G;
+                    if (A.sym) A.diag[(size_t)t * nso + s] = G;
+                }
+                continue;
+            }
+            if (A.mode == 2) {
+                const int i1 = A.pair_index[s * nso + t], i2 = A.pair_index[u * nso + v];
+                A.gfull[(size_t)i1 * A.npairs_total + i2] = G;
+                A.gfull[(size_t)i2 * A.npairs_total + i1] = G;
+                if (A.sym) {
+                    const int j1 = A.pair_index[t * nso + s], j2 = A.pair_index[v * nso + u];
+                    A.gfull[(size_t)j1 * A.npairs_total + i2] = G; A.gfull[(size_t)i2 * A.npairs_total + j1] = G;
+                    A.gfull[(size_t)i1 * A.npairs_total + j2] = G; A.gfull[(size_t)j2 * A.npairs_total + i1] = G;
+                    A.gfull[(size_t)j1 * A.npairs_total + j2] = G; A.gfull[(size_t)j2 * A.npairs_total + j1] = G;
+                }
+                continue;
+            }
+            // reference screens: Schwarz product, then the value itself
+            const double sprod = A.sch[s * nso + t] * A.sch[u * nso + v];
+            const bool ssig = sprod > A.itol;
+            // images of (s,t,u,v) under the integral's permutational symmetry
+            int im[8][4];
+            int nim = 0;
+            {
+                const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
+                for (int k = 0; k < 2; ++k) {
+                    const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
+                    im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
+                    if (A.sym) {
+                        im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
+                        im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
+                        im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
+                    }
+                }
+            }
+            double wsum = 0.0;
+            int stab = 0;
+            cnt[CNT_ENTRIES]++;
+            for (int k = 0; k < nim; ++k) {
+                const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
+                if (a == s && b == t && c == u && d == v) ++stab;
+                bool dup = false;
+                for (int k2 = 0; k2 < k; ++k2)
+                    dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
+                if (dup) continue;
+                // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
+                const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
+                const double val = shortcut ? A.sch[a * nso + b] * A.sch[a * nso + b] : G;
+                const bool vsig = ssig && fabs(val) > A.itol;
+                // as the direct integral of task io=a, ko=b, jo=c, lo=d
+                bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+                if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
+                // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
+                bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+                if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
+                if (vd) { cnt[CNT_SCHWARZ_EREP] += ssig; cnt[CNT_VALUE_EREP] += vsig; }
+                if (vx) { cnt[CNT_SCHWARZ_EXCH] += ssig; cnt[CNT_VALUE_EXCH] += vsig; }
+                if (ssig && !shortcut) {
+                    const int calls = (vd ? 1 : 0) + ((vx && b != d) ? 1 : 0);
+                    cnt[CNT_INT2E] += calls;
+                    cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
+                }
+                if (ssig && shortcut && vd) cnt[CNT_SHORTCUT]++;
+                if (vsig) wsum += val * w_term(A.Pa, A.Pb, nso, a, b, c, d);
+            }
+            (void)stab;
+            epart += 0.5 * wsum;
+        }
+        if (A.mode == 1) {
+            // deterministic block reduction of the tile's energy
+            for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
+            if (lane == 0) s_red[warp] = epart;
+            for (int i = 0; i < CNT_N; ++i)
+                if (cnt[i]) atomicAdd(&s_cnt[i], cnt[i]);
+            __syncthreads();
+            if (tid == 0) {
+                double e = 0.0;
+                for (int w = 0; w < nw; ++w) e += s_red[w];
+                A.tileE[tl] = e * A.c0;
+            }
+            if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
+        }
+    }
+}
+
+}  // namespace vb
