@@ -74,6 +74,7 @@ def load(build_if_needed: bool = True):
     L.vb_engine_accum_len.argtypes = [C.c_void_p]
     L.vb_engine_stream.restype = C.c_void_p
     L.vb_engine_stream.argtypes = [C.c_void_p]
+    L.vb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -158,3 +159,12 @@ class Engine:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize(self.device)
         return self.energy_finish(r)
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    """Measured FP64 FMA peak (TFLOP/s) of one GPU: the ERI kernel's roofline denominator."""
+    L = load()
+    v = C.c_double(0.0)
+    if L.vb_measure_fp64_peak(device, C.byref(v)) != 0:
+        raise RuntimeError(L.vb_last_error().decode())
+    return v.value

@@ -154,6 +154,11 @@ double* vb_engine_accum_device(const vb_engine* e) { return e->eng->accum_device
 int vb_engine_accum_len(const vb_engine* e) { return e->eng->accum_len(); }
 void* vb_engine_stream(const vb_engine* e) { return e->eng->stream(); }
 
+int vb_measure_fp64_peak(int device, double* tflops)
+{
+    return guarded([&] { *tflops = vb::measure_fp64_peak_tflops(device); });
+}
+
 /* ---- reference-compatible layer ------------------------------------------------------------- */
 void valence_api_initialize_(int* info, int* call_mpi_init, int* comm)
 {
