@@ -60,6 +60,7 @@ def lib():
         L.vo_set_memo.argtypes = [C.c_void_p, C.c_int]
         L.vo_set_coords.argtypes = [C.c_void_p, C.c_void_p]
         L.vo_reset_orbitals.argtypes = [C.c_void_p]
+        L.vo_guess_partial.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3
         L.vo_baseline_sample.restype = C.c_longlong
         L.vo_baseline_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_double)]
         for f in ("vo_nelec", "vo_natom", "vo_norbs", "vo_npairs_schwarz"):
@@ -144,6 +145,11 @@ class Oracle:
     def set_coords(self, x_angstrom):
         x = np.ascontiguousarray(x_angstrom, dtype=np.float64).ravel()
         self.L.vo_set_coords(self.h, x.ctypes.data)
+
+    def guess_partial(self, irank: int, nrank: int):
+        e, w, n = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+        self.L.vo_guess_partial(self.h, irank, nrank, C.byref(e), C.byref(w), C.byref(n))
+        return e.value, w.value, n.value
 
     def baseline_sample(self, irank: int, nrank: int, task_limit: int):
         e = C.c_double(0.0)

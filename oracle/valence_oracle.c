@@ -1216,6 +1216,20 @@ int vo_guess_energy(vo_ctx *c, int nrank, vo_result *out)
     return 0;
 }
 
+/* one rank's partial sums of guess_energy under the reference's round-robin decomposition
+ * (task = irank, irank + nrank, ...; valence.F90:1089,1162-1163); the caller sums over ranks
+ * (xm_equalize_scalar) and forms energy/wfnorm + enucrep. */
+int vo_guess_partial(vo_ctx *c, int irank, int nrank, double *energy, double *wfnorm, double *enucrep)
+{
+    setup_energy(c);
+    memset(&c->cnt, 0, sizeof c->cnt);
+    c->nrank = nrank; c->irank = irank;
+    guess_partial(c, energy, wfnorm);
+    c->nrank = 1; c->irank = 0;
+    *enucrep = c->enucrep;
+    return 0;
+}
+
 /* one rank's share of the 2e loop only, for the timed CPU baseline:
  * returns shell quartets evaluated (simint_compute_eri-equivalent calls) */
 long long vo_baseline_sample(vo_ctx *c, int irank, int nrank, long long task_limit, double *energy_partial)

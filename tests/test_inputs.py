@@ -1,0 +1,56 @@
+"""Input reader / writer (host logic): record-based list-directed semantics of
+/root/reference/src/xm_module.F90:25-335, exercised on the committed fixtures."""
+import pytest
+
+from conftest import golden_names, load_golden
+from valence_b200 import inputs
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_write_parse_roundtrip(name):
+    inp, _ = load_golden(name)
+    again = inputs.parse(inputs.write(inp))
+    assert again.to_json() == inp.to_json()
+
+
+def test_header_counts_consistent():
+    for name in golden_names():
+        inp, _ = load_golden(name)
+        assert len(inp.orbitals) == inp.norbs
+        assert len(inp.atom_t) == inp.natom and len(inp.types) == inp.natom_t
+        assert sum(len(t.shells) for t in inp.types) <= inp.num_sh
+
+
+def test_record_semantics_discard_rest_of_line_and_d_exponents():
+    # 16th integer on the header record, prose after the control record, D exponents, commas,
+    # a READ spanning records, and trailing free text are all legal
+    text = """1 1 0 1 0 1 1 0 1 1 0 0 0 0 1 300
+    20 20 20 0 0 0 0.0D0 0.0 ignored words
+    1 0.0 0.0, 0.0
+    1.0 1
+    0 1
+    0.5D+00
+    1 1
+    1
+    1 1.0
+    free text after the last orbital 1 2 3
+    """
+    inp = inputs.parse(text)
+    assert inp.natom == 1 and inp.nunpd == 1 and inp.types[0].shells[0].exps == [0.5]
+    assert inp.orbitals[0].atoms == [1] and inp.orbitals[0].terms == [(1, 1.0)]
+
+
+def test_truncated_input_raises():
+    with pytest.raises(EOFError):
+        inputs.parse("1 1 0 1 0 2 2 0 1 1 0 0 0 0 1\n20 20 20 0 0 0 0 0\n1 0 0 0\n")
+
+
+@pytest.mark.parametrize("n", [1, 2, 16])
+def test_water_cluster_generator(n):
+    inp = inputs.water_cluster(n)
+    assert inp.natom == 3 * n and inp.ndocc == 5 * n and inp.nelec == 10 * n
+    assert inp.num_sh == 7 and inp.num_pr == 18 and inp.nang == 1
+    again = inputs.parse(inputs.write(inp))
+    assert again.to_json() == inp.to_json()
+    sc = inputs.water_cluster(n, sc_molecules=1)
+    assert sc.npair == 2 and sc.ndocc == 5 * n - 2 and sc.nelec == 10 * n

@@ -7,6 +7,7 @@
 #include <array>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -102,12 +103,13 @@ struct Engine::Impl {
     DBuf<int2> opairs, tiles;
     DBuf<PGDesc> pgs;
     DBuf<SPRec> sps;
-    DBuf<Item> items;
-    DBuf<PrimPair> pps;
+        DBuf<PrimPair> pps;
     DBuf<unsigned int> counter;
-    DBuf<unsigned long long> counters;
+    DBuf<unsigned long long> counters, pq_counters;
+    DBuf<int> pp_eoff;
     // state carried from energy_partial to energy_finish
     double enuc = 0, e1 = 0, wfnorm = 0;
+    double tau = 1e-22;   // primitive-quartet magnitude cut; VB_PRIM_TAU overrides
     int launches = 0;
     double t_begin = 0;
 };
@@ -131,6 +133,7 @@ Engine::Engine(const Input& in, int device) : in_(in), impl_(new Impl)
     boys_make_table(tab.data());
     I.boys.upload(tab, I.st);
     I.xyz_angs = in.coords;
+    if (const char* t = std::getenv("VB_PRIM_TAU")) I.tau = std::atof(t);
     reset_orbitals();
     I.accum.alloc(1 + CNT_N);
     CK(cudaStreamSynchronize(I.st));
@@ -326,20 +329,23 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
 
     // ---- pair groups, shell-pair tables, folded densities ------------------------------------
     TileSetup ts;
-    build_tiles(in, bas, wf, orbs2e, /*chunk=*/6, &ts);
+    // magnitude cuts: the Schwarz (diagonal) pass must resolve (st|st) down to itol^2, the energy pass
+    // needs the integrals to ~itol; never looser than the configured tau
+    const double tau_diag = std::min(I.tau, 0.01 * itol * itol), tau_energy = std::min(I.tau, 0.01 * itol);
+    build_tiles(in, bas, wf, orbs2e, tau_diag, &ts);
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
-    const size_t smem = ((size_t)dq_cap + 32 * 32) * sizeof(double);
-    if (smem > 200 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+    const size_t smem = ((size_t)dq_cap + (TILE_THREADS / 32) * 32 * 32) * sizeof(double);
+    if (smem > 220 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
     for (int s = 0; s < nso; ++s) {
         nshb[s] = (int)orbs2e[wf.bra[wf.slot(s, 0)]].sh.size();
         nshk[s] = (int)orbs2e[wf.ket[wf.slot(s, 0)]].sh.size();
     }
-    I.pgs.upload(ts.pgs, st); I.pg_pairs.upload(ts.pg_pairs, st); I.sps.upload(ts.sps, st); I.items.upload(ts.items, st);
+    I.pgs.upload(ts.pgs, st); I.pg_pairs.upload(ts.pg_pairs, st); I.sps.upload(ts.sps, st); I.pp_eoff.upload(ts.pp_eoff, st);
     I.pps.upload(ts.pps, st); I.dmat.upload(ts.dmat, st); I.nsh_bra.upload(nshb, st); I.nsh_ket.upload(nshk, st);
-    I.counter.alloc(1); I.counters.alloc(CNT_N);
+    I.counter.alloc(1); I.counters.alloc(CNT_N); I.pq_counters.alloc(NPTYPE * NPTYPE);
     const bool gen = ts.lmax >= 2;
     int grid_cap = I.nsm * 2;
     if (gen) { grid_cap = std::min(grid_cap, 64); I.gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
@@ -348,7 +354,7 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
-    A.pgs = I.pgs.p; A.pg_pairs = I.pg_pairs.p; A.sps = I.sps.p; A.items = I.items.p; A.pps = I.pps.p; A.dmat = I.dmat.p;
+    A.pgs = I.pgs.p; A.pg_pairs = I.pg_pairs.p; A.sps = I.sps.p; A.pps = I.pps.p; A.pp_eoff = I.pp_eoff.p; A.tau = tau_diag; A.pq_counters = I.pq_counters.p; A.dmat = I.dmat.p;
     A.boys = I.boys.p; A.counter = I.counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = -1;
     A.dq_cap = dq_cap; A.itol = itol; A.Pa = I.Pa.p; A.Pb = I.Pb.p; A.c0 = c0; A.nsh_bra = I.nsh_bra.p; A.nsh_ket = I.nsh_ket.p;
     A.counters = I.counters.p; A.gen_scratch = I.gen_scratch.p;
@@ -401,42 +407,15 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
         }
     }
     const long long ntiles = (long long)tiles.size();
-    // workload statistics for this rank's shard
-    {
-        std::vector<double> F(NPTYPE * NPTYPE);
-        for (int a = 0; a < NPTYPE; ++a) for (int b = 0; b < NPTYPE; ++b) F[a * NPTYPE + b] = flops_prim_quartet(a, b);
-        std::vector<std::array<long long, NPTYPE>> npp(npg), nsp(npg), nit(npg);
-        for (int g = 0; g < npg; ++g)
-            for (int t = 0; t < NPTYPE; ++t) {
-                nsp[g][t] = ts.pgs[g].sp_beg[t + 1] - ts.pgs[g].sp_beg[t];
-                nit[g][t] = ts.pgs[g].item_beg[t + 1] - ts.pgs[g].item_beg[t];
-                long long n = 0;
-                for (int k = ts.pgs[g].sp_beg[t]; k < ts.pgs[g].sp_beg[t + 1]; ++k) n += ts.sps[k].pp_cnt;
-                npp[g][t] = n;
-            }
-        double fl = 0.0;
-        long long aoq = 0, pq = 0, mine = 0;
-        for (long long k = rank; k < ntiles; k += nranks) {
-            const int P = tiles[k].x, Q = tiles[k].y;
-            ++mine;
-            for (int a = 0; a < NPTYPE; ++a)
-                for (int b = 0; b < NPTYPE; ++b) {
-                    aoq += nsp[P][a] * nsp[Q][b];
-                    pq += npp[P][a] * npp[Q][b];
-                    fl += (double)npp[P][a] * npp[Q][b] * F[a * NPTYPE + b];
-                    fl += (double)nsp[P][a] * nit[Q][b] * pt_ne(a) * pt_ne(b) * 2.0 * ts.pgs[Q].np;   // first half transform
-                }
-            fl += 2.0 * ts.pgs[P].ne * ts.pgs[P].np * ts.pgs[Q].np;                                   // second half transform
-        }
-        out->n_ao_quartets = aoq; out->n_prim_quartets = pq; out->flops_model = fl; out->n_tiles_mine = mine;
-    }
+    out->n_tiles_mine = 0;
+    for (long long k = rank; k < ntiles; k += nranks) out->n_tiles_mine++;
     double t4 = now_ms();
     // ---- energy pass ---------------------------------------------------------------------------
     I.sch.upload(sch, st);
     I.tiles.upload(tiles, st);
     I.tileE.alloc((size_t)std::max<long long>(ntiles, 1));
-    I.tileE.zero(st); I.counter.zero(st); I.counters.zero(st);
-    A.tiles = I.tiles.p; A.ntiles = (int)ntiles; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1;
+    I.tileE.zero(st); I.counter.zero(st); I.counters.zero(st); I.pq_counters.zero(st);
+    A.tiles = I.tiles.p; A.ntiles = (int)ntiles; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
     A.sch = I.sch.p; A.tileE = I.tileE.p;
     CK(cudaEventRecord(I.ev2, st));
     if (out->n_tiles_mine > 0) launch((int)out->n_tiles_mine);
@@ -449,6 +428,17 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
         // counters -> accumulator tail as doubles (exact below 2^53), one tiny kernel-free copy via host
         std::vector<unsigned long long> c;
         I.counters.download(c, st);
+        // executed primitive quartets per class -> algorithmic flop count of this rank's tile pass
+        std::vector<unsigned long long> pq;
+        I.pq_counters.download(pq, st);
+        double fl = 0.0;
+        long long npq = 0;
+        for (int a = 0; a < NPTYPE; ++a)
+            for (int b = 0; b < NPTYPE; ++b) {
+                fl += (double)pq[a * NPTYPE + b] * flops_prim_quartet(a, b);
+                npq += (long long)pq[a * NPTYPE + b];
+            }
+        out->flops_model = fl; out->n_prim_quartets = npq;
         std::vector<double> cd(CNT_N);
         for (int i = 0; i < CNT_N; ++i) cd[i] = (double)c[i];
         CK(cudaMemcpyAsync(I.accum.p + 1, cd.data(), CNT_N * sizeof(double), cudaMemcpyHostToDevice, st));

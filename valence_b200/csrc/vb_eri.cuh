@@ -14,6 +14,7 @@
 #define VB_HD __host__ __device__ __forceinline__
 #else
 #define VB_HD inline
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 #endif
 
 namespace vb {
@@ -62,8 +63,8 @@ VB_HD constexpr int pt_ne(int t) { return ncum(pt_E(t)) - coff(pt_la(t)); }     
 // ---------------------------------------------------------------------------
 constexpr int BOYS_COLS = 16;                 // MTOP + 8
 constexpr double BOYS_STEP = 1.0 / 16.0;
-constexpr double BOYS_TMAX = 36.0;
-constexpr int BOYS_ROWS = 36 * 16 + 1;
+constexpr double BOYS_TMAX = 64.0;              // beyond: exp(-T) < 2e-28, pure asymptotic series
+constexpr int BOYS_ROWS = 64 * 16 + 1;
 
 inline void boys_reference(int mmax, double T, double* F)   // host: exact series / erf
 {
@@ -88,35 +89,39 @@ inline void boys_make_table(double* tab)   // BOYS_ROWS * BOYS_COLS doubles
     for (int k = 0; k < BOYS_ROWS; ++k) boys_reference(BOYS_COLS - 1, k * BOYS_STEP, tab + (size_t)k * BOYS_COLS);
 }
 
+VB_HD double boys_taylor(const double* __restrict__ r, double d)   // sum_j r[j] d^j / j!, j < 8
+{
+    double f = r[7] * (1.0 / 5040.0);
+    f = f * d + r[6] * (1.0 / 720.0);
+    f = f * d + r[5] * (1.0 / 120.0);
+    f = f * d + r[4] * (1.0 / 24.0);
+    f = f * d + r[3] * (1.0 / 6.0);
+    f = f * d + r[2] * 0.5;
+    f = f * d + r[1];
+    return f * d + r[0];
+}
+
 template <int M>
 VB_HD void boys(const double* __restrict__ tab, double T, double* F)   // F[0..M]
 {
     if (T < BOYS_TMAX) {
         int k = (int)(T * (1.0 / BOYS_STEP) + 0.5);
         double d = k * BOYS_STEP - T;                 // F_m(T) = sum_j F_{m+j}(T_k) d^j / j!
-        const double* r = tab + (size_t)k * BOYS_COLS + M;
-        double f = r[7] * (1.0 / 5040.0);
-        f = f * d + r[6] * (1.0 / 720.0);
-        f = f * d + r[5] * (1.0 / 120.0);
-        f = f * d + r[4] * (1.0 / 24.0);
-        f = f * d + r[3] * (1.0 / 6.0);
-        f = f * d + r[2] * 0.5;
-        f = f * d + r[1];
-        f = f * d + r[0];
-        F[M] = f;
-        if (M > 0) {
+        const double* r = tab + (size_t)k * BOYS_COLS;
+        if constexpr (M <= 2) {                       // low orders: one Taylor series each, no exp
+#pragma unroll
+            for (int m = 0; m <= M; ++m) F[m] = boys_taylor(r + m, d);
+        } else {
+            F[M] = boys_taylor(r + M, d);
             double eT = exp(-T), t2 = 2.0 * T;
 #pragma unroll
             for (int m = M; m > 0; --m) F[m - 1] = (t2 * F[m] + eT) * (1.0 / (2.0 * m - 1.0));
         }
     } else {
-        double rt = 1.0 / T;
-        F[0] = 0.5 * sqrt(PI * rt);
-        if (M > 0) {
-            double eT = exp(-T), h = 0.5 * rt;
+        double r = rsqrt(T), rt = r * r;
+        F[0] = 0.88622692545275801365 * r;            // sqrt(pi)/2 / sqrt(T)
 #pragma unroll
-            for (int m = 0; m < M; ++m) F[m + 1] = ((2.0 * m + 1.0) * F[m] - eT) * h;
-        }
+        for (int m = 0; m < M; ++m) F[m + 1] = (m + 0.5) * F[m] * rt;
     }
 }
 
@@ -125,33 +130,26 @@ VB_HD void boys_rt(int M, const double* __restrict__ tab, double T, double* F)  
     if (T < BOYS_TMAX) {
         int k = (int)(T * (1.0 / BOYS_STEP) + 0.5);
         double d = k * BOYS_STEP - T;
-        const double* r = tab + (size_t)k * BOYS_COLS + M;
-        double f = r[7] * (1.0 / 5040.0);
-        f = f * d + r[6] * (1.0 / 720.0);
-        f = f * d + r[5] * (1.0 / 120.0);
-        f = f * d + r[4] * (1.0 / 24.0);
-        f = f * d + r[3] * (1.0 / 6.0);
-        f = f * d + r[2] * 0.5;
-        f = f * d + r[1];
-        f = f * d + r[0];
-        F[M] = f;
+        F[M] = boys_taylor(tab + (size_t)k * BOYS_COLS + M, d);
         double eT = exp(-T), t2 = 2.0 * T;
         for (int m = M; m > 0; --m) F[m - 1] = (t2 * F[m] + eT) / (2.0 * m - 1.0);
     } else {
-        double rt = 1.0 / T, eT = exp(-T), h = 0.5 * rt;
-        F[0] = 0.5 * sqrt(PI * rt);
-        for (int m = 0; m < M; ++m) F[m + 1] = ((2.0 * m + 1.0) * F[m] - eT) * h;
+        double r = 1.0 / sqrt(T), rt = r * r;
+        F[0] = 0.88622692545275801365 * r;
+        for (int m = 0; m < M; ++m) F[m + 1] = (m + 0.5) * F[m] * rt;
     }
 }
 
 // ---------------------------------------------------------------------------
 // primitive shell-pair record (64 bytes, staged through shared memory)
 // ---------------------------------------------------------------------------
-struct alignas(16) PrimPair {
+struct alignas(16) PrimPair {   // 80 bytes
     double Px, Py, Pz;     // Gaussian product centre
     double p;              // a + b
-    double K;              // c_a c_b exp(-ab/p |AB|^2) * sqrt(2) pi^(5/4)
+    double ip;             // 1 / p
+    double Kp;             // c_a c_b exp(-ab/p |AB|^2) * sqrt(2) pi^(5/4) / p
     double PAx, PAy, PAz;  // P - A, A = centre carrying the angular momentum (la >= lb)
+    double w;              // magnitude bound used to skip negligible primitive quartets
 };
 
 struct QuartetGeom {       // everything the VRR needs for one primitive quartet
@@ -268,22 +266,21 @@ VB_HD void vrr_generic(int LA, int EA, int LC, int EC, const QuartetGeom& g, con
 #undef TT
 }
 
-// geometry of one primitive quartet; returns T = rho |PQ|^2 and the prefactor
+// geometry of one primitive quartet; returns T = rho |PQ|^2 and the prefactor K_a K_b / (p q sqrt(p+q)).
+// Division-free: one rsqrt.
 VB_HD void quartet_geom(const PrimPair& a, const PrimPair& b, QuartetGeom& g, double& T, double& pref)
 {
-    double p = a.p, q = b.p, pq = p + q, ipq = 1.0 / pq;
-    double rho = p * q * ipq;
-    double dx = a.Px - b.Px, dy = a.Py - b.Py, dz = a.Pz - b.Pz;
-    T = rho * (dx * dx + dy * dy + dz * dz);
-    pref = a.K * b.K * sqrt(ipq) / (p * q);                    // K_a K_b / (p q sqrt(p+q))
-    (void)rho;
-    // W - P = -(q/(p+q)) (P-Q),  W - Q = (p/(p+q)) (P-Q)
-    double wq = q * ipq, wp = p * ipq;
+    const double p = a.p, q = b.p;
+    const double r = rsqrt(p + q), ipq = r * r;
+    const double wq = q * ipq, wp = p * ipq;             // rho/p, rho/q
+    const double dx = a.Px - b.Px, dy = a.Py - b.Py, dz = a.Pz - b.Pz;
+    T = p * wq * (dx * dx + dy * dy + dz * dz);
+    pref = a.Kp * b.Kp * r;
     g.PA[0] = a.PAx; g.PA[1] = a.PAy; g.PA[2] = a.PAz;
     g.QC[0] = b.PAx; g.QC[1] = b.PAy; g.QC[2] = b.PAz;
-    g.WP[0] = -wq * dx; g.WP[1] = -wq * dy; g.WP[2] = -wq * dz;
-    g.WQ[0] = wp * dx; g.WQ[1] = wp * dy; g.WQ[2] = wp * dz;
-    g.h2p = 0.5 / p; g.h2q = 0.5 / q; g.h2pq = 0.5 * ipq; g.rp = wq; g.rq = wp;
+    g.WP[0] = -wq * dx; g.WP[1] = -wq * dy; g.WP[2] = -wq * dz;   // W - P
+    g.WQ[0] = wp * dx; g.WQ[1] = wp * dy; g.WQ[2] = wp * dz;      // W - Q
+    g.h2p = 0.5 * a.ip; g.h2q = 0.5 * b.ip; g.h2pq = 0.5 * ipq; g.rp = wq; g.rq = wp;
 }
 
 }  // namespace vb

@@ -30,8 +30,10 @@ struct TileArgs {
     const PGDesc* pgs;
     const int* pg_pairs;
     const SPRec* sps;
-    const Item* items;
     const PrimPair* pps;
+    const int* pp_eoff;
+    double tau;                      // primitive-quartet magnitude cut (0 = none)
+    unsigned long long* pq_counters; // primitive quartets evaluated, per class tb*NPTYPE+tk
     const double* dmat;
     const double* boys;
     const int2* tiles;

@@ -200,7 +200,7 @@ static const OrbShell* find_shell(const ExpOrb& o, int gshell)
 }
 
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs,
-                 int chunk, TileSetup* out)
+                 double tau, TileSetup* out)
 {
     (void)in;
     TileSetup& ts = *out;
@@ -245,82 +245,48 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
     }
     // --- pair groups --------------------------------------------------------
     const double SQ2PI54 = std::sqrt(2.0) * std::pow(PI, 1.25);
-    const double KTHR = 1e-30;
     const int ng = (int)ts.groups.size();
+    struct TmpSP {
+        int type, A, B;
+        bool swapped;
+        double wmax;
+        std::vector<PrimPair> pp;
+        std::vector<double> dt;   // folded density [nE][np]
+    };
     std::vector<double> dcart(36), dfold(64);
-    for (int g = 0; g < ng; ++g) {
-        for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h) {
-            const EntryGroup& G = ts.groups[g];
-            const EntryGroup& H = ts.groups[h];
-            // orbital pairs of this group
-            std::vector<int> pairs;
-            for (int s : G.entries)
-                for (int t : H.entries) {
-                    if (wf.sym && g == h && t > s) continue;
-                    pairs.push_back(s);
-                    pairs.push_back(t);
-                }
-            const int np = (int)pairs.size() / 2;
-            if (np == 0) continue;
-            // oriented shell pairs with their primitive pairs
-            struct TmpSP { int type, A, B, pp_beg, pp_cnt; bool swapped; };
-            std::vector<TmpSP> tsp;
-            size_t pp_mark = ts.pps.size();
-            for (int X : G.shells)
-                for (int Y : H.shells) {
-                    bool sw = bas.shells[X].l < bas.shells[Y].l;
-                    int A = sw ? Y : X, B = sw ? X : Y;
-                    const GShell& sa = bas.shells[A];
-                    const GShell& sb = bas.shells[B];
-                    double AB2 = 0.0;
-                    for (int d = 0; d < 3; ++d) AB2 += (sa.r[d] - sb.r[d]) * (sa.r[d] - sb.r[d]);
-                    int beg = (int)ts.pps.size();
-                    for (int ia = 0; ia < sa.nprim; ++ia)
-                        for (int ib = 0; ib < sb.nprim; ++ib) {
-                            double a = bas.exps[sa.prim_off + ia], b = bas.exps[sb.prim_off + ib], p = a + b;
-                            double K = bas.coefs[sa.prim_off + ia] * bas.coefs[sb.prim_off + ib] * std::exp(-a * b / p * AB2) * SQ2PI54;
-                            if (!(std::fabs(K) > KTHR)) continue;
-                            PrimPair pp;
-                            pp.Px = (a * sa.r[0] + b * sb.r[0]) / p;
-                            pp.Py = (a * sa.r[1] + b * sb.r[1]) / p;
-                            pp.Pz = (a * sa.r[2] + b * sb.r[2]) / p;
-                            pp.p = p;
-                            pp.K = K;
-                            pp.PAx = pp.Px - sa.r[0]; pp.PAy = pp.Py - sa.r[1]; pp.PAz = pp.Pz - sa.r[2];
-                            ts.pps.push_back(pp);
-                        }
-                    int cnt = (int)ts.pps.size() - beg;
-                    if (cnt == 0) continue;
-                    tsp.push_back({ptype(sa.l, sb.l), A, B, beg, cnt, sw});
-                }
-            if (tsp.empty()) { ts.pps.resize(pp_mark); continue; }
-            std::stable_sort(tsp.begin(), tsp.end(), [](const TmpSP& a, const TmpSP& b) { return a.type < b.type; });
-            PGDesc pg;
-            std::memset(&pg, 0, sizeof pg);
-            pg.g = g; pg.h = h; pg.np = np; pg.pair_beg = (int)ts.pg_pairs.size() / 2;
-            ts.pg_pairs.insert(ts.pg_pairs.end(), pairs.begin(), pairs.end());
-            int ne = 0;
-            std::vector<int> eoffs(tsp.size());
-            for (size_t k = 0; k < tsp.size(); ++k) { eoffs[k] = ne; ne += pt_ne(tsp[k].type); }
-            pg.ne = ne;
-            pg.d_off = (long long)ts.dmat.size();
-            ts.dmat.resize(ts.dmat.size() + (size_t)ne * np, 0.0);
-            double* D = ts.dmat.data() + pg.d_off;
-            // shell-pair records + folded densities
-            int t_cur = 0;
-            for (int t = 0; t <= NPTYPE; ++t) pg.sp_beg[t] = 0;
-            int sp_base = (int)ts.sps.size();
-            for (size_t k = 0; k < tsp.size(); ++k) {
-                const TmpSP& sp = tsp[k];
-                while (t_cur <= sp.type) pg.sp_beg[t_cur++] = sp_base + (int)k;
-                ts.sps.push_back({sp.type, eoffs[k], sp.pp_beg, sp.pp_cnt});
+    // one pair group; pass 0 only measures the largest primitive weight, pass 1 emits
+    auto do_pair_group = [&](int g, int h, int pass, double wcut) {
+        const EntryGroup& G = ts.groups[g];
+        const EntryGroup& H = ts.groups[h];
+        std::vector<int> pairs;
+        for (int s : G.entries)
+            for (int t : H.entries) {
+                if (wf.sym && g == h && t > s) continue;
+                pairs.push_back(s);
+                pairs.push_back(t);
+            }
+        const int np = (int)pairs.size() / 2;
+        if (np == 0) return;
+        std::vector<TmpSP> tsp;
+        for (int X : G.shells)
+            for (int Y : H.shells) {
+                TmpSP sp;
+                sp.swapped = bas.shells[X].l < bas.shells[Y].l;
+                sp.A = sp.swapped ? Y : X;
+                sp.B = sp.swapped ? X : Y;
                 const GShell& sa = bas.shells[sp.A];
                 const GShell& sb = bas.shells[sp.B];
+                sp.type = ptype(sa.l, sb.l);
+                const int na = ncart(sa.l), nb = ncart(sb.l), nE = pt_ne(sp.type), EA = pt_E(sp.type);
                 double AB[3] = {sa.r[0] - sb.r[0], sa.r[1] - sb.r[1], sa.r[2] - sb.r[2]};
-                int na = ncart(sa.l), nb = ncart(sb.l), nE = pt_ne(sp.type);
+                double AB2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+                // folded densities of every orbital pair on this shell pair
+                sp.dt.assign((size_t)nE * np, 0.0);
+                double dmaxL[EMAX + 1] = {0, 0, 0, 0, 0};   // max |folded density| per angular momentum of e
+                bool any = false;
                 for (int ip = 0; ip < np; ++ip) {
                     int s = pairs[2 * ip], t = pairs[2 * ip + 1];
-                    const ExpOrb& ob = orbs[wf.bra[wf.slot(s, 0)]];   // electron-1 bra-side orbital
+                    const ExpOrb& ob = orbs[wf.bra[wf.slot(s, 0)]];   // bra-side orbital of the pair
                     const ExpOrb& ok = orbs[wf.ket[wf.slot(t, 0)]];   // ket-side orbital
                     // original orientation: X from group g (orbital ob), Y from group h (orbital ok)
                     const OrbShell* cA = find_shell(sp.swapped ? ok : ob, sp.A);
@@ -336,27 +302,89 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                     if (!nz) continue;
                     std::fill(dfold.begin(), dfold.begin() + nE, 0.0);
                     hrr_fold(sa.l, sb.l, AB, dcart.data(), dfold.data());
-                    for (int e = 0; e < nE; ++e) D[(size_t)(eoffs[k] + e) * np + ip] += dfold[e];
+                    for (int e = 0; e < nE; ++e) {
+                        sp.dt[(size_t)e * np + ip] = dfold[e];
+                        int L = c_L(coff(sa.l) + e);
+                        dmaxL[L] = std::max(dmaxL[L], std::fabs(dfold[e]));
+                        any = any || dfold[e] != 0.0;
+                    }
                 }
+                if (!any) continue;   // no orbital pair has density on this shell pair
+                sp.wmax = 0.0;
+                for (int ia = 0; ia < sa.nprim; ++ia)
+                    for (int ib = 0; ib < sb.nprim; ++ib) {
+                        double a = bas.exps[sa.prim_off + ia], b = bas.exps[sb.prim_off + ib], p = a + b;
+                        double K = bas.coefs[sa.prim_off + ia] * bas.coefs[sb.prim_off + ib] * std::exp(-a * b / p * AB2) * SQ2PI54;
+                        if (K == 0.0) continue;
+                        PrimPair pp;
+                        pp.Px = (a * sa.r[0] + b * sb.r[0]) / p;
+                        pp.Py = (a * sa.r[1] + b * sb.r[1]) / p;
+                        pp.Pz = (a * sa.r[2] + b * sb.r[2]) / p;
+                        pp.p = p;
+                        pp.ip = 1.0 / p;
+                        pp.Kp = K / p;
+                        pp.PAx = pp.Px - sa.r[0]; pp.PAy = pp.Py - sa.r[1]; pp.PAz = pp.Pz - sa.r[2];
+                        // Schwarz-type magnitude: the charge cloud sum_e dt[e] [e0| of this primitive pair has
+                        // self-repulsion <= w^2, so its share of any (st|uv) is <= w_p w_q.
+                        // [ss|ss]_pp = Kp^2 / sqrt(2p); each unit of angular momentum adds a factor
+                        // <= |PA| + 1/sqrt(p) (generous: includes the 1/2p and 1/4p terms).
+                        double len = std::sqrt(pp.PAx * pp.PAx + pp.PAy * pp.PAy + pp.PAz * pp.PAz) + 1.0 / std::sqrt(p);
+                        double poly = 0.0, lp = 1.0;
+                        for (int L = 0; L <= EA; ++L) { if (L >= sa.l) poly += dmaxL[L] * lp * ncart(L); lp *= 2.0 * len; }
+                        pp.w = std::fabs(pp.Kp) * std::pow(2.0 * p, -0.25) * poly;
+                        if (pass == 1 && !(pp.w * wcut >= tau)) continue;
+                        sp.wmax = std::max(sp.wmax, pp.w);
+                        if (pass == 1) sp.pp.push_back(pp);
+                    }
+                if (pass == 0) { ts.wmax = std::max(ts.wmax, sp.wmax); continue; }
+                if (sp.pp.empty()) continue;
+                std::stable_sort(sp.pp.begin(), sp.pp.end(), [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
+                tsp.push_back(std::move(sp));
             }
-            while (t_cur <= NPTYPE) pg.sp_beg[t_cur++] = sp_base + (int)tsp.size();
-            // ket items: chunks of primitive pairs, per type, longest first
-            for (int t = 0; t < NPTYPE; ++t) {
-                pg.item_beg[t] = (int)ts.items.size();
-                std::vector<Item> tmp;
-                for (int k = pg.sp_beg[t]; k < pg.sp_beg[t + 1]; ++k) {
-                    const SPRec& r = ts.sps[k];
-                    for (int o = 0; o < r.pp_cnt; o += chunk) tmp.push_back({r.eoff, r.pp_beg + o, std::min(chunk, r.pp_cnt - o), 0});
-                }
-                std::stable_sort(tmp.begin(), tmp.end(), [](const Item& a, const Item& b) { return a.pp_cnt > b.pp_cnt; });
-                ts.items.insert(ts.items.end(), tmp.begin(), tmp.end());
-            }
-            pg.item_beg[NPTYPE] = (int)ts.items.size();
-            ts.max_ne = std::max(ts.max_ne, ne);
-            ts.max_np = std::max(ts.max_np, np);
-            ts.pgs.push_back(pg);
+        if (pass == 0 || tsp.empty()) return;
+        // by type, strongest shell pairs first
+        std::stable_sort(tsp.begin(), tsp.end(), [](const TmpSP& a, const TmpSP& b) {
+            return a.type != b.type ? a.type < b.type : a.wmax > b.wmax;
+        });
+        PGDesc pg;
+        std::memset(&pg, 0, sizeof pg);
+        pg.g = g; pg.h = h; pg.np = np; pg.pair_beg = (int)ts.pg_pairs.size() / 2;
+        ts.pg_pairs.insert(ts.pg_pairs.end(), pairs.begin(), pairs.end());
+        int ne = 0;
+        for (const TmpSP& sp : tsp) ne += pt_ne(sp.type);
+        pg.ne = ne;
+        pg.d_off = (long long)ts.dmat.size();
+        ts.dmat.resize(ts.dmat.size() + (size_t)ne * np, 0.0);
+        double* D = ts.dmat.data() + pg.d_off;
+        int t_cur = 0, eoff = 0;
+        const int sp_base = (int)ts.sps.size();
+        std::vector<SPRec> recs;
+        for (size_t k = 0; k < tsp.size(); ++k) {
+            const TmpSP& sp = tsp[k];
+            while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
+            const int nE = pt_ne(sp.type);
+            recs.push_back({sp.type, eoff, (int)ts.pps.size(), (int)sp.pp.size()});
+            for (const PrimPair& pp : sp.pp) { ts.pps.push_back(pp); ts.pp_eoff.push_back(eoff); }
+            std::copy(sp.dt.begin(), sp.dt.end(), D + (size_t)eoff * np);
+            eoff += nE;
         }
-    }
+        while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
+        // bra-side work units are handed out dynamically inside a tile: most expensive first
+        std::stable_sort(recs.begin(), recs.end(), [](const SPRec& a, const SPRec& b) {
+            return a.pp_cnt * pt_ne(a.type) > b.pp_cnt * pt_ne(b.type);
+        });
+        ts.sps.insert(ts.sps.end(), recs.begin(), recs.end());
+        pg.sp_beg[0] = sp_base;
+        for (int t = 1; t <= NPTYPE; ++t) pg.sp_beg[t] = sp_base + (int)recs.size();
+        ts.max_ne = std::max(ts.max_ne, ne);
+        ts.max_np = std::max(ts.max_np, np);
+        ts.pgs.push_back(pg);
+    };
+    // pass 0: the largest weights live in the one-group pair groups
+    for (int g = 0; g < ng; ++g) do_pair_group(g, g, 0, 0.0);
+    const double wcut = ts.wmax;
+    for (int g = 0; g < ng; ++g)
+        for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h) do_pair_group(g, h, 1, wcut);
     for (const GShell& s : bas.shells) ts.lmax = std::max(ts.lmax, s.l);
 }
 

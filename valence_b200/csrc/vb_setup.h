@@ -41,12 +41,9 @@ struct SPRec {          // one oriented shell pair of a pair group (whole contra
     int eoff;           // first [e0| component of this shell pair inside the group's e-space
     int pp_beg, pp_cnt; // range in the primitive-pair array
 };
-struct Item {           // ket work item: a chunk of one shell pair's primitive pairs
-    int eoff, pp_beg, pp_cnt, pad;
-};
 struct PGDesc {
     int sp_beg[NPTYPE + 1];     // shell pairs sorted by type
-    int item_beg[NPTYPE + 1];   // items sorted by type
+    int pp_beg[NPTYPE + 1];     // primitive pairs sorted by type, then shell pair (ket lanes walk these)
     long long d_off;            // offset of the folded density block [ne][np]
     int ne, np;                 // # e-components, # orbital pairs
     int pair_beg;               // offset into the pair list (s,t)
@@ -75,8 +72,9 @@ struct TileSetup {
     std::vector<PGDesc> pgs;
     std::vector<int> pg_pairs;      // 2 ints (s,t) per pair
     std::vector<SPRec> sps;
-    std::vector<Item> items;
     std::vector<PrimPair> pps;
+    std::vector<int> pp_eoff;       // per primitive pair: e-offset of its shell pair inside the group
+    double wmax = 0.0;              // largest primitive-pair magnitude bound (for pruning)
     std::vector<double> dmat;       // folded densities, per pair group [e][p]
     int max_ne = 0, max_np = 0;
     int lmax = 0;
@@ -92,7 +90,9 @@ ExpOrb expand_orbital(const Input& in, const Basis& bas, const std::vector<std::
 // global shell and component of OBS position `pos` (1-based) of orbital `orb`
 bool obs_position(const Input& in, const Basis& bas, int orb, int pos, int* gshell, int* comp);
 
+// tau: primitive pairs whose largest possible contribution to any orbital-level integral stays
+// below tau are dropped at set-up (0 keeps everything the reference computes)
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs2e,
-                 int chunk, TileSetup* out);
+                 double tau, TileSetup* out);
 
 }  // namespace vb

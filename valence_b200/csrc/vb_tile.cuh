@@ -22,39 +22,66 @@ __device__ __forceinline__ double w_term(const double* __restrict__ Pa, const do
     return (ast + bst) * (auv + buv) - asv * aut - bsv * but;
 }
 
+// One warp-batch of class (TB|TK): the warp owns bra shell pair `sp`; lane = one ket primitive
+// pair of type TK (flat list, shell pairs contiguous).  Every lane runs the same trip count
+// (the bra contraction), so there is no divergence inside the batch.  The contracted partial
+// blocks of lanes that belong to the same ket shell pair are summed by a segmented warp
+// reduction, then the segment heads are half-transformed with the staged ket densities.
 template <int TB, int TK>
-__device__ __forceinline__ void eri_batch(const TileArgs& A, const SPRec& sp, const Item& it, bool active,
-                                          const PrimPair* __restrict__ kpps, double* __restrict__ acc)
+__device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& sp, const PGDesc& Q, int base, int nket, int lane,
+                                               const double* __restrict__ Dq, double* __restrict__ H, unsigned long long& npq)
 {
     constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
-    const int nq = active ? it.pp_cnt : 0;
+    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    double acc[NE * NF];
+#pragma unroll
+    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+    const bool active = base + lane < nket;
+    const int kidx = Q.pp_beg[TK] + base + (active ? lane : 0);
+    PrimPair b = A.pps[kidx];
+    int seg = active ? A.pp_eoff[kidx] : -1 - lane;
+    if (!active) { b.Kp = 0.0; b.w = 0.0; }
+    // largest ket weight of the batch -> how many (sorted) bra primitives can still matter
+    double wq = b.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wq = fmax(wq, __shfl_xor_sync(0xffffffffu, wq, o));
+    int nbra = 0;
     for (int ip = 0; ip < sp.pp_cnt; ++ip) {
         const PrimPair a = A.pps[sp.pp_beg + ip];
-        for (int iq = 0; iq < nq; ++iq) {
-            const PrimPair b = kpps[it.pp_beg + iq];
-            QuartetGeom g;
-            double T, pref;
-            quartet_geom(a, b, g, T, pref);
-            double F[M + 1];
-            boys<M>(A.boys, T, F);
+        if (!(a.w * wq >= A.tau)) break;           // bra primitives are sorted by weight
+        ++nbra;
+        QuartetGeom g;
+        double T, pref;
+        quartet_geom(a, b, g, T, pref);
+        double F[M + 1];
+        boys<M>(A.boys, T, F);
 #pragma unroll
-            for (int m = 0; m <= M; ++m) F[m] *= pref;
-            if constexpr (M == 0) acc[0] += F[0];
-            else vrr_unrolled<LA, EA, LC, EC>(g, F, acc);
+        for (int m = 0; m <= M; ++m) F[m] *= pref;
+        if constexpr (M == 0) acc[0] += F[0];
+        else vrr_unrolled<LA, EA, LC, EC>(g, F, acc);
+    }
+    if (nbra == 0) return;
+    if (lane == 0) npq += (unsigned long long)nbra * min(32, nket - base);
+    // segmented reduction over lanes of the same ket shell pair (segments are contiguous)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int so = __shfl_down_sync(0xffffffffu, seg, o);
+        const bool take = (lane + o < 32) && (so == seg);
+#pragma unroll
+        for (int i = 0; i < NE * NF; ++i) {
+            const double v = __shfl_down_sync(0xffffffffu, acc[i], o);
+            if (take) acc[i] += v;
         }
     }
-}
-
-// first half transformation: H[e] (lane = ket orbital pair q) += sum_src sum_f acc_src[e][f] * Dq[(eoff_src+f)][q]
-template <int NE, int NF>
-__device__ __forceinline__ void half_transform(const double* __restrict__ acc, int eoff, int cnt, int lane, int npq,
-                                               const double* __restrict__ Dq, double* __restrict__ H)
-{
-    for (int src = 0; src < cnt; ++src) {
-        const int eo = __shfl_sync(0xffffffffu, eoff, src);
+    const int sprev = __shfl_up_sync(0xffffffffu, seg, 1);
+    unsigned heads = __ballot_sync(0xffffffffu, active && (lane == 0 || sprev != seg));
+    while (heads) {
+        const int src = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int eo = __shfl_sync(0xffffffffu, seg, src);
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            const double dq = (lane < npq) ? Dq[(eo + f) * npq + lane] : 0.0;
+            const double dq = (lane < Q.np) ? Dq[(eo + f) * Q.np + lane] : 0.0;
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 const double v = __shfl_sync(0xffffffffu, acc[e * NF + f], src);
@@ -64,39 +91,31 @@ __device__ __forceinline__ void half_transform(const double* __restrict__ acc, i
     }
 }
 
-template <int TB, int TK>
-__device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& sp, const PGDesc& Q, int base, int nit, int lane,
-                                               const PrimPair* __restrict__ kpps, const double* __restrict__ Dq, double* __restrict__ H)
-{
-    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
-    double acc[NE * NF];
-#pragma unroll
-    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
-    const bool active = base + lane < nit;
-    Item it = {0, 0, 0, 0};
-    if (active) it = A.items[Q.item_beg[TK] + base + lane];
-    eri_batch<TB, TK>(A, sp, it, active, kpps, acc);
-    half_transform<NE, NF>(acc, it.eoff, min(32, nit - base), lane, Q.np, Dq, H);
-}
-
 // generic path (any class with a d shell): runtime loops, scratch in global memory
-__device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, const SPRec& sp, const PGDesc& Q, int base, int nit,
-                                           int lane, const PrimPair* __restrict__ kpps, const double* __restrict__ Dq,
-                                           double* __restrict__ H, double* __restrict__ scratch)
+__device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, const SPRec& sp, const PGDesc& Q, int base, int nket,
+                                           int lane, const double* __restrict__ Dq, double* __restrict__ H,
+                                           double* __restrict__ scratch, unsigned long long& npq)
 {
     const int LA = pt_la(tb), EA = pt_E(tb), LC = pt_la(tk), EC = pt_E(tk), M = EA + EC;
     const int NE = pt_ne(tb), NF = pt_ne(tk);
     double* T = scratch;                       // GEN_SCRATCH
     double* acc = scratch + GEN_SCRATCH;       // up to 31*31
     for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
-    const bool active = base + lane < nit;
-    Item it = {0, 0, 0, 0};
-    if (active) it = A.items[Q.item_beg[tk] + base + lane];
-    const int nq = active ? it.pp_cnt : 0;
-    for (int ip = 0; ip < sp.pp_cnt; ++ip) {
-        const PrimPair a = A.pps[sp.pp_beg + ip];
-        for (int iq = 0; iq < nq; ++iq) {
-            const PrimPair b = kpps[it.pp_beg + iq];
+    const bool active = base + lane < nket;
+    const int kidx = Q.pp_beg[tk] + base + (active ? lane : 0);
+    PrimPair b = A.pps[kidx];
+    const int eoff = A.pp_eoff[kidx];
+    if (!active) { b.Kp = 0.0; b.w = 0.0; }
+    double wq = b.w;
+    for (int o = 16; o > 0; o >>= 1) wq = fmax(wq, __shfl_xor_sync(0xffffffffu, wq, o));
+    int nbra = 0;
+    for (; nbra < sp.pp_cnt; ++nbra)
+        if (!(A.pps[sp.pp_beg + nbra].w * wq >= A.tau)) break;
+    if (nbra == 0) return;
+    if (lane == 0) npq += (unsigned long long)nbra * min(32, nket - base);
+    if (active)
+        for (int ip = 0; ip < nbra; ++ip) {
+            const PrimPair a = A.pps[sp.pp_beg + ip];
             QuartetGeom g;
             double Tt, pref, F[MTOP + 1];
             quartet_geom(a, b, g, Tt, pref);
@@ -104,10 +123,9 @@ __device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, co
             for (int m = 0; m <= M; ++m) F[m] *= pref;
             vrr_generic(LA, EA, LC, EC, g, F, T, acc);
         }
-    }
-    const int cnt = min(32, nit - base);
+    const int cnt = min(32, nket - base);
     for (int src = 0; src < cnt; ++src) {
-        const int eo = __shfl_sync(0xffffffffu, it.eoff, src);
+        const int eo = __shfl_sync(0xffffffffu, eoff, src);
         for (int f = 0; f < NF; ++f) {
             const double dq = (lane < Q.np) ? Dq[(eo + f) * Q.np + lane] : 0.0;
             for (int e = 0; e < NE; ++e) {
@@ -124,14 +142,15 @@ constexpr int HMAX_GEN = 31;                     // pt_ne(dd)
 constexpr int GEN_PER_THREAD = GEN_SCRATCH + HMAX_GEN * HMAX_GEN;
 
 template <bool GEN>
-__global__ void __launch_bounds__(TILE_THREADS) k_tile(const TileArgs A)
+__global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileArgs A)
 {
     extern __shared__ double smem[];
     double* Dq = smem;                            // [Q.ne][Q.np]
     double* Gt = smem + A.dq_cap;                 // [32][32]
-    __shared__ int s_tile;
+    __shared__ int s_tile, s_unit;
     __shared__ double s_red[TILE_THREADS / 32];
     __shared__ unsigned long long s_cnt[CNT_N];
+    __shared__ unsigned long long s_pq[NPTYPE * NPTYPE];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = TILE_THREADS / 32;
     constexpr int HM = GEN ? HMAX_GEN : HMAX_UNR;
     double* scratch = nullptr;
@@ -141,6 +160,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const TileArgs A)
         __syncthreads();
         if (tid == 0) s_tile = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
         if (tid < CNT_N) s_cnt[tid] = 0ull;
+        if (tid < NPTYPE * NPTYPE) s_pq[tid] = 0ull;
         __syncthreads();
         const long long tl = (long long)A.tile_first + (long long)s_tile * A.tile_stride;
         if (tl >= A.ntiles) break;
@@ -148,32 +168,44 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const TileArgs A)
         const PGDesc P = A.pgs[tq.x];
         const PGDesc Q = A.pgs[tq.y];
         for (int i = tid; i < Q.ne * Q.np; i += TILE_THREADS) Dq[i] = A.dmat[Q.d_off + i];
-        for (int i = tid; i < 32 * 32; i += TILE_THREADS) Gt[i] = 0.0;
+        double* Gw = Gt + warp * (32 * 32);       // this warp's private accumulator [p][q]
+        for (int i = lane; i < 32 * 32; i += 32) Gw[i] = 0.0;
+        if (tid == 0) s_unit = 0;
         __syncthreads();
 
+        // work units (bra shell pair, ket class) are handed out dynamically, most expensive first
+        constexpr int NT = GEN ? NPTYPE : 3;
         const int nsp = P.sp_beg[NPTYPE] - P.sp_beg[0];
-        for (int isp = warp; isp < nsp; isp += nw) {
-            const SPRec sp = A.sps[P.sp_beg[0] + isp];
+        const int nunits = nsp * NT;
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_unit, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= nunits) break;
+            const int tk = u % NT;
+            const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+            if (nket == 0) continue;
+            const SPRec sp = A.sps[P.sp_beg[0] + u / NT];
+            const int cls = sp.type * NPTYPE + tk;
             double H[HM];
 #pragma unroll
             for (int e = 0; e < HM; ++e) H[e] = 0.0;
-            for (int tk = 0; tk < (GEN ? NPTYPE : 3); ++tk) {
-                const int nit = Q.item_beg[tk + 1] - Q.item_beg[tk];
-                for (int base = 0; base < nit; base += 32) {
-                    const int cls = sp.type * NPTYPE + tk;
-                    switch (cls) {
-#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, Q, base, nit, lane, A.pps, Dq, H); break;
-                        VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
-                        VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
-                        VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
+            unsigned long long npq = 0ull;
+            for (int base = 0; base < nket; base += 32) {
+                switch (cls) {
+#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, Q, base, nket, lane, Dq, H, npq); break;
+                    VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
+                    VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
+                    VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
 #undef VB_CASE
-                        default:
-                            if constexpr (GEN) batch_generic(A, sp.type, tk, sp, Q, base, nit, lane, A.pps, Dq, H, scratch);
-                            break;
-                    }
+                    default:
+                        if constexpr (GEN) batch_generic(A, sp.type, tk, sp, Q, base, nket, lane, Dq, H, scratch, npq);
+                        break;
                 }
             }
-            // second half transformation: G[p][q] += sum_e Dp[eoff+e][p] H[e]
+            if (!__any_sync(0xffffffffu, npq != 0ull)) continue;   // nothing survived the magnitude cut
+            if (lane == 0 && npq) atomicAdd(&s_pq[cls], npq);
+            // second half transformation into the warp-private tile: G[p][q] += sum_e Dp[eoff+e][p] H[e]
             if (lane < Q.np) {
                 const double* Dp = A.dmat + P.d_off + (size_t)sp.eoff * P.np;
                 const int ne = pt_ne(sp.type);
@@ -182,12 +214,21 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const TileArgs A)
 #pragma unroll
                     for (int e = 0; e < HM; ++e)
                         if (e < ne) g += Dp[e * P.np + p] * H[e];
-                    atomicAdd(&Gt[p * 32 + lane], g);
+                    Gw[p * 32 + lane] += g;
                 }
             }
         }
         __syncthreads();
+        // fold the warp-private tiles into warp 0's
+        for (int i = tid; i < 32 * 32; i += TILE_THREADS) {
+            double g = 0.0;
+#pragma unroll
+            for (int w = 0; w < TILE_THREADS / 32; ++w) g += Gt[w * (32 * 32) + i];
+            Gt[i] = g;
+        }
+        __syncthreads();
 
+        if (tid < NPTYPE * NPTYPE && s_pq[tid]) atomicAdd(&A.pq_counters[tid], s_pq[tid]);
         // ---- contraction with the cofactor densities --------------------------------------
         double epart = 0.0;
         unsigned long long cnt[CNT_N];
