@@ -67,6 +67,7 @@ typedef struct vb_energy_result {
     double t_total_ms, t_host_setup_ms, t_1e_ms, t_density_ms, t_diag_ms, t_tiles_ms;
     int launches, diag_launches, tile_launches;
     double min_pivot_ratio;
+    long long h2d_bytes, d2h_bytes;   /* host<->device bytes copied by this call */
 } vb_energy_result;
 
 const char* vb_last_error(void);

@@ -61,6 +61,8 @@ def lib():
         L.vo_set_coords.argtypes = [C.c_void_p, C.c_void_p]
         L.vo_reset_orbitals.argtypes = [C.c_void_p]
         L.vo_guess_partial.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3
+        L.vo_baseline_timed.restype = C.c_longlong
+        L.vo_baseline_timed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
         L.vo_baseline_sample.restype = C.c_longlong
         L.vo_baseline_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_double)]
         for f in ("vo_nelec", "vo_natom", "vo_norbs", "vo_npairs_schwarz"):
@@ -155,3 +157,31 @@ class Oracle:
         e = C.c_double(0.0)
         nq = self.L.vo_baseline_sample(self.h, irank, nrank, task_limit, C.byref(e))
         return int(nq), e.value
+
+    def baseline_timed(self, irank: int, nrank: int, seconds: float):
+        el = C.c_double(0.0)
+        nq = self.L.vo_baseline_timed(self.h, irank, nrank, seconds, C.byref(el))
+        return int(nq), el.value
+
+
+def _baseline_worker(args):
+    path, irank, nrank, seconds = args
+    o = Oracle(path, memo=False)
+    nq, el = o.baseline_timed(irank, nrank, seconds)
+    o.close()
+    return nq, el
+
+
+def cpu_baseline(path: str, seconds: float = 12.0, nproc: int = 0) -> dict:
+    """The reference algorithm (literal restatement, no memoisation) on the host cores with the
+    reference's own decomposition: rank r of nproc takes tasks r, r+nproc, ... (valence.F90:1162-1163).
+    Every worker runs for `seconds`; throughput = shell quartets / max elapsed."""
+    import multiprocessing as mp
+    nproc = nproc or (os.cpu_count() or 1)
+    build()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(nproc) as pool:
+        res = pool.map(_baseline_worker, [(path, r, nproc, seconds) for r in range(nproc)])
+    nq = sum(r[0] for r in res)
+    el = max(r[1] for r in res)
+    return {"shell_quartets": nq, "seconds": el, "quartets_per_s": nq / el if el > 0 else 0.0, "cores": nproc}

@@ -27,6 +27,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "vo_internal.h"
 
 /* ------------------------------------------------------------------------ */
@@ -87,6 +88,8 @@ typedef struct vo_ctx {
     memo_t *memo, *memo2;
     int memo_on;
     long long task_limit;          /* >0: stop the 2e loop after this many tasks (baseline sample) */
+    double deadline;               /* >0: wall-clock second (CLOCK_MONOTONIC) after which the timed sample stops */
+    int expired;
     int quiet;
     double *integrals_store;
 } vo_ctx;
@@ -543,8 +546,12 @@ static void ovint(vo_ctx *c, int io, int jo) { oneint(c, io, jo, 0); }
 static void int1e(vo_ctx *c, int io, int jo) { oneint(c, io, jo, 1); }
 
 /* valence.F90:3184-3438 */
+static double mono_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 static void int2e(vo_ctx *c, int io, int jo, int ko, int lo)
 {
+    if (c->deadline > 0.0 && !c->expired && mono_now() > c->deadline) c->expired = 1;
+    if (c->expired) { c->gint = 0.0; return; }
     scatter(c, io, c->coeffi); scatter(c, jo, c->coeffj); scatter(c, ko, c->coeffk); scatter(c, lo, c->coeffl);
     double gint = 0.0;
     int ish_beg = 1;
@@ -992,6 +999,7 @@ static void vsvb_energy(vo_ctx *c, int iorb, int num_non_docc, int num_spatial_o
     c->in2e = 1;
     for (long long loctask = 1; loctask <= mytasks; ++loctask) {
         int ijorb, klorb, io, jo, ko, lo;
+        if (c->expired) break;
         c->cnt.ntasks++;
         if (sym) xm_dtriang8(1 + task, &ijorb, &klorb);
         else { klorb = (int)(1 + task / ij8); ijorb = (int)(1 + task % ij8); }
@@ -1247,6 +1255,65 @@ long long vo_baseline_sample(vo_ctx *c, int irank, int nrank, long long task_lim
     vsvb_energy(c, 0, nnd, nnd + c->ndocc, &e, &w, 0, 1);
     c->nrank = 1; c->irank = 0; c->task_limit = 0;
     if (energy_partial) *energy_partial = e;
+    return c->cnt.shell_quartets - before;
+}
+
+/* Timed sample of the reference algorithm for the CPU baseline: this rank's share of
+ * schwarz_ints and of the 2e loop (round-robin, valence.F90:1162-1163,1513) runs until
+ * `seconds` of wall clock are used up.  Returns simint_compute_eri-equivalent calls made and
+ * the time they took (set-up excluded).  Memoisation must be off for a faithful timing. */
+long long vo_baseline_timed(vo_ctx *c, int irank, int nrank, double seconds, double *elapsed)
+{
+    setup_energy(c);
+    memset(&c->cnt, 0, sizeof c->cnt);
+    int nnd = 2 * c->npair + c->nunpd, nso = nnd + c->ndocc;
+    default_lists(c, nnd);
+    wfndet(c);
+    double t0 = mono_now();
+    c->deadline = t0 + seconds; c->expired = 0;
+    long long before = c->cnt.shell_quartets;
+    /* schwarz_ints, this rank's share (valence.F90:1509-1520) */
+    {
+        int task = 0;
+        for (int i = 1; i <= nso && !c->expired; ++i)
+            for (int j = 1; j <= i && !c->expired; ++j) {
+                task = task + 1;
+                if (task % nrank == irank) {
+                    int ie = i; if (i > nnd) ie = 2 * i - nnd;
+                    int je = j; if (j > nnd) je = 2 * j - nnd;
+                    int2e(c, c->bra[ie], c->ket[je], c->bra[ie], c->ket[je]);
+                    c->schwarz[indx(i, j)] = sqrt(c->gint);
+                }
+            }
+    }
+    if (!c->expired) {
+        /* the 2e loop needs the whole table: the other ranks' entries are filled here untimed */
+        double pause = mono_now();
+        c->deadline = 0.0;
+        int task = 0;
+        for (int i = 1; i <= nso; ++i)
+            for (int j = 1; j <= i; ++j) {
+                task = task + 1;
+                if (task % nrank != irank) {
+                    int ie = i; if (i > nnd) ie = 2 * i - nnd;
+                    int je = j; if (j > nnd) je = 2 * j - nnd;
+                    long long keep = c->cnt.shell_quartets;
+                    int memo = c->memo_on; c->memo_on = 1;
+                    int2e(c, c->bra[ie], c->ket[je], c->bra[ie], c->ket[je]);
+                    c->memo_on = memo; c->cnt.shell_quartets = keep;
+                    c->schwarz[indx(i, j)] = sqrt(c->gint);
+                }
+            }
+        double resume = mono_now();
+        t0 += resume - pause;
+        c->deadline = t0 + seconds;
+        c->store_eri = 0; c->nrank = nrank; c->irank = irank;
+        double e, w;
+        vsvb_energy(c, 0, nnd, nso, &e, &w, 0, 1);
+        c->nrank = 1; c->irank = 0;
+    }
+    *elapsed = mono_now() - t0;
+    c->deadline = 0.0; c->expired = 0;
     return c->cnt.shell_quartets - before;
 }
 

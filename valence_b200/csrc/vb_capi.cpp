@@ -27,7 +27,7 @@ void to_c(const vb::EnergyResult& r, vb_energy_result* o)
     o->flops_model = r.flops_model; o->ref_shell_quartets = r.ref_shell_quartets;
     o->t_total_ms = r.t_total; o->t_host_setup_ms = r.t_host_setup; o->t_1e_ms = r.t_1e; o->t_density_ms = r.t_density;
     o->t_diag_ms = r.t_diag; o->t_tiles_ms = r.t_tiles; o->launches = r.launches; o->diag_launches = r.diag_launches;
-    o->tile_launches = r.tile_launches; o->min_pivot_ratio = r.min_pivot_ratio;
+    o->tile_launches = r.tile_launches; o->min_pivot_ratio = r.min_pivot_ratio; o->h2d_bytes = r.h2d_bytes; o->d2h_bytes = r.d2h_bytes;
 }
 
 template <class F>

@@ -25,6 +25,8 @@ namespace vb {
 
 namespace {
 
+long long g_h2d_bytes = 0, g_d2h_bytes = 0;   // host<->device traffic of the current call
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -45,6 +47,7 @@ struct DBuf {
     {
         alloc(v.size());
         if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        g_h2d_bytes += (long long)(v.size() * sizeof(T));
     }
     void zero(cudaStream_t st) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
     void download(std::vector<T>& v, cudaStream_t st)
@@ -52,6 +55,7 @@ struct DBuf {
         v.resize(n);
         if (n) CK(cudaMemcpyAsync(v.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        g_d2h_bytes += (long long)(n * sizeof(T));
     }
 };
 
@@ -187,6 +191,7 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
     *out = EnergyResult();
     I.launches = 0;
     I.t_begin = now_ms();
+    g_h2d_bytes = 0; g_d2h_bytes = 0;
     const Input& in = in_;
     const int norbs = in.norbs(), nval = norbs - in.ndf;
     if (in.npair > 0) throw std::runtime_error("valence_b200: spin-coupled pairs are not supported by this build of the GPU engine");
@@ -503,6 +508,7 @@ void Engine::energy_finish(EnergyResult* out)
     out->numerator = I.e1 + out->e2;
     out->energy = out->numerator / I.wfnorm + I.enuc;     // valence.F90:344
     out->launches = I.launches;
+    out->h2d_bytes = g_h2d_bytes + 8 * CNT_N; out->d2h_bytes = g_d2h_bytes + 8 * (1 + CNT_N);
     out->t_total = now_ms() - I.t_begin;
 }
 
