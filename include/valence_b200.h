@@ -85,6 +85,8 @@ int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out);
 double* vb_engine_accum_device(const vb_engine* e);
 int vb_engine_accum_len(const vb_engine* e);
 void* vb_engine_stream(const vb_engine* e);
+/* debugging aid: per-tile energy partials of the last tile pass (returns their count) */
+long long vb_engine_debug_tile_energies(const vb_engine* e, double* out, long long cap);
 /* measured FP64 FMA peak of the device in TFLOP/s (roofline denominator of the ERI kernel) */
 int vb_measure_fp64_peak(int device, double* tflops);
 

@@ -154,6 +154,8 @@ double* vb_engine_accum_device(const vb_engine* e) { return e->eng->accum_device
 int vb_engine_accum_len(const vb_engine* e) { return e->eng->accum_len(); }
 void* vb_engine_stream(const vb_engine* e) { return e->eng->stream(); }
 
+long long vb_engine_debug_tile_energies(const vb_engine* e, double* out, long long cap) { return e->eng->debug_tile_energies(out, cap); }
+
 int vb_measure_fp64_peak(int device, double* tflops)
 {
     return guarded([&] { *tflops = vb::measure_fp64_peak_tflops(device); });

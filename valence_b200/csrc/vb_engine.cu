@@ -111,6 +111,7 @@ struct Engine::Impl {
     DBuf<unsigned int> counter;
     DBuf<unsigned long long> counters, pq_counters;
     DBuf<int> pp_eoff;
+    DBuf<double> pp_wseg;
     // state carried from energy_partial to energy_finish
     double enuc = 0, e1 = 0, wfnorm = 0;
     double tau = 1e-22;   // primitive-quartet magnitude cut; VB_PRIM_TAU overrides
@@ -162,6 +163,14 @@ void Engine::reset_orbitals()
 }
 
 double* Engine::accum_device() const { return impl_->accum.p; }
+long long Engine::debug_tile_energies(double* out, long long cap) const
+{
+    long long n = (long long)impl_->tileE.n;
+    if (out && cap >= n) {
+        cudaMemcpy(out, impl_->tileE.p, n * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    return n;
+}
 int Engine::accum_len() const { return 1 + CNT_N; }
 void* Engine::stream() const { return (void*)impl_->st; }
 
@@ -348,7 +357,7 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
         nshb[s] = (int)orbs2e[wf.bra[wf.slot(s, 0)]].sh.size();
         nshk[s] = (int)orbs2e[wf.ket[wf.slot(s, 0)]].sh.size();
     }
-    I.pgs.upload(ts.pgs, st); I.pg_pairs.upload(ts.pg_pairs, st); I.sps.upload(ts.sps, st); I.pp_eoff.upload(ts.pp_eoff, st);
+    I.pgs.upload(ts.pgs, st); I.pg_pairs.upload(ts.pg_pairs, st); I.sps.upload(ts.sps, st); I.pp_eoff.upload(ts.pp_eoff, st); I.pp_wseg.upload(ts.pp_wseg, st);
     I.pps.upload(ts.pps, st); I.dmat.upload(ts.dmat, st); I.nsh_bra.upload(nshb, st); I.nsh_ket.upload(nshk, st);
     I.counter.alloc(1); I.counters.alloc(CNT_N); I.pq_counters.alloc(NPTYPE * NPTYPE);
     const bool gen = ts.lmax >= 2;
@@ -359,7 +368,7 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
-    A.pgs = I.pgs.p; A.pg_pairs = I.pg_pairs.p; A.sps = I.sps.p; A.pps = I.pps.p; A.pp_eoff = I.pp_eoff.p; A.tau = tau_diag; A.pq_counters = I.pq_counters.p; A.dmat = I.dmat.p;
+    A.pgs = I.pgs.p; A.pg_pairs = I.pg_pairs.p; A.sps = I.sps.p; A.pps = I.pps.p; A.pp_eoff = I.pp_eoff.p; A.pp_wseg = I.pp_wseg.p; A.tau = tau_diag; A.pq_counters = I.pq_counters.p; A.dmat = I.dmat.p;
     A.boys = I.boys.p; A.counter = I.counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = -1;
     A.dq_cap = dq_cap; A.itol = itol; A.Pa = I.Pa.p; A.Pb = I.Pb.p; A.c0 = c0; A.nsh_bra = I.nsh_bra.p; A.nsh_ket = I.nsh_ket.p;
     A.counters = I.counters.p; A.gen_scratch = I.gen_scratch.p;

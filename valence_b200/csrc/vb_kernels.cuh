@@ -32,6 +32,7 @@ struct TileArgs {
     const SPRec* sps;
     const PrimPair* pps;
     const int* pp_eoff;
+    const double* pp_wseg;
     double tau;                      // primitive-quartet magnitude cut (0 = none)
     unsigned long long* pq_counters; // primitive quartets evaluated, per class tb*NPTYPE+tk
     const double* dmat;

@@ -363,8 +363,9 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             const TmpSP& sp = tsp[k];
             while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
             const int nE = pt_ne(sp.type);
-            recs.push_back({sp.type, eoff, (int)ts.pps.size(), (int)sp.pp.size()});
-            for (const PrimPair& pp : sp.pp) { ts.pps.push_back(pp); ts.pp_eoff.push_back(eoff); }
+            recs.push_back({sp.type, eoff, (int)ts.pps.size(), (int)sp.pp.size(), sp.wmax});
+            pg.kwmax[sp.type] = std::max(pg.kwmax[sp.type], sp.wmax);
+            for (const PrimPair& pp : sp.pp) { ts.pps.push_back(pp); ts.pp_eoff.push_back(eoff); ts.pp_wseg.push_back(sp.wmax); }
             std::copy(sp.dt.begin(), sp.dt.end(), D + (size_t)eoff * np);
             eoff += nE;
         }

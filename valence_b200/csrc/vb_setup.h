@@ -40,6 +40,7 @@ struct SPRec {          // one oriented shell pair of a pair group (whole contra
     int type;           // ptype(la, lb)
     int eoff;           // first [e0| component of this shell pair inside the group's e-space
     int pp_beg, pp_cnt; // range in the primitive-pair array
+    double wmax;        // largest primitive weight of the shell pair
 };
 struct PGDesc {
     int sp_beg[NPTYPE + 1];     // shell pairs sorted by type
@@ -49,6 +50,7 @@ struct PGDesc {
     int pair_beg;               // offset into the pair list (s,t)
     int g, h;                   // entry groups
     double smax;                // max Schwarz value over the pairs (filled after the diagonal pass)
+    double kwmax[NPTYPE];       // largest primitive weight per pair type
 };
 
 struct EntryGroup {
@@ -74,6 +76,7 @@ struct TileSetup {
     std::vector<SPRec> sps;
     std::vector<PrimPair> pps;
     std::vector<int> pp_eoff;       // per primitive pair: e-offset of its shell pair inside the group
+    std::vector<double> pp_wseg;    // per primitive pair: largest weight of its shell pair (non-increasing per type)
     double wmax = 0.0;              // largest primitive-pair magnitude bound (for pruning)
     std::vector<double> dmat;       // folded densities, per pair group [e][p]
     int max_ne = 0, max_np = 0;

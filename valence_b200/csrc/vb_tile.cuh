@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
     extern __shared__ double smem[];
     double* Dq = smem;                            // [Q.ne][Q.np]
     double* Gt = smem + A.dq_cap;                 // [32][32]
-    __shared__ int s_tile, s_unit;
+    __shared__ int s_tile;
     __shared__ double s_red[TILE_THREADS / 32];
     __shared__ unsigned long long s_cnt[CNT_N];
     __shared__ unsigned long long s_pq[NPTYPE * NPTYPE];
@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
     double* scratch = nullptr;
     if constexpr (GEN) scratch = A.gen_scratch + ((size_t)blockIdx.x * TILE_THREADS + tid) * GEN_PER_THREAD;
 
+    if (tid < CNT_N) s_cnt[tid] = 0ull;
+    if (tid < NPTYPE * NPTYPE) s_pq[tid] = 0ull;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_tile = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
-        if (tid < CNT_N) s_cnt[tid] = 0ull;
-        if (tid < NPTYPE * NPTYPE) s_pq[tid] = 0ull;
         __syncthreads();
         const long long tl = (long long)A.tile_first + (long long)s_tile * A.tile_stride;
         if (tl >= A.ntiles) break;
@@ -170,28 +170,28 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
         for (int i = tid; i < Q.ne * Q.np; i += TILE_THREADS) Dq[i] = A.dmat[Q.d_off + i];
         double* Gw = Gt + warp * (32 * 32);       // this warp's private accumulator [p][q]
         for (int i = lane; i < 32 * 32; i += 32) Gw[i] = 0.0;
-        if (tid == 0) s_unit = 0;
         __syncthreads();
 
         // work units (bra shell pair, ket class) are handed out dynamically, most expensive first
         constexpr int NT = GEN ? NPTYPE : 3;
         const int nsp = P.sp_beg[NPTYPE] - P.sp_beg[0];
         const int nunits = nsp * NT;
-        for (;;) {
-            int u = 0;
-            if (lane == 0) u = atomicAdd(&s_unit, 1);
-            u = __shfl_sync(0xffffffffu, u, 0);
-            if (u >= nunits) break;
+        // units are dealt round-robin to the warps in cost order: a fixed assignment, so every
+        // tile result is bitwise reproducible (all ranks must derive the same Schwarz table)
+        for (int u = warp; u < nunits; u += nw) {
             const int tk = u % NT;
             const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
             if (nket == 0) continue;
             const SPRec sp = A.sps[P.sp_beg[0] + u / NT];
+            if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;      // nothing in this class can matter
             const int cls = sp.type * NPTYPE + tk;
             double H[HM];
 #pragma unroll
             for (int e = 0; e < HM; ++e) H[e] = 0.0;
             unsigned long long npq = 0ull;
             for (int base = 0; base < nket; base += 32) {
+                // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
+                if (!(sp.wmax * A.pp_wseg[Q.pp_beg[tk] + base] >= A.tau)) break;
                 switch (cls) {
 #define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, Q, base, nket, lane, Dq, H, npq); break;
                     VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
                 }
             }
             if (!__any_sync(0xffffffffu, npq != 0ull)) continue;   // nothing survived the magnitude cut
-            if (lane == 0 && npq) atomicAdd(&s_pq[cls], npq);
+            if (lane == 0) atomicAdd(&s_pq[cls], npq);
             // second half transformation into the warp-private tile: G[p][q] += sum_e Dp[eoff+e][p] H[e]
             if (lane < Q.np) {
                 const double* Dp = A.dmat + P.d_off + (size_t)sp.eoff * P.np;
@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
         }
         __syncthreads();
 
-        if (tid < NPTYPE * NPTYPE && s_pq[tid]) atomicAdd(&A.pq_counters[tid], s_pq[tid]);
         // ---- contraction with the cofactor densities --------------------------------------
         double epart = 0.0;
         unsigned long long cnt[CNT_N];
@@ -264,6 +263,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
             // reference screens: Schwarz product, then the value itself
             const double sprod = A.sch[s * nso + t] * A.sch[u * nso + v];
             const bool ssig = sprod > A.itol;
+            if (!ssig) continue;       // screened: contributes nothing and is counted nowhere
             // images of (s,t,u,v) under the integral's permutational symmetry
             int im[8][4];
             int nim = 0;
@@ -324,9 +324,12 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
                 for (int w = 0; w < nw; ++w) e += s_red[w];
                 A.tileE[tl] = e * A.c0;
             }
-            if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
         }
     }
+    // one flush per CTA (same-address global atomics per tile would serialise in L2)
+    __syncthreads();
+    if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
+    if (tid < NPTYPE * NPTYPE && s_pq[tid]) atomicAdd(&A.pq_counters[tid], s_pq[tid]);
 }
 
 }  // namespace vb
