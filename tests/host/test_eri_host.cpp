@@ -70,6 +70,16 @@ int main() {
         std::vector<double> acc(NE*NF, 0.0), acc2(NE*NF, 0.0);
         auto P = pairs(A,B), Q = pairs(C,D);
         run_generic(l[0],EA,l[2],EC,P,Q,tab.data(),acc.data());
+        if (l[0] <= 1 && l[2] <= 1) {   // compact table-driven path vs loop-based generic
+            std::vector<double> acc3(NE*NF, 0.0), sc(CMP_SCRATCH);
+            for (auto& a : P) for (auto& b : Q) {
+                QuartetGeom g; double T, pref; quartet_geom(a, b, g, T, pref);
+                double F[MTOP+1]; boys_rt(EA+EC, tab.data(), T, F); for (int m = 0; m <= EA+EC; ++m) F[m] *= pref;
+                vrr_compact(l[0],EA,l[2],EC,g,F,sc.data(),acc3.data());
+            }
+            double mx = 0; for (int i = 0; i < NE*NF; ++i) mx = std::fmax(mx, std::fabs(acc[i]));
+            for (int i = 0; i < NE*NF; ++i) worst_ug = std::fmax(worst_ug, std::fabs(acc[i]-acc3[i])/mx);
+        }
         bool unr = l[0] <= 1 && l[2] <= 1;
         if (unr) {
             int tb = ptype(l[0],l[1]), tk = ptype(l[2],l[3]);

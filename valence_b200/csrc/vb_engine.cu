@@ -350,7 +350,7 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
-    const size_t smem = ((size_t)dq_cap + (TILE_THREADS / 32) * 32 * 32) * sizeof(double);
+    const size_t smem = ((size_t)dq_cap + (size_t)ts.max_ne * 32) * sizeof(double);
     if (smem > 220 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
     for (int s = 0; s < nso; ++s) {

@@ -370,13 +370,18 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             eoff += nE;
         }
         while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
-        // bra-side work units are handed out dynamically inside a tile: most expensive first
+        // per type, most expensive shell pairs first (they are dealt round-robin to the warps)
         std::stable_sort(recs.begin(), recs.end(), [](const SPRec& a, const SPRec& b) {
-            return a.pp_cnt * pt_ne(a.type) > b.pp_cnt * pt_ne(b.type);
+            return a.type != b.type ? a.type < b.type : a.pp_cnt > b.pp_cnt;
         });
         ts.sps.insert(ts.sps.end(), recs.begin(), recs.end());
-        pg.sp_beg[0] = sp_base;
-        for (int t = 1; t <= NPTYPE; ++t) pg.sp_beg[t] = sp_base + (int)recs.size();
+        {
+            int k = 0;
+            for (int t = 0; t <= NPTYPE; ++t) {
+                while (k < (int)recs.size() && recs[k].type < t) ++k;
+                pg.sp_beg[t] = sp_base + k;
+            }
+        }
         ts.max_ne = std::max(ts.max_ne, ne);
         ts.max_np = std::max(ts.max_np, np);
         ts.pgs.push_back(pg);

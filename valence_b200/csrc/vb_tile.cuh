@@ -22,6 +22,11 @@ __device__ __forceinline__ double w_term(const double* __restrict__ Pa, const do
     return (ast + bst) * (auv + buv) - asv * aut - bsv * but;
 }
 
+constexpr int TILE_THREADS = 256;
+constexpr int HMAX_UNR = 9;                      // pt_ne(pp)
+constexpr int HMAX_GEN = 31;                     // pt_ne(dd)
+constexpr int GEN_PER_THREAD = GEN_SCRATCH + HMAX_GEN * HMAX_GEN;
+
 // One warp-batch of class (TB|TK): the warp owns bra shell pair `sp`; lane = one ket primitive
 // pair of type TK (flat list, shell pairs contiguous).  Every lane runs the same trip count
 // (the bra contraction), so there is no divergence inside the batch.  The contracted partial
@@ -136,17 +141,21 @@ __device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, co
     }
 }
 
-constexpr int TILE_THREADS = 256;
-constexpr int HMAX_UNR = 9;                      // pt_ne(pp)
-constexpr int HMAX_GEN = 31;                     // pt_ne(dd)
-constexpr int GEN_PER_THREAD = GEN_SCRATCH + HMAX_GEN * HMAX_GEN;
+
+// add a warp's half-transformed rows of one bra shell pair into the CTA's H tile (lane = ket pair q)
+template <int NEH>
+__device__ __forceinline__ void add_rows(double* __restrict__ Hs, int eoff, const double* __restrict__ H, int lane)
+{
+#pragma unroll
+    for (int e = 0; e < NEH; ++e) Hs[(eoff + e) * 32 + lane] += H[e];
+}
 
 template <bool GEN>
 __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileArgs A)
 {
     extern __shared__ double smem[];
     double* Dq = smem;                            // [Q.ne][Q.np]
-    double* Gt = smem + A.dq_cap;                 // [32][32]
+    double* Hs = smem + A.dq_cap;                 // half-transformed tile [P.ne][32]
     __shared__ int s_tile;
     __shared__ double s_red[TILE_THREADS / 32];
     __shared__ unsigned long long s_cnt[CNT_N];
@@ -168,63 +177,58 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
         const PGDesc P = A.pgs[tq.x];
         const PGDesc Q = A.pgs[tq.y];
         for (int i = tid; i < Q.ne * Q.np; i += TILE_THREADS) Dq[i] = A.dmat[Q.d_off + i];
-        double* Gw = Gt + warp * (32 * 32);       // this warp's private accumulator [p][q]
-        for (int i = lane; i < 32 * 32; i += 32) Gw[i] = 0.0;
+        for (int i = tid; i < P.ne * 32; i += TILE_THREADS) Hs[i] = 0.0;
         __syncthreads();
 
-        // work units (bra shell pair, ket class) are handed out dynamically, most expensive first
+        // First half transformation.  All warps walk the classes (tb|tk) in the same order, so at any
+        // time the CTA executes one class body (instruction-cache friendly); inside a class the bra
+        // shell pairs of type tb are dealt round-robin to the warps in cost order.  The assignment is
+        // static, hence every tile result is bitwise reproducible (all ranks derive the same Schwarz
+        // table), and each row of Hs is only ever touched by one warp.
         constexpr int NT = GEN ? NPTYPE : 3;
-        const int nsp = P.sp_beg[NPTYPE] - P.sp_beg[0];
-        const int nunits = nsp * NT;
-        // units are dealt round-robin to the warps in cost order: a fixed assignment, so every
-        // tile result is bitwise reproducible (all ranks must derive the same Schwarz table)
-        for (int u = warp; u < nunits; u += nw) {
-            const int tk = u % NT;
-            const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-            if (nket == 0) continue;
-            const SPRec sp = A.sps[P.sp_beg[0] + u / NT];
-            if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;      // nothing in this class can matter
-            const int cls = sp.type * NPTYPE + tk;
-            double H[HM];
+        for (int tb = 0; tb < NT; ++tb) {
+            const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb];
+            if (nspb == 0) continue;
+            for (int tk = 0; tk < NT; ++tk) {
+                const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+                if (nket == 0 || !(P.kwmax[tb] * Q.kwmax[tk] >= A.tau)) continue;   // nothing in this class can matter
+                const int cls = tb * NPTYPE + tk;
+                unsigned long long npq = 0ull;
+                for (int i = warp; i < nspb; i += nw) {
+                    const SPRec sp = A.sps[P.sp_beg[tb] + i];
+                    if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
+                    double H[HM];
 #pragma unroll
-            for (int e = 0; e < HM; ++e) H[e] = 0.0;
-            unsigned long long npq = 0ull;
-            for (int base = 0; base < nket; base += 32) {
-                // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
-                if (!(sp.wmax * A.pp_wseg[Q.pp_beg[tk] + base] >= A.tau)) break;
-                switch (cls) {
+                    for (int e = 0; e < HM; ++e) H[e] = 0.0;
+                    unsigned long long n0 = npq;
+                    for (int base = 0; base < nket; base += 32) {
+                        // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
+                        if (!(sp.wmax * A.pp_wseg[Q.pp_beg[tk] + base] >= A.tau)) break;
+                        switch (cls) {
 #define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, Q, base, nket, lane, Dq, H, npq); break;
-                    VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
-                    VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
-                    VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
+                            VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
+                            VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
+                            VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
 #undef VB_CASE
-                    default:
-                        if constexpr (GEN) batch_generic(A, sp.type, tk, sp, Q, base, nket, lane, Dq, H, scratch, npq);
-                        break;
+                            default:
+                                if constexpr (GEN) batch_generic(A, tb, tk, sp, Q, base, nket, lane, Dq, H, scratch, npq);
+                                break;
+                        }
+                    }
+                    if (__shfl_sync(0xffffffffu, npq != n0 ? 1 : 0, 0) && lane < Q.np) {
+                        switch (pt_ne(tb)) {
+                            case 1: add_rows<1>(Hs, sp.eoff, H, lane); break;
+                            case 3: add_rows<3>(Hs, sp.eoff, H, lane); break;
+                            case 9: add_rows<9>(Hs, sp.eoff, H, lane); break;
+                            default:
+                                if constexpr (GEN)
+                                    for (int e = 0; e < pt_ne(tb); ++e) Hs[(sp.eoff + e) * 32 + lane] += H[e];
+                                break;
+                        }
+                    }
                 }
+                if (lane == 0 && npq) atomicAdd(&s_pq[cls], npq);
             }
-            if (!__any_sync(0xffffffffu, npq != 0ull)) continue;   // nothing survived the magnitude cut
-            if (lane == 0) atomicAdd(&s_pq[cls], npq);
-            // second half transformation into the warp-private tile: G[p][q] += sum_e Dp[eoff+e][p] H[e]
-            if (lane < Q.np) {
-                const double* Dp = A.dmat + P.d_off + (size_t)sp.eoff * P.np;
-                const int ne = pt_ne(sp.type);
-                for (int p = 0; p < P.np; ++p) {
-                    double g = 0.0;
-#pragma unroll
-                    for (int e = 0; e < HM; ++e)
-                        if (e < ne) g += Dp[e * P.np + p] * H[e];
-                    Gw[p * 32 + lane] += g;
-                }
-            }
-        }
-        __syncthreads();
-        // fold the warp-private tiles into warp 0's
-        for (int i = tid; i < 32 * 32; i += TILE_THREADS) {
-            double g = 0.0;
-#pragma unroll
-            for (int w = 0; w < TILE_THREADS / 32; ++w) g += Gt[w * (32 * 32) + i];
-            Gt[i] = g;
         }
         __syncthreads();
 
@@ -238,9 +242,22 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
         for (int idx = tid; idx < P.np * Q.np; idx += TILE_THREADS) {
             const int p = idx / Q.np, q = idx % Q.np;
             if (diag_tile && q > p) continue;
-            const double G = Gt[p * 32 + q];
             const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
             const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
+            if (A.mode == 0 && !(diag_tile && p == q)) continue;
+            bool ssig = true;
+            if (A.mode == 1) {
+                // reference screen on the Schwarz product (valence.F90:1189-1190); screened entries
+                // contribute nothing and are counted nowhere, so their integral is not even formed
+                ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
+                if (!ssig) continue;
+            }
+            // second half transformation for this entry: (st|uv) = sum_e Dp[e][p] Hs[e][q]
+            double G = 0.0;
+            {
+                const double* Dp = A.dmat + P.d_off + p;
+                for (int e = 0; e < P.ne; ++e) G += Dp[(size_t)e * P.np] * Hs[e * 32 + q];
+            }
             if (A.mode == 0) {
                 if (diag_tile && p == q) {
                     A.diag[(size_t)s * nso + t] = G;
@@ -260,10 +277,6 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
                 }
                 continue;
             }
-            // reference screens: Schwarz product, then the value itself
-            const double sprod = A.sch[s * nso + t] * A.sch[u * nso + v];
-            const bool ssig = sprod > A.itol;
-            if (!ssig) continue;       // screened: contributes nothing and is counted nowhere
             // images of (s,t,u,v) under the integral's permutational symmetry
             int im[8][4];
             int nim = 0;
