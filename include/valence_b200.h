@@ -82,6 +82,10 @@ int vb_engine_energy(vb_engine* e, vb_energy_result* out);
  * doubles at vb_engine_accum_device() over ranks (one NCCL all-reduce); every rank calls _finish. */
 int vb_engine_energy_partial(vb_engine* e, int rank, int nranks, vb_energy_result* out);
 int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out);
+/* first_order_opt matrices (valence.F90:527-764) of 1-based orbital iorb: ham/ovl receive the
+ * norbas x norbas column-major matrices <Psi[chi_ib]|H_el|Psi[chi_jb]>, <Psi[chi_ib]|Psi[chi_jb]>
+ * (numerators: not divided by the norm, no nuclear repulsion); cap = doubles available in each. */
+int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int cap, int* norbas, vb_energy_result* stats);
 double* vb_engine_accum_device(const vb_engine* e);
 int vb_engine_accum_len(const vb_engine* e);
 void* vb_engine_stream(const vb_engine* e);

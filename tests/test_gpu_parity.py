@@ -183,3 +183,54 @@ def test_reference_compatible_c_abi_and_cli(write_input, tmp_path):
         lib.valence_api_finalize_(ctypes.byref(one))
     finally:
         del os.environ["VALENCE_INPUT"]
+
+
+SC_CASES = ["examples__h2.sz", "examples__h2.dz", "examples__he1s2s", "examples__be.sv", "examples__be.2SC",
+            "examples__be2s3s.2SC", "examples__h2o.SC", "examples__lih.SCval", "examples__lih.exstate",
+            "testing__lih", "testing__lih-sv", "testing__h2o-vdz-sc1", "testing__be-sc", "testing__be-scv3s+2sc"]
+
+
+@pytest.mark.parametrize("name", SC_CASES)
+def test_spin_coupled_energies_match_oracle(name, write_input):
+    """Rumer pairs / several spin couplings: Nsc^2 4^Np determinant pairs (valence.F90:1574-1588)."""
+    path, gold = write_input(name)
+    inp, _ = load_golden(name)
+    r, ro = gpu_and_oracle(path)
+    tol = 1e-10 if inp.ntol_d >= 16 else 1e-7
+    assert abs(r["energy"] - ro["energy"]) < tol
+    assert abs(r["energy"] - gold["guess_energy"]) < max(tol, 2e-10)
+    for k in EXACT:
+        assert r["counters"][k] == ro["counters"][k], k
+
+
+def test_spin_coupled_water_cluster(write_input):
+    """Synthetic (H2O)_2 with the OH bonds of the first molecule spin coupled."""
+    from valence_b200 import inputs
+    path, _ = write_input(inputs.water_cluster(2, tol=(10, 20, 10), sc_molecules=1))
+    r, ro = gpu_and_oracle(path)
+    assert abs(r["energy"] - ro["energy"]) < 1e-10
+
+
+FIRST_ORDER = [("examples__h2o", 1), ("examples__h2o", 4), ("examples__li", 1), ("examples__li", 2),
+               ("examples__be.2SC", 1), ("examples__be.DBF", 2), ("examples__cu+.3d94s1", 1), ("examples__cu+.3d94s1", 5),
+               ("examples__ch4", 2), ("examples__h2o.SC", 3), ("examples__lih.SCval", 1), ("examples__fe3+", 3)]
+
+
+@pytest.mark.parametrize("name,iorb", FIRST_ORDER)
+def test_first_order_matrices_match_oracle(name, iorb, write_input):
+    """The "orbital gradient" accumulators of first_order_opt (valence.F90:527-764):
+    ham(ib,jb), ovl(ib,jb) to 1e-8 (BASELINE.json north_star); includes singular substituted
+    overlap blocks (atoms), DBF terms, the spin-average pass and d shells."""
+    from valence_b200 import api
+    from oracle.oracle import Oracle
+    path, _ = write_input(name)
+    o = Oracle(path)
+    Ho, So, _ = o.first_order(iorb)
+    o.close()
+    eng = api.Engine(path)
+    Hg, Sg, _ = eng.first_order(iorb)
+    eng.close()
+    assert Hg.shape == Ho.shape
+    assert np.abs(Hg - Ho).max() < 1e-8
+    assert np.abs(Sg - So).max() < 1e-8
+    assert np.allclose(Hg, Hg.T, atol=0) and np.allclose(Sg, Sg.T, atol=0)

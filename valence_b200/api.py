@@ -74,6 +74,7 @@ def load(build_if_needed: bool = True):
     L.vb_engine_accum_len.argtypes = [C.c_void_p]
     L.vb_engine_stream.restype = C.c_void_p
     L.vb_engine_stream.argtypes = [C.c_void_p]
+    L.vb_engine_first_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(CEnergyResult)]
     L.vb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -130,6 +131,17 @@ class Engine:
         r = CEnergyResult()
         self._check(self.L.vb_engine_energy(self.h, C.byref(r)))
         return r.asdict()
+
+    def first_order(self, iorb: int):
+        """ham, ovl (norbas x norbas) of first_order_opt for 1-based orbital iorb, plus run statistics."""
+        cap = 64 * 64
+        ham = np.zeros(cap)
+        ovl = np.zeros(cap)
+        n = C.c_int(0)
+        r = CEnergyResult()
+        self._check(self.L.vb_engine_first_order(self.h, iorb, ham.ctypes.data, ovl.ctypes.data, cap, C.byref(n), C.byref(r)))
+        k = n.value
+        return ham[:k * k].reshape(k, k).T.copy(), ovl[:k * k].reshape(k, k).T.copy(), r.asdict()
 
     # --- sharded form (one process per GPU) ---------------------------------
     def energy_partial(self, rank: int, nranks: int) -> CEnergyResult:

@@ -5,7 +5,9 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "../../include/valence_b200.h"
 #include "vb_engine.h"
@@ -147,6 +149,20 @@ int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out)
         r.min_pivot_ratio = out->min_pivot_ratio; r.enucrep = out->enucrep; r.e1 = out->e1; r.wfnorm = out->wfnorm;
         e->eng->energy_finish(&r);
         to_c(r, out);
+    });
+}
+
+int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int cap, int* norbas, vb_energy_result* stats)
+{
+    return guarded([&] {
+        std::vector<double> h, s;
+        vb::EnergyResult r;
+        int n = e->eng->first_order(iorb - 1, &h, &s, &r);
+        *norbas = n;
+        if (n * n > cap) throw std::runtime_error("first_order: output buffers too small");
+        std::copy(h.begin(), h.end(), ham);
+        std::copy(s.begin(), s.end(), ovl);
+        if (stats) to_c(r, stats);
     });
 }
 

@@ -12,6 +12,7 @@
 #include <numeric>
 #include <stdexcept>
 
+#include "vb_cofactor.h"
 #include "vb_kernels.cuh"
 #include "vb_tile.cuh"
 
@@ -113,6 +114,14 @@ struct Engine::Impl {
     DBuf<int> pp_eoff;
     DBuf<double> pp_wseg;
     // state carried from energy_partial to energy_finish
+    Basis bas;
+    std::vector<ExpOrb> orbs1e, orbs2e;
+    std::vector<std::vector<double>> cnorm;          // normalised weights of the current call
+    DBuf<double> cof;
+    double dtol = 0, itol = 0;
+    void prepare(const Input& in, int subject);
+    void evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only, int rank, int nranks,
+                  EnergyResult* out, std::vector<double>* sch_out);
     double enuc = 0, e1 = 0, wfnorm = 0;
     double tau = 1e-22;   // primitive-quartet magnitude cut; VB_PRIM_TAU overrides
     int launches = 0;
@@ -192,24 +201,20 @@ void build_csr(const Basis& bas, const std::vector<ExpOrb>& orbs, std::vector<in
 
 }  // namespace
 
-void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
+// Everything that depends only on geometry and orbital weights (valence.F90:71-145): basis,
+// nuclear repulsion, AO one-electron matrices, normalised orbitals and their expansions.
+// subject >= 0 appends one single-AO orbital per expansion term of orbital `subject`
+// (the dummy orbitals of first_order_opt, valence.F90:619-664), ids norbs, norbs+1, ...
+void Engine::Impl::prepare(const Input& in, int subject)
 {
-    Impl& I = *impl_;
-    CK(cudaSetDevice(I.device));
-    cudaStream_t st = I.st;
-    *out = EnergyResult();
-    I.launches = 0;
-    I.t_begin = now_ms();
-    g_h2d_bytes = 0; g_d2h_bytes = 0;
-    const Input& in = in_;
+    CK(cudaSetDevice(device));
     const int norbs = in.norbs(), nval = norbs - in.ndf;
-    if (in.npair > 0) throw std::runtime_error("valence_b200: spin-coupled pairs are not supported by this build of the GPU engine");
-
-    // ---- geometry, basis, nuclear repulsion (valence.F90:71-93) ------------------------------
     std::vector<double> xyz(3 * in.natom);
-    for (int i = 0; i < 3 * in.natom; ++i) xyz[i] = I.xyz_angs[i] * ANGS2BOHR;
-    Basis bas = build_basis(in, xyz);
-    I.enuc = nuclear_repulsion(in, xyz);
+    for (int i = 0; i < 3 * in.natom; ++i) xyz[i] = xyz_angs[i] * ANGS2BOHR;
+    bas = build_basis(in, xyz);
+    enuc = nuclear_repulsion(in, xyz);
+    dtol = std::pow(10.0, -in.ntol_d);
+    itol = std::pow(10.0, -in.ntol_i);
     const int nao = bas.nao, nshell = (int)bas.shells.size();
     {
         std::vector<DevShell> ds(nshell);
@@ -222,130 +227,156 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
             for (int d = 0; d < 3; ++d) nuc[4 * a + d] = xyz[3 * a + d];
             nuc[4 * a + 3] = in.types[in.atom_t[a] - 1].charge;
         }
-        I.shells.upload(ds, st); I.exps.upload(bas.exps, st); I.coefs.upload(bas.coefs, st); I.nuc.upload(nuc, st);
+        shells.upload(ds, st); exps.upload(bas.exps, st); coefs.upload(bas.coefs, st); this->nuc.upload(nuc, st);
     }
-    double t0 = now_ms();
-    // ---- AO one-electron matrices ------------------------------------------------------------
-    I.S.alloc((size_t)nao * nao); I.H.alloc((size_t)nao * nao);
+    S.alloc((size_t)nao * nao); H.alloc((size_t)nao * nao);
     {
         long long npair = (long long)nshell * (nshell + 1) / 2;
         int bs = 64;
-        k_ao_1e<<<(unsigned)((npair + bs - 1) / bs), bs, 0, st>>>(I.shells.p, nshell, I.exps.p, I.coefs.p, I.nuc.p, in.natom, I.boys.p, nao, I.S.p, I.H.p);
+        k_ao_1e<<<(unsigned)((npair + bs - 1) / bs), bs, 0, st>>>(shells.p, nshell, exps.p, coefs.p, this->nuc.p, in.natom, boys.p, nao, S.p, H.p);
         CK(cudaGetLastError());
-        I.launches++;
+        launches++;
     }
-    // ---- normalise DBFs, then orbitals (valence.F90:144-145, normal :2157-2182) --------------
-    reset_orbitals();
+    // normalise DBFs, then orbitals (valence.F90:144-145, normal :2157-2182); the raw weights stay untouched
+    cnorm = coeff;
     auto self_overlaps = [&](int lo, int hi) {
         if (hi <= lo) return;
         std::vector<ExpOrb> ex;
-        for (int o = lo; o < hi; ++o) ex.push_back(expand_orbital(in, bas, I.coeff, o));
+        for (int o = lo; o < hi; ++o) ex.push_back(expand_orbital(in, bas, cnorm, o));
         std::vector<int> ptr, ao;
         std::vector<double> c;
         build_csr(bas, ex, &ptr, &ao, &c);
         std::vector<int2> prs;
         for (int o = 0; o < hi - lo; ++o) prs.push_back(make_int2(o, o));
-        I.optr.upload(ptr, st); I.oao.upload(ao, st); I.oc.upload(c, st); I.opairs.upload(prs, st);
-        I.one_e.alloc(prs.size());
-        k_orb_1e<<<(unsigned)((prs.size() + 127) / 128), 128, 0, st>>>(I.optr.p, I.oao.p, I.oc.p, I.opairs.p, (int)prs.size(), nao, I.S.p, nullptr, I.one_e.p, nullptr);
+        optr.upload(ptr, st); oao.upload(ao, st); oc.upload(c, st); opairs.upload(prs, st);
+        one_e.alloc(prs.size());
+        k_orb_1e<<<(unsigned)((prs.size() + 127) / 128), 128, 0, st>>>(optr.p, oao.p, oc.p, opairs.p, (int)prs.size(), nao, S.p, nullptr, one_e.p, nullptr);
         CK(cudaGetLastError());
-        I.launches++;
-        std::vector<double> s;
-        I.one_e.download(s, st);
+        launches++;
+        std::vector<double> sv;
+        one_e.download(sv, st);
         for (int o = lo; o < hi; ++o) {
-            double f = std::pow(s[o - lo], -0.5);
-            for (double& w : I.coeff[o]) w = w * f;
+            double f = std::pow(sv[o - lo], -0.5);
+            for (double& w : cnorm[o]) w = w * f;
         }
     };
     self_overlaps(nval, norbs);
     self_overlaps(0, nval);
-
-    // ---- wavefunction lists (guess_energy, valence.F90:324-336) ------------------------------
-    Wavefunction wf;
-    wf.nnd = in.nnd();
-    wf.nso = wf.nnd + in.ndocc;
-    wf.sym = true;
-    for (int i = 0; i < wf.nnd; ++i) { wf.bra.push_back(i); wf.ket.push_back(i); }
-    for (int d = 0; d < in.ndocc; ++d) for (int k = 0; k < 2; ++k) { wf.bra.push_back(wf.nnd + d); wf.ket.push_back(wf.nnd + d); }
-    const int nso = wf.nso, nelec = in.nelec();
-
-    // ---- orbital expansions: full (1e) and weight-screened (2e, valence.F90:3296-3348) -------
-    const double dtol = std::pow(10.0, -in.ntol_d), itol = std::pow(10.0, -in.ntol_i);
-    std::vector<ExpOrb> orbs1e(norbs), orbs2e(norbs);
-    for (int o = 0; o < norbs; ++o) {
-        orbs1e[o] = expand_orbital(in, bas, I.coeff, o);
+    // orbital expansions: full (1e) and weight-screened (2e, valence.F90:3296-3348)
+    orbs1e.assign(norbs, ExpOrb());
+    for (int o = 0; o < norbs; ++o) orbs1e[o] = expand_orbital(in, bas, cnorm, o);
+    if (subject >= 0) {
+        const OrbitalDef& od = in.orbitals[subject];
+        for (size_t ib = 0; ib < od.xp.size(); ++ib) {
+            ExpOrb d;
+            int gs = 0, cmp = 0;
+            if (od.xp[ib] >= 1 && obs_position(in, bas, subject, od.xp[ib], &gs, &cmp)) {
+                OrbShell os;
+                os.gshell = gs;
+                std::memset(os.c, 0, sizeof os.c);
+                os.c[cmp] = 1.0;
+                d.sh.push_back(os);
+            }
+            orbs1e.push_back(d);   // a DBF term leaves a null orbital here (valence.F90:616-617)
+        }
+    }
+    orbs2e.assign(orbs1e.size(), ExpOrb());
+    for (size_t o = 0; o < orbs1e.size(); ++o)
         for (const OrbShell& s : orbs1e[o].sh) {
             double sum = 0.0;
             for (int k = 0; k < ncart(bas.shells[s.gshell].l); ++k) sum = sum + s.c[k] * s.c[k];
             if (sum > dtol) orbs2e[o].sh.push_back(s);
         }
-    }
-    // ---- entry-level overlap and core-Hamiltonian matrices (wfndet :1440-1480, 1e loop :1072) -
     {
         std::vector<int> ptr, ao;
         std::vector<double> c;
         build_csr(bas, orbs1e, &ptr, &ao, &c);
+        optr.upload(ptr, st); oao.upload(ao, st); oc.upload(c, st);
+    }
+}
+
+// One vsvb_energy evaluation (valence.F90:1010-1434) for the bra/ket lists in wf.
+//   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
+//             valence.F90:667 vs 674-704); null -> run the diagonal pass (schwarz_ints)
+//   diag_only: stop after the Schwarz table (returned in sch_out)
+void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only,
+                            int rank, int nranks, EnergyResult* out, std::vector<double>* sch_out)
+{
+    const int nso = wf.nso, nelec = in.nelec(), nao = bas.nao;
+    double t1 = now_ms();
+    // ---- entry-level overlap and core-Hamiltonian matrices (wfndet :1440-1480, 1e loop :1072) ----
+    {
         std::vector<int2> prs((size_t)nso * nso);
         for (int s = 0; s < nso; ++s)
             for (int t = 0; t < nso; ++t) prs[(size_t)s * nso + t] = make_int2(wf.bra[wf.slot(s, 0)], wf.ket[wf.slot(t, 0)]);
-        I.optr.upload(ptr, st); I.oao.upload(ao, st); I.oc.upload(c, st); I.opairs.upload(prs, st);
-        I.Se.alloc(prs.size()); I.He.alloc(prs.size());
-        k_orb_1e<<<(unsigned)((prs.size() + 127) / 128), 128, 0, st>>>(I.optr.p, I.oao.p, I.oc.p, I.opairs.p, (int)prs.size(), nao, I.S.p, I.H.p, I.Se.p, I.He.p);
+        opairs.upload(prs, st);
+        Se.alloc(prs.size()); He.alloc(prs.size());
+        k_orb_1e<<<(unsigned)((prs.size() + 127) / 128), 128, 0, st>>>(optr.p, oao.p, oc.p, opairs.p, (int)prs.size(), nao, S.p, H.p, Se.p, He.p);
         CK(cudaGetLastError());
-        I.launches++;
+        launches++;
     }
-    double t1 = now_ms();
-    // ---- spin-block inverses and entry-level densities ---------------------------------------
-    // alpha block: unpaired entries then DOCC entries; beta block: DOCC entries (valence.F90:2461-2480)
-    std::vector<int> ea, eb, posa(nso, -1), posb(nso, -1);
-    for (int s = 0; s < nso; ++s) { posa[s] = (int)ea.size(); ea.push_back(s); }
-    for (int s = wf.nnd; s < nso; ++s) { posb[s] = (int)eb.size(); eb.push_back(s); }
-    const int na = (int)ea.size(), nb = (int)eb.size();
-    I.ea_bra.upload(ea, st); I.eb_bra.upload(eb, st); I.posa_bra.upload(posa, st); I.posb_bra.upload(posb, st);
-    I.Ma.alloc((size_t)na * na + 1); I.Mb.alloc((size_t)nb * nb + 1);
-    if (na) { k_gather_block<<<(na * na + 255) / 256, 256, 0, st>>>(I.Se.p, nso, I.ea_bra.p, I.ea_bra.p, na, I.Ma.p); I.launches++; }
-    if (nb) { k_gather_block<<<(nb * nb + 255) / 256, 256, 0, st>>>(I.Se.p, nso, I.eb_bra.p, I.eb_bra.p, nb, I.Mb.p); I.launches++; }
-    CK(cudaGetLastError());
-    double deta = 1.0, detb = 1.0;
-    {
-        // two independent launches (the matrices live in separate buffers)
-        std::vector<long long> z = {0};
-        I.gj_off.upload(z, st); I.gj_poff.upload(z, st);
-        I.piv.alloc((size_t)std::max(na, nb) * 2 + 2);
-        I.gjout.alloc(4);
-        I.gj_n.upload(std::vector<int>{na, nb}, st);
-        k_gj_inverse<<<1, 1024, 0, st>>>(I.Ma.p, I.gj_n.p, I.gj_off.p, I.piv.p, I.gj_poff.p, I.gjout.p);
-        k_gj_inverse<<<1, 1024, 0, st>>>(I.Mb.p, I.gj_n.p + 1, I.gj_off.p, I.piv.p + std::max(na, nb) + 1, I.gj_poff.p, I.gjout.p + 2);
-        CK(cudaGetLastError());
-        I.launches += 2;
-        std::vector<double> g;
-        I.gjout.download(g, st);
-        deta = g[0]; detb = g[2];
-        out->min_pivot_ratio = std::min(g[1], g[3]);
-        if (!(deta != 0.0) || !(detb != 0.0) || out->min_pivot_ratio < 1e-13)
-            throw std::runtime_error("valence_b200: singular spin-block overlap matrix (linearly dependent orbitals)");
-    }
-    I.Pa.alloc((size_t)nso * nso); I.Pb.alloc((size_t)nso * nso);
-    k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(I.Ma.p, na, I.posa_bra.p, I.posa_bra.p, nso, I.Pa.p);
-    k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(I.Mb.p, nb, I.posb_bra.p, I.posb_bra.p, nso, I.Pb.p);
-    I.one_e.alloc(2);
-    k_one_electron_energy<<<1, 1024, 0, st>>>(I.Se.p, I.He.p, I.Pa.p, I.Pb.p, nso * nso, I.one_e.p);
-    CK(cudaGetLastError());
-    I.launches += 3;
-    const double c0 = deta * detb;
-    {
-        std::vector<double> oe;
-        I.one_e.download(oe, st);
-        I.e1 = c0 * oe[0];
-        I.wfnorm = c0 * oe[1] / (double)nelec;    // valence.F90:1106
+    // ---- cofactor densities ------------------------------------------------------------------------
+    const int na = in.nalpha(), nb = in.nbeta();
+    const bool fast = in.npair == 0 && wf.sym && std::max(na, nb) > 64;   // large closed/open-shell single determinant
+    double c0 = 1.0;
+    int ndp = 0;
+    if (!diag_only) {
+        if (fast) {
+            // alpha block: unpaired entries then DOCC entries; beta block: DOCC entries (valence.F90:2461-2480)
+            std::vector<int> ea, eb, posa(nso, -1), posb(nso, -1);
+            for (int s = 0; s < nso; ++s) { posa[s] = (int)ea.size(); ea.push_back(s); }
+            for (int s = wf.nnd; s < nso; ++s) { posb[s] = (int)eb.size(); eb.push_back(s); }
+            ea_bra.upload(ea, st); eb_bra.upload(eb, st); posa_bra.upload(posa, st); posb_bra.upload(posb, st);
+            Ma.alloc((size_t)na * na + 1); Mb.alloc((size_t)nb * nb + 1);
+            if (na) { k_gather_block<<<(na * na + 255) / 256, 256, 0, st>>>(Se.p, nso, ea_bra.p, ea_bra.p, na, Ma.p); launches++; }
+            if (nb) { k_gather_block<<<(nb * nb + 255) / 256, 256, 0, st>>>(Se.p, nso, eb_bra.p, eb_bra.p, nb, Mb.p); launches++; }
+            CK(cudaGetLastError());
+            std::vector<long long> z = {0};
+            gj_off.upload(z, st); gj_poff.upload(z, st);
+            piv.alloc((size_t)std::max(na, nb) * 2 + 2);
+            gjout.alloc(4);
+            gj_n.upload(std::vector<int>{na, nb}, st);
+            k_gj_inverse<<<1, 1024, 0, st>>>(Ma.p, gj_n.p, gj_off.p, piv.p, gj_poff.p, gjout.p);
+            k_gj_inverse<<<1, 1024, 0, st>>>(Mb.p, gj_n.p + 1, gj_off.p, piv.p + std::max(na, nb) + 1, gj_poff.p, gjout.p + 2);
+            CK(cudaGetLastError());
+            launches += 2;
+            std::vector<double> g;
+            gjout.download(g, st);
+            out->min_pivot_ratio = std::min(g[1], g[3]);
+            if (!(g[0] != 0.0) || !(g[2] != 0.0) || out->min_pivot_ratio < 1e-13)
+                throw std::runtime_error("valence_b200: singular spin-block overlap matrix (linearly dependent orbitals)");
+            c0 = g[0] * g[2];
+            Pa.alloc((size_t)nso * nso); Pb.alloc((size_t)nso * nso);
+            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Ma.p, na, posa_bra.p, posa_bra.p, nso, Pa.p);
+            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mb.p, nb, posb_bra.p, posb_bra.p, nso, Pb.p);
+            one_e.alloc(2);
+            k_one_electron_energy<<<1, 1024, 0, st>>>(Se.p, He.p, Pa.p, Pb.p, nso * nso, one_e.p);
+            CK(cudaGetLastError());
+            launches += 3;
+            std::vector<double> oe;
+            one_e.download(oe, st);
+            e1 = c0 * oe[0];
+            wfnorm = c0 * oe[1] / (double)nelec;    // valence.F90:1106
+        } else {
+            // small blocks / several determinant pairs / possibly singular blocks: factorise on the host
+            // (O(n^3) once per determinant pair, n <= 64), contract on the GPU
+            std::vector<double> hSe, hHe;
+            Se.download(hSe, st); He.download(hHe, st);
+            CofactorSet cs;
+            build_cofactors(in, wf, hSe, &cs);
+            one_electron_from_cofactors(cs, hSe, hHe, nelec, &e1, &wfnorm);
+            out->min_pivot_ratio = cs.min_sigma_ratio;
+            cof.upload(cs.data, st);
+            ndp = cs.ndp;
+        }
     }
     double t2 = now_ms();
 
-    // ---- pair groups, shell-pair tables, folded densities ------------------------------------
-    TileSetup ts;
+    // ---- pair groups, shell-pair tables, folded densities ---------------------------------------------
     // magnitude cuts: the Schwarz (diagonal) pass must resolve (st|st) down to itol^2, the energy pass
     // needs the integrals to ~itol; never looser than the configured tau
-    const double tau_diag = std::min(I.tau, 0.01 * itol * itol), tau_energy = std::min(I.tau, 0.01 * itol);
+    const double tau_diag = std::min(tau, 0.01 * itol * itol), tau_energy = std::min(tau, 0.01 * itol);
+    TileSetup ts;
     build_tiles(in, bas, wf, orbs2e, tau_diag, &ts);
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
@@ -357,48 +388,60 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
         nshb[s] = (int)orbs2e[wf.bra[wf.slot(s, 0)]].sh.size();
         nshk[s] = (int)orbs2e[wf.ket[wf.slot(s, 0)]].sh.size();
     }
-    I.pgs.upload(ts.pgs, st); I.pg_pairs.upload(ts.pg_pairs, st); I.sps.upload(ts.sps, st); I.pp_eoff.upload(ts.pp_eoff, st); I.pp_wseg.upload(ts.pp_wseg, st);
-    I.pps.upload(ts.pps, st); I.dmat.upload(ts.dmat, st); I.nsh_bra.upload(nshb, st); I.nsh_ket.upload(nshk, st);
-    I.counter.alloc(1); I.counters.alloc(CNT_N); I.pq_counters.alloc(NPTYPE * NPTYPE);
+    pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st); pp_eoff.upload(ts.pp_eoff, st); pp_wseg.upload(ts.pp_wseg, st);
+    pps.upload(ts.pps, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
+    counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
     const bool gen = ts.lmax >= 2;
-    int grid_cap = I.nsm * 2;
-    if (gen) { grid_cap = std::min(grid_cap, 64); I.gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
+    int grid_cap = nsm * 2;
+    if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
     if (gen) CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
-    A.pgs = I.pgs.p; A.pg_pairs = I.pg_pairs.p; A.sps = I.sps.p; A.pps = I.pps.p; A.pp_eoff = I.pp_eoff.p; A.pp_wseg = I.pp_wseg.p; A.tau = tau_diag; A.pq_counters = I.pq_counters.p; A.dmat = I.dmat.p;
-    A.boys = I.boys.p; A.counter = I.counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = -1;
-    A.dq_cap = dq_cap; A.itol = itol; A.Pa = I.Pa.p; A.Pb = I.Pb.p; A.c0 = c0; A.nsh_bra = I.nsh_bra.p; A.nsh_ket = I.nsh_ket.p;
-    A.counters = I.counters.p; A.gen_scratch = I.gen_scratch.p;
+    A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pp_eoff = pp_eoff.p; A.pp_wseg = pp_wseg.p; A.tau = tau_diag;
+    A.pq_counters = pq_counters.p; A.dmat = dmat.p;
+    A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
+    A.dq_cap = dq_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
+    A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     auto launch = [&](int ntiles_mine) {
         int grid = std::max(1, std::min(grid_cap, ntiles_mine));
         if (gen) k_tile<true><<<grid, TILE_THREADS, smem, st>>>(A);
         else k_tile<false><<<grid, TILE_THREADS, smem, st>>>(A);
         CK(cudaGetLastError());
-        I.launches++;
+        launches++;
     };
     double t3 = now_ms();
-    // ---- diagonal pass: (st|st) for every pair -> Schwarz table (schwarz_ints, :1489-1523) ----
-    std::vector<double> diag;
-    {
+    // ---- diagonal pass: (st|st) for every pair -> Schwarz table (schwarz_ints, :1489-1523) ------------
+    std::vector<double> sch;
+    if (sch_in) {
+        sch = *sch_in;
+    } else {
+        std::vector<double> dg;
         std::vector<int2> dt(npg);
         for (int i = 0; i < npg; ++i) dt[i] = make_int2(i, i);
-        I.tiles.upload(dt, st);
-        I.diag.alloc((size_t)nso * nso);
-        I.diag.zero(st); I.counter.zero(st);
-        A.tiles = I.tiles.p; A.ntiles = npg; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = I.diag.p;
-        CK(cudaEventRecord(I.ev0, st));
+        tiles.upload(dt, st);
+        diag.alloc((size_t)nso * nso);
+        diag.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
+        A.tiles = tiles.p; A.ntiles = npg; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
+        CK(cudaEventRecord(ev0, st));
         launch(npg);
-        CK(cudaEventRecord(I.ev1, st));
-        out->diag_launches = 1;
-        I.diag.download(diag, st);
+        CK(cudaEventRecord(ev1, st));
+        out->diag_launches++;
+        diag.download(dg, st);
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        out->t_diag += ms;
+        // reference table: schwarz(indx(i,j)) = sqrt((bra_i ket_j|bra_i ket_j)), i >= j, looked up symmetrically
+        sch.resize((size_t)nso * nso);
+        for (int s = 0; s < nso; ++s)
+            for (int t = 0; t < nso; ++t) sch[(size_t)s * nso + t] = std::sqrt(dg[(size_t)std::max(s, t) * nso + std::min(s, t)]);
     }
-    // reference table: schwarz(indx(i,j)) = sqrt((bra_i ket_j|bra_i ket_j)), i >= j, looked up symmetrically
-    std::vector<double> sch((size_t)nso * nso);
-    for (int s = 0; s < nso; ++s)
-        for (int t = 0; t < nso; ++t) sch[(size_t)s * nso + t] = std::sqrt(diag[(size_t)std::max(s, t) * nso + std::min(s, t)]);
+    if (sch_out) *sch_out = sch;
+    out->n_entries = nso; out->n_groups = (long long)ts.groups.size(); out->n_pairgroups = npg;
+    out->t_density += t2 - t1;
+    if (diag_only) { out->t_host_setup += t3 - t2; return; }
     for (PGDesc& pg : ts.pgs) {
         double m = 0.0;
         for (int p = 0; p < pg.np; ++p) {
@@ -407,44 +450,43 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
         }
         pg.smax = m;
     }
-    // ---- tile list: pair-group pairs that can hold a significant integral --------------------
+    // ---- tile list: pair-group pairs that can hold a significant integral ----------------------------
     std::vector<int> order(npg);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ts.pgs[a].smax > ts.pgs[b].smax; });
-    std::vector<int2> tiles;
+    std::vector<int2> tl;
     for (int i = 0; i < npg; ++i) {
         const double si = ts.pgs[order[i]].smax;
         for (int j = i; j < npg; ++j) {
             if (!(si * ts.pgs[order[j]].smax > itol)) break;
             int a = order[i], b = order[j];
-            tiles.push_back(make_int2(std::max(a, b), std::min(a, b)));
+            tl.push_back(make_int2(std::max(a, b), std::min(a, b)));
         }
     }
-    const long long ntiles = (long long)tiles.size();
-    out->n_tiles_mine = 0;
-    for (long long k = rank; k < ntiles; k += nranks) out->n_tiles_mine++;
+    const long long ntiles = (long long)tl.size();
+    long long mine = 0;
+    for (long long k = rank; k < ntiles; k += nranks) mine++;
     double t4 = now_ms();
-    // ---- energy pass ---------------------------------------------------------------------------
-    I.sch.upload(sch, st);
-    I.tiles.upload(tiles, st);
-    I.tileE.alloc((size_t)std::max<long long>(ntiles, 1));
-    I.tileE.zero(st); I.counter.zero(st); I.counters.zero(st); I.pq_counters.zero(st);
-    A.tiles = I.tiles.p; A.ntiles = (int)ntiles; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
-    A.sch = I.sch.p; A.tileE = I.tileE.p;
-    CK(cudaEventRecord(I.ev2, st));
-    if (out->n_tiles_mine > 0) launch((int)out->n_tiles_mine);
-    CK(cudaEventRecord(I.ev3, st));
-    out->tile_launches = out->n_tiles_mine > 0 ? 1 : 0;
-    k_sum<<<1, 1024, 0, st>>>(I.tileE.p, ntiles, I.accum.p);
+    // ---- energy pass ---------------------------------------------------------------------------------
+    this->sch.upload(sch, st);
+    tiles.upload(tl, st);
+    tileE.alloc((size_t)std::max<long long>(ntiles, 1));
+    tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
+    A.tiles = tiles.p; A.ntiles = (int)ntiles; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
+    A.sch = this->sch.p; A.tileE = tileE.p;
+    CK(cudaEventRecord(ev2, st));
+    if (mine > 0) launch((int)mine);
+    CK(cudaEventRecord(ev3, st));
+    out->tile_launches += mine > 0 ? 1 : 0;
+    k_sum<<<1, 1024, 0, st>>>(tileE.p, ntiles, accum.p);
     CK(cudaGetLastError());
-    I.launches++;
+    launches++;
     {
-        // counters -> accumulator tail as doubles (exact below 2^53), one tiny kernel-free copy via host
         std::vector<unsigned long long> c;
-        I.counters.download(c, st);
+        counters.download(c, st);
         // executed primitive quartets per class -> algorithmic flop count of this rank's tile pass
         std::vector<unsigned long long> pq;
-        I.pq_counters.download(pq, st);
+        pq_counters.download(pq, st);
         double fl = 0.0;
         long long npq = 0;
         for (int a = 0; a < NPTYPE; ++a)
@@ -452,19 +494,125 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
                 fl += (double)pq[a * NPTYPE + b] * flops_prim_quartet(a, b);
                 npq += (long long)pq[a * NPTYPE + b];
             }
-        out->flops_model = fl; out->n_prim_quartets = npq;
+        out->flops_model += fl; out->n_prim_quartets += npq;
         std::vector<double> cd(CNT_N);
         for (int i = 0; i < CNT_N; ++i) cd[i] = (double)c[i];
-        CK(cudaMemcpyAsync(I.accum.p + 1, cd.data(), CNT_N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(accum.p + 1, cd.data(), CNT_N * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
     }
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, I.ev0, I.ev1)); out->t_diag = ms;
-    CK(cudaEventElapsedTime(&ms, I.ev2, I.ev3)); out->t_tiles = ms;
-    out->t_host_setup = (t0 - I.t_begin) + (t3 - t2) + (t4 - t3);
-    out->t_1e = t1 - t0; out->t_density = t2 - t1;
-    out->n_entries = nso; out->n_groups = (long long)ts.groups.size(); out->n_pairgroups = npg; out->n_tiles = ntiles;
-    out->enucrep = I.enuc; out->e1 = I.e1; out->wfnorm = I.wfnorm;
+    CK(cudaEventElapsedTime(&ms, ev2, ev3)); out->t_tiles += ms;
+    out->t_host_setup += (t3 - t2) + (t4 - t3);
+    out->n_tiles += ntiles; out->n_tiles_mine += mine;
+    out->enucrep = enuc; out->e1 = e1; out->wfnorm = wfnorm;
+}
+
+namespace {
+
+Wavefunction default_wavefunction(const Input& in)   // guess_energy, valence.F90:324-336
+{
+    Wavefunction wf;
+    wf.nnd = in.nnd();
+    wf.nso = wf.nnd + in.ndocc;
+    wf.sym = true;
+    wf.subject = -1;
+    for (int i = 0; i < wf.nnd; ++i) { wf.bra.push_back(i); wf.ket.push_back(i); }
+    for (int d = 0; d < in.ndocc; ++d) for (int k = 0; k < 2; ++k) { wf.bra.push_back(wf.nnd + d); wf.ket.push_back(wf.nnd + d); }
+    return wf;
+}
+
+}  // namespace
+
+void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
+{
+    Impl& I = *impl_;
+    CK(cudaSetDevice(I.device));
+    *out = EnergyResult();
+    I.launches = 0;
+    I.t_begin = now_ms();
+    g_h2d_bytes = 0; g_d2h_bytes = 0;
+    I.prepare(in_, -1);
+    double t1 = now_ms();
+    out->t_1e = t1 - I.t_begin;
+    Wavefunction wf = default_wavefunction(in_);
+    I.evaluate(in_, wf, nullptr, false, rank, nranks, out, nullptr);
+}
+
+// first_order_opt matrices (valence.F90:527-764) for 0-based orbital `iorb`:
+//   ham(ib,jb) = <Psi[slot e <- chi_ib] | H_el | Psi[slot e <- chi_jb]>, ovl likewise (not divided,
+//   no nuclear repulsion); column-major n x n in ham/ovl (n = # expansion terms of the orbital).
+int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* stats)
+{
+    Impl& I = *impl_;
+    CK(cudaSetDevice(I.device));
+    const Input& in = in_;
+    if (iorb < 0 || iorb >= in.norbs() - in.ndf) throw std::runtime_error("first_order: orbital index out of range");
+    EnergyResult acc;
+    I.launches = 0;
+    I.t_begin = now_ms();
+    g_h2d_bytes = 0; g_d2h_bytes = 0;
+    I.prepare(in, iorb);
+    const int norbs = in.norbs(), nnd0 = in.nnd(), ndocc = in.ndocc;
+    const int norbas = (int)in.orbitals[iorb].xp.size();
+    // wave-function lists (valence.F90:557-605)
+    Wavefunction wf;
+    int eslot;   // 0-based electron slot that is substituted
+    if (iorb < nnd0) {
+        wf = default_wavefunction(in);
+        eslot = iorb;
+    } else {
+        wf.nnd = nnd0 + 2;
+        wf.nso = nnd0 + ndocc + 1;
+        for (int i = 0; i < nnd0; ++i) { wf.bra.push_back(i); wf.ket.push_back(i); }
+        for (int k = 0; k < 2; ++k) { wf.bra.push_back(iorb); wf.ket.push_back(iorb); }
+        for (int d = nnd0; d < nnd0 + ndocc; ++d)
+            if (d != iorb) for (int k = 0; k < 2; ++k) { wf.bra.push_back(d); wf.ket.push_back(d); }
+        eslot = nnd0;
+    }
+    wf.sym = true;
+    wf.subject = -1;
+    // Schwarz table of the unsubstituted lists (valence.F90:666-667); the (ib,jb) loop reuses it
+    std::vector<double> sch;
+    I.evaluate(in, wf, nullptr, true, 0, 1, &acc, &sch);
+    ham->assign((size_t)norbas * norbas, 0.0);
+    ovl->assign((size_t)norbas * norbas, 0.0);
+    const int npass = (in.nunpd > 0 && iorb >= nnd0) ? 2 : 1;   // spin average, valence.F90:709-749
+    for (int pass = 0; pass < npass; ++pass) {
+        Wavefunction w2 = wf;
+        const int es = eslot + pass;              // beta-spin position in the second pass
+        w2.sym = false;
+        w2.subject = es;                          // slot index == entry index for the non-DOCC part of the list
+        for (int ib = 0; ib < norbas; ++ib) {
+            int idf = in.orbitals[iorb].xp[ib];
+            w2.bra[es] = idf < 1 ? norbs + idf - 1 : norbs + ib;
+            for (int jb = 0; jb <= ib; ++jb) {
+                int jdf = in.orbitals[iorb].xp[jb];
+                w2.ket[es] = jdf < 1 ? norbs + jdf - 1 : norbs + jb;
+                EnergyResult r;
+                I.evaluate(in, w2, &sch, false, 0, 1, &r, nullptr);
+                std::vector<double> a(1 + CNT_N);
+                CK(cudaMemcpyAsync(a.data(), I.accum.p, a.size() * sizeof(double), cudaMemcpyDeviceToHost, I.st));
+                CK(cudaStreamSynchronize(I.st));
+                const double num = r.e1 + a[0];
+                (*ham)[(size_t)jb * norbas + ib] += num;
+                (*ovl)[(size_t)jb * norbas + ib] += r.wfnorm;
+                acc.t_tiles += r.t_tiles; acc.flops_model += r.flops_model; acc.n_prim_quartets += r.n_prim_quartets;
+                acc.n_tiles += r.n_tiles; acc.tile_launches += r.tile_launches;
+                for (int i = 0; i < CNT_N; ++i) acc.counters[i] += (long long)(a[1 + i] + 0.5);
+            }
+        }
+    }
+    for (int i = 0; i < norbas; ++i)
+        for (int j = 0; j < i; ++j) {
+            (*ham)[(size_t)i * norbas + j] = (*ham)[(size_t)j * norbas + i];
+            (*ovl)[(size_t)i * norbas + j] = (*ovl)[(size_t)j * norbas + i];
+        }
+    acc.enucrep = I.enuc;
+    acc.launches = I.launches;
+    acc.t_total = now_ms() - I.t_begin;
+    acc.h2d_bytes = g_h2d_bytes; acc.d2h_bytes = g_d2h_bytes;
+    if (stats) *stats = acc;
+    return norbas;
 }
 
 // FP64 FMA peak of this GPU, measured: 8 independent DFMA chains per thread, full occupancy.

@@ -49,7 +49,10 @@ struct TileArgs {
     double itol;
     const double* Pa;                // entry-level alpha / beta densities, nso*nso
     const double* Pb;
-    double c0;                       // det(alpha block) * det(beta block) * coupling weights
+    double c0;                       // det(alpha block) * det(beta block) (fast path), 1 on the general path
+    const double* cof;               // general path: packed cofactor data per determinant pair (vb_cofactor.h)
+    int ndp;                         // # determinant pairs on the general path, 0 = fast path (Pa/Pb/c0)
+    long long cof_stride;
     const int* nsh_bra;              // # shells passing the weight screen, per entry (bra / ket orbital)
     const int* nsh_ket;
     double* tileE;                   // mode 1: per-tile energy partial (deterministic reduction later)

@@ -8,6 +8,7 @@
 //      screens them (valence.F90:1189-1190, 1213-1216, 1286-1287) and contracted with the
 //      cofactor densities; nothing but one double per tile reaches HBM.
 #pragma once
+#include "vb_cofactor.h"
 #include "vb_kernels.cuh"
 
 namespace vb {
@@ -26,6 +27,54 @@ constexpr int TILE_THREADS = 256;
 constexpr int HMAX_UNR = 9;                      // pt_ne(pp)
 constexpr int HMAX_GEN = 31;                     // pt_ne(dd)
 constexpr int GEN_PER_THREAD = GEN_SCRATCH + HMAX_GEN * HMAX_GEN;
+
+// General cofactor weight (vb_cofactor.h): sum over determinant pairs of
+//   C2a C0b + C1a(s,t) C1b(u,v) + C1b(s,t) C1a(u,v) + C0a C2b
+struct CofBlock {
+    double dN, pZ, pw0, pw1;
+    int nz;
+    const double *G, *uz, *vz;
+};
+__device__ __forceinline__ double cof_c1(const CofBlock& B, int nso, int s, int t)
+{
+    double v = B.pZ * B.G[s * nso + t];
+    if (B.nz > 0) v += B.pw0 * B.uz[s] * B.vz[t];
+    if (B.nz > 1) v += B.pw1 * B.uz[nso + s] * B.vz[nso + t];
+    return B.dN * v;
+}
+__device__ __forceinline__ double cof_c2(const CofBlock& B, int nso, int s, int t, int u, int v)
+{
+    const double gst = B.G[s * nso + t], guv = B.G[u * nso + v], gsv = B.G[s * nso + v], gut = B.G[u * nso + t];
+    double r = B.pZ * (gst * guv - gsv * gut);
+    for (int z = 0; z < B.nz; ++z) {
+        const double* uz = B.uz + z * nso;
+        const double* vz = B.vz + z * nso;
+        r += (z == 0 ? B.pw0 : B.pw1) * (vz[v] * uz[u] * gst - vz[v] * uz[s] * gut - vz[t] * uz[u] * gsv + vz[t] * uz[s] * guv);
+    }
+    if (B.nz == 2)
+        r += (B.vz[t] * B.vz[nso + v] - B.vz[nso + t] * B.vz[v]) * (B.uz[s] * B.uz[nso + u] - B.uz[nso + s] * B.uz[u]);
+    return B.dN * r;
+}
+__device__ __noinline__ double w_general(const double* __restrict__ cof, int ndp, long long stride, int nso, int s, int t, int u, int v)
+{
+    double sum = 0.0;
+    for (int d = 0; d < ndp; ++d) {
+        const double* D = cof + (long long)d * stride;
+        CofBlock a, b;
+        a.dN = D[1]; a.pZ = D[2]; a.pw0 = D[3]; a.pw1 = D[4]; a.nz = (int)D[5];
+        b.dN = D[6]; b.pZ = D[7]; b.pw0 = D[8]; b.pw1 = D[9]; b.nz = (int)D[10];
+        a.G = D + COF_HEADER; b.G = a.G + nso * nso;
+        a.uz = b.G + nso * nso; a.vz = a.uz + 2 * nso; b.uz = a.vz + 2 * nso; b.vz = b.uz + 2 * nso;
+        if (a.dN == 0.0 && b.dN == 0.0) continue;
+        const double c0a = a.dN * a.pZ, c0b = b.dN * b.pZ;
+        double w = 0.0;
+        if (c0b != 0.0) w += cof_c2(a, nso, s, t, u, v) * c0b;
+        if (c0a != 0.0) w += cof_c2(b, nso, s, t, u, v) * c0a;
+        w += cof_c1(a, nso, s, t) * cof_c1(b, nso, u, v) + cof_c1(b, nso, s, t) * cof_c1(a, nso, u, v);
+        sum += D[0] * w;
+    }
+    return sum;
+}
 
 // One warp-batch of class (TB|TK): the warp owns bra shell pair `sp`; lane = one ket primitive
 // pair of type TK (flat list, shell pairs contiguous).  Every lane runs the same trip count
@@ -320,7 +369,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
                     cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
                 }
                 if (ssig && shortcut && vd) cnt[CNT_SHORTCUT]++;
-                if (vsig) wsum += val * w_term(A.Pa, A.Pb, nso, a, b, c, d);
+                if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
             }
             (void)stab;
             epart += 0.5 * wsum;
