@@ -24,7 +24,7 @@ static std::vector<PrimPair> pairs(const Sh& A, const Sh& B) {
     for (size_t i = 0; i < A.ex.size(); ++i) for (size_t j = 0; j < B.ex.size(); ++j) {
         double a = A.ex[i], b = B.ex[j], p = a + b; PrimPair pp;
         pp.Px = (a*A.r[0]+b*B.r[0])/p; pp.Py = (a*A.r[1]+b*B.r[1])/p; pp.Pz = (a*A.r[2]+b*B.r[2])/p; pp.p = p;
-        pp.ip = 1.0/p; pp.Kp = A.co[i]*B.co[j]*std::exp(-a*b/p*AB2)*std::sqrt(2.0)*std::pow(PI,1.25)/p; pp.w = 1.0;
+        pp.ip = 1.0/p; pp.Kp = A.co[i]*B.co[j]*std::exp(-a*b/p*AB2)*std::sqrt(2.0)*std::pow(PI,1.25)/p; pp.w = 1.0; pp.wseg = 1.0; pp.eoff = 0; pp.pad = 0;
         pp.PAx = pp.Px-A.r[0]; pp.PAy = pp.Py-A.r[1]; pp.PAz = pp.Pz-A.r[2]; v.push_back(pp);
     }
     return v;

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libvalence_b200.so")
+LIB = os.path.join(HERE, "libvalence_b200" + os.environ.get("VB_LIB_SUFFIX", "") + ".so")
 CLI = os.path.join(HERE, "valence")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -28,7 +28,7 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [NVCC, *FLAGS, "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [NVCC, *FLAGS, *os.environ.get("VB_EXTRA_FLAGS", "").split(), "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:

@@ -111,8 +111,6 @@ struct Engine::Impl {
         DBuf<PrimPair> pps;
     DBuf<unsigned int> counter;
     DBuf<unsigned long long> counters, pq_counters;
-    DBuf<int> pp_eoff;
-    DBuf<double> pp_wseg;
     // state carried from energy_partial to energy_finish
     Basis bas;
     std::vector<ExpOrb> orbs1e, orbs2e;
@@ -381,28 +379,32 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
-    const size_t smem = ((size_t)dq_cap + (size_t)ts.max_ne * 32) * sizeof(double);
-    if (smem > 220 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+    const int dq_cap2 = (dq_cap + 1) & ~1, hs_cap = ts.max_ne * 32, sp_cap = std::max(1, ts.max_nsp);
+    int pp_cap = std::max(1, ts.max_npp);
+    size_t smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
+    if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
+    else pp_cap = 0;   // primitive tables stay in global memory
+    if (smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
     for (int s = 0; s < nso; ++s) {
         nshb[s] = (int)orbs2e[wf.bra[wf.slot(s, 0)]].sh.size();
         nshk[s] = (int)orbs2e[wf.ket[wf.slot(s, 0)]].sh.size();
     }
-    pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st); pp_eoff.upload(ts.pp_eoff, st); pp_wseg.upload(ts.pp_wseg, st);
+    pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
     pps.upload(ts.pps, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
     const bool gen = ts.lmax >= 2;
-    int grid_cap = nsm * 2;
+    int grid_cap = nsm * VB_MINBLOCKS;
     if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
     if (gen) CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
-    A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pp_eoff = pp_eoff.p; A.pp_wseg = pp_wseg.p; A.tau = tau_diag;
+    A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
-    A.dq_cap = dq_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     auto launch = [&](int ntiles_mine) {

@@ -143,13 +143,15 @@ VB_HD void boys_rt(int M, const double* __restrict__ tab, double T, double* F)  
 // ---------------------------------------------------------------------------
 // primitive shell-pair record (64 bytes, staged through shared memory)
 // ---------------------------------------------------------------------------
-struct alignas(16) PrimPair {   // 80 bytes
+struct alignas(16) PrimPair {   // 96 bytes (multiple of 16: moved with cp.async.bulk)
     double Px, Py, Pz;     // Gaussian product centre
     double p;              // a + b
     double ip;             // 1 / p
     double Kp;             // c_a c_b exp(-ab/p |AB|^2) * sqrt(2) pi^(5/4) / p
     double PAx, PAy, PAz;  // P - A, A = centre carrying the angular momentum (la >= lb)
     double w;              // magnitude bound used to skip negligible primitive quartets
+    double wseg;           // largest w of this primitive pair's shell pair (non-increasing within a pair type)
+    int eoff, pad;         // e-offset of the shell pair inside its pair group
 };
 
 struct QuartetGeom {       // everything the VRR needs for one primitive quartet

@@ -31,8 +31,6 @@ struct TileArgs {
     const int* pg_pairs;
     const SPRec* sps;
     const PrimPair* pps;
-    const int* pp_eoff;
-    const double* pp_wseg;
     double tau;                      // primitive-quartet magnitude cut (0 = none)
     unsigned long long* pq_counters; // primitive quartets evaluated, per class tb*NPTYPE+tk
     const double* dmat;
@@ -44,6 +42,7 @@ struct TileArgs {
     int mode;                        // 0 = diagonal (Schwarz) pass, 1 = energy, 2 = export G
     int nso, nnd, sym, subject;
     int dq_cap;                      // doubles reserved for the staged ket density
+    int hs_cap, pp_cap, sp_cap;      // shared-memory capacities: H tile (doubles), primitive pairs per side, shell pairs
     double* diag;                    // mode 0: (s,t) -> (st|st)
     const double* sch;               // mode 1: Schwarz table as the reference indexes it, nso*nso
     double itol;

@@ -354,7 +354,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         for (const TmpSP& sp : tsp) ne += pt_ne(sp.type);
         pg.ne = ne;
         pg.d_off = (long long)ts.dmat.size();
-        ts.dmat.resize(ts.dmat.size() + (size_t)ne * np, 0.0);
+        ts.dmat.resize(ts.dmat.size() + (((size_t)ne * np + 1) & ~(size_t)1), 0.0);   // keep blocks 16-byte aligned
         double* D = ts.dmat.data() + pg.d_off;
         int t_cur = 0, eoff = 0;
         const int sp_base = (int)ts.sps.size();
@@ -363,9 +363,9 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             const TmpSP& sp = tsp[k];
             while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
             const int nE = pt_ne(sp.type);
-            recs.push_back({sp.type, eoff, (int)ts.pps.size(), (int)sp.pp.size(), sp.wmax});
+            recs.push_back({sp.type, eoff, (int)ts.pps.size(), (int)sp.pp.size(), sp.wmax, 0.0});
             pg.kwmax[sp.type] = std::max(pg.kwmax[sp.type], sp.wmax);
-            for (const PrimPair& pp : sp.pp) { ts.pps.push_back(pp); ts.pp_eoff.push_back(eoff); ts.pp_wseg.push_back(sp.wmax); }
+            for (PrimPair pp : sp.pp) { pp.eoff = eoff; pp.pad = 0; pp.wseg = sp.wmax; ts.pps.push_back(pp); }
             std::copy(sp.dt.begin(), sp.dt.end(), D + (size_t)eoff * np);
             eoff += nE;
         }
@@ -382,6 +382,8 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                 pg.sp_beg[t] = sp_base + k;
             }
         }
+        ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
+        ts.max_nsp = std::max(ts.max_nsp, (int)recs.size());
         ts.max_ne = std::max(ts.max_ne, ne);
         ts.max_np = std::max(ts.max_np, np);
         ts.pgs.push_back(pg);

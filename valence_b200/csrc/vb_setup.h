@@ -41,6 +41,7 @@ struct SPRec {          // one oriented shell pair of a pair group (whole contra
     int eoff;           // first [e0| component of this shell pair inside the group's e-space
     int pp_beg, pp_cnt; // range in the primitive-pair array
     double wmax;        // largest primitive weight of the shell pair
+    double pad;         // 32 bytes: staged with cp.async.bulk
 };
 struct PGDesc {
     int sp_beg[NPTYPE + 1];     // shell pairs sorted by type
@@ -75,11 +76,9 @@ struct TileSetup {
     std::vector<int> pg_pairs;      // 2 ints (s,t) per pair
     std::vector<SPRec> sps;
     std::vector<PrimPair> pps;
-    std::vector<int> pp_eoff;       // per primitive pair: e-offset of its shell pair inside the group
-    std::vector<double> pp_wseg;    // per primitive pair: largest weight of its shell pair (non-increasing per type)
     double wmax = 0.0;              // largest primitive-pair magnitude bound (for pruning)
     std::vector<double> dmat;       // folded densities, per pair group [e][p]
-    int max_ne = 0, max_np = 0;
+    int max_ne = 0, max_np = 0, max_npp = 0, max_nsp = 0;
     int lmax = 0;
 };
 

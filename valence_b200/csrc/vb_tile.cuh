@@ -13,6 +13,37 @@
 
 namespace vb {
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared) completed through an mbarrier ---------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 __device__ __forceinline__ int tri_index(int a, int c) { return a * (a + 1) / 2 + c; }   // a >= c, 0-based
 
 // W(s,t,u,v) = P[s,t] P[u,v] - sum_sigma P^s[s,v] P^s[u,t]   (times c0 outside)
@@ -23,7 +54,13 @@ __device__ __forceinline__ double w_term(const double* __restrict__ Pa, const do
     return (ast + bst) * (auv + buv) - asv * aut - bsv * but;
 }
 
-constexpr int TILE_THREADS = 256;
+#ifndef VB_TILE_THREADS
+#define VB_TILE_THREADS 256
+#endif
+#ifndef VB_MINBLOCKS
+#define VB_MINBLOCKS 1
+#endif
+constexpr int TILE_THREADS = VB_TILE_THREADS;
 constexpr int HMAX_UNR = 9;                      // pt_ne(pp)
 constexpr int HMAX_GEN = 31;                     // pt_ne(dd)
 constexpr int GEN_PER_THREAD = GEN_SCRATCH + HMAX_GEN * HMAX_GEN;
@@ -82,7 +119,8 @@ __device__ __noinline__ double w_general(const double* __restrict__ cof, int ndp
 // blocks of lanes that belong to the same ket shell pair are summed by a segmented warp
 // reduction, then the segment heads are half-transformed with the staged ket densities.
 template <int TB, int TK>
-__device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& sp, const PGDesc& Q, int base, int nket, int lane,
+__device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& sp, const PrimPair* __restrict__ bpp,
+                                               const PrimPair* __restrict__ kpp, int npQ, int base, int nket, int lane,
                                                const double* __restrict__ Dq, double* __restrict__ H, unsigned long long& npq)
 {
     constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
@@ -91,9 +129,8 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
 #pragma unroll
     for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
     const bool active = base + lane < nket;
-    const int kidx = Q.pp_beg[TK] + base + (active ? lane : 0);
-    PrimPair b = A.pps[kidx];
-    int seg = active ? A.pp_eoff[kidx] : -1 - lane;
+    PrimPair b = kpp[base + (active ? lane : 0)];
+    int seg = active ? b.eoff : -1 - lane;
     if (!active) { b.Kp = 0.0; b.w = 0.0; }
     // largest ket weight of the batch -> how many (sorted) bra primitives can still matter
     double wq = b.w;
@@ -101,7 +138,7 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
     for (int o = 16; o > 0; o >>= 1) wq = fmax(wq, __shfl_xor_sync(0xffffffffu, wq, o));
     int nbra = 0;
     for (int ip = 0; ip < sp.pp_cnt; ++ip) {
-        const PrimPair a = A.pps[sp.pp_beg + ip];
+        const PrimPair a = bpp[ip];
         if (!(a.w * wq >= A.tau)) break;           // bra primitives are sorted by weight
         ++nbra;
         QuartetGeom g;
@@ -116,6 +153,7 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
     }
     if (nbra == 0) return;
     if (lane == 0) npq += (unsigned long long)nbra * min(32, nket - base);
+    (void)A;
     // segmented reduction over lanes of the same ket shell pair (segments are contiguous)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -133,9 +171,10 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
         const int src = __ffs(heads) - 1;
         heads &= heads - 1;
         const int eo = __shfl_sync(0xffffffffu, seg, src);
+        const double* row = Dq + eo * npQ + (lane < npQ ? lane : 0);
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-            const double dq = (lane < Q.np) ? Dq[(eo + f) * Q.np + lane] : 0.0;
+            const double dq = row[f * npQ];
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 const double v = __shfl_sync(0xffffffffu, acc[e * NF + f], src);
@@ -146,7 +185,8 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
 }
 
 // generic path (any class with a d shell): runtime loops, scratch in global memory
-__device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, const SPRec& sp, const PGDesc& Q, int base, int nket,
+__device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, const SPRec& sp, const PrimPair* __restrict__ bpp,
+                                           const PrimPair* __restrict__ kpp, int npQ, int base, int nket,
                                            int lane, const double* __restrict__ Dq, double* __restrict__ H,
                                            double* __restrict__ scratch, unsigned long long& npq)
 {
@@ -156,20 +196,19 @@ __device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, co
     double* acc = scratch + GEN_SCRATCH;       // up to 31*31
     for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
     const bool active = base + lane < nket;
-    const int kidx = Q.pp_beg[tk] + base + (active ? lane : 0);
-    PrimPair b = A.pps[kidx];
-    const int eoff = A.pp_eoff[kidx];
+    PrimPair b = kpp[base + (active ? lane : 0)];
+    const int eoff = b.eoff;
     if (!active) { b.Kp = 0.0; b.w = 0.0; }
     double wq = b.w;
     for (int o = 16; o > 0; o >>= 1) wq = fmax(wq, __shfl_xor_sync(0xffffffffu, wq, o));
     int nbra = 0;
     for (; nbra < sp.pp_cnt; ++nbra)
-        if (!(A.pps[sp.pp_beg + nbra].w * wq >= A.tau)) break;
+        if (!(bpp[nbra].w * wq >= A.tau)) break;
     if (nbra == 0) return;
     if (lane == 0) npq += (unsigned long long)nbra * min(32, nket - base);
     if (active)
         for (int ip = 0; ip < nbra; ++ip) {
-            const PrimPair a = A.pps[sp.pp_beg + ip];
+            const PrimPair a = bpp[ip];
             QuartetGeom g;
             double Tt, pref, F[MTOP + 1];
             quartet_geom(a, b, g, Tt, pref);
@@ -181,7 +220,7 @@ __device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, co
     for (int src = 0; src < cnt; ++src) {
         const int eo = __shfl_sync(0xffffffffu, eoff, src);
         for (int f = 0; f < NF; ++f) {
-            const double dq = (lane < Q.np) ? Dq[(eo + f) * Q.np + lane] : 0.0;
+            const double dq = (lane < npQ) ? Dq[(eo + f) * npQ + lane] : 0.0;
             for (int e = 0; e < NE; ++e) {
                 const double v = __shfl_sync(0xffffffffu, acc[e * NF + f], src);
                 H[e] += v * dq;
@@ -200,11 +239,20 @@ __device__ __forceinline__ void add_rows(double* __restrict__ Hs, int eoff, cons
 }
 
 template <bool GEN>
-__global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileArgs A)
+__global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(const TileArgs A)
 {
-    extern __shared__ double smem[];
-    double* Dq = smem;                            // [Q.ne][Q.np]
-    double* Hs = smem + A.dq_cap;                 // half-transformed tile [P.ne][32]
+    extern __shared__ __align__(16) double smem[];
+    double* Dq = smem;                                          // [Q.ne][Q.np]
+    double* Hs = Dq + A.dq_cap;                                 // half-transformed tile [P.ne][32]
+    SPRec* spss = reinterpret_cast<SPRec*>(Hs + A.hs_cap);      // bra shell pairs of P
+    PrimPair* kpp_s = reinterpret_cast<PrimPair*>(spss + A.sp_cap);   // ket primitive pairs of Q (when they fit)
+    PrimPair* bpp_s = kpp_s + A.pp_cap;                         // bra primitive pairs of P
+    __shared__ unsigned long long s_bar;
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __shared__ int s_tile;
     __shared__ double s_red[TILE_THREADS / 32];
     __shared__ unsigned long long s_cnt[CNT_N];
@@ -225,8 +273,29 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
         const int2 tq = A.tiles[tl];
         const PGDesc P = A.pgs[tq.x];
         const PGDesc Q = A.pgs[tq.y];
-        for (int i = tid; i < Q.ne * Q.np; i += TILE_THREADS) Dq[i] = A.dmat[Q.d_off + i];
+        // stage the tile's tables with TMA bulk copies (one elected thread issues, all wait on the mbarrier)
+        const int nkpp = Q.pp_beg[NPTYPE] - Q.pp_beg[0], nbpp = P.pp_beg[NPTYPE] - P.pp_beg[0];
+        const int nspP = P.sp_beg[NPTYPE] - P.sp_beg[0];
+        if (tid == 0) {
+            // the buffers were last read through the generic proxy (previous tile): order before async writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned bq = (unsigned)((((size_t)Q.ne * Q.np + 1) & ~(size_t)1) * sizeof(double));
+            const unsigned bk = A.pp_cap ? (unsigned)(nkpp * sizeof(PrimPair)) : 0u, bb = A.pp_cap ? (unsigned)(nbpp * sizeof(PrimPair)) : 0u;
+            const unsigned bs = (unsigned)(nspP * sizeof(SPRec));
+            mbar_expect_tx(&s_bar, bq + bk + bb + bs);
+            tma_bulk_g2s(Dq, A.dmat + Q.d_off, bq, &s_bar);
+            tma_bulk_g2s(spss, A.sps + P.sp_beg[0], bs, &s_bar);
+            if (A.pp_cap) {
+                tma_bulk_g2s(kpp_s, A.pps + Q.pp_beg[0], bk, &s_bar);
+                tma_bulk_g2s(bpp_s, A.pps + P.pp_beg[0], bb, &s_bar);
+            }
+        }
+        // large orbital basis sets: the primitive tables stay in global memory (L1/L2)
+        const PrimPair* kpps = A.pp_cap ? kpp_s : A.pps + Q.pp_beg[0];
+        const PrimPair* bpps = A.pp_cap ? bpp_s : A.pps + P.pp_beg[0];
         for (int i = tid; i < P.ne * 32; i += TILE_THREADS) Hs[i] = 0.0;
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
         __syncthreads();
 
         // First half transformation.  All warps walk the classes (tb|tk) in the same order, so at any
@@ -244,7 +313,9 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
                 const int cls = tb * NPTYPE + tk;
                 unsigned long long npq = 0ull;
                 for (int i = warp; i < nspb; i += nw) {
-                    const SPRec sp = A.sps[P.sp_beg[tb] + i];
+                    const SPRec sp = spss[P.sp_beg[tb] - P.sp_beg[0] + i];
+                    const PrimPair* bpp = bpps + (sp.pp_beg - P.pp_beg[0]);
+                    const PrimPair* kpp = kpps + (Q.pp_beg[tk] - Q.pp_beg[0]);
                     if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
                     double H[HM];
 #pragma unroll
@@ -252,15 +323,15 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : 2) k_tile(const TileAr
                     unsigned long long n0 = npq;
                     for (int base = 0; base < nket; base += 32) {
                         // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
-                        if (!(sp.wmax * A.pp_wseg[Q.pp_beg[tk] + base] >= A.tau)) break;
+                        if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
                         switch (cls) {
-#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, Q, base, nket, lane, Dq, H, npq); break;
+#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, npq); break;
                             VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
                             VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
                             VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
 #undef VB_CASE
                             default:
-                                if constexpr (GEN) batch_generic(A, tb, tk, sp, Q, base, nket, lane, Dq, H, scratch, npq);
+                                if constexpr (GEN) batch_generic(A, tb, tk, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, scratch, npq);
                                 break;
                         }
                     }
