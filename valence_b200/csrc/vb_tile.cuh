@@ -235,7 +235,7 @@ template <int NEH>
 __device__ __forceinline__ void add_rows(double* __restrict__ Hs, int eoff, const double* __restrict__ H, int lane)
 {
 #pragma unroll
-    for (int e = 0; e < NEH; ++e) Hs[(eoff + e) * 32 + lane] += H[e];
+    for (int e = 0; e < NEH; ++e) atomicAdd(&Hs[(eoff + e) * 32 + lane], H[e]);
 }
 
 template <bool GEN>
@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __shared__ int s_tile;
+    __shared__ int s_tile, s_unit;
+    __shared__ int s_cum[NPTYPE * NPTYPE + 1];
     __shared__ double s_red[TILE_THREADS / 32];
     __shared__ unsigned long long s_cnt[CNT_N];
     __shared__ unsigned long long s_pq[NPTYPE * NPTYPE];
@@ -303,51 +304,78 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
         // shell pairs of type tb are dealt round-robin to the warps in cost order.  The assignment is
         // static, hence every tile result is bitwise reproducible (all ranks derive the same Schwarz
         // table), and each row of Hs is only ever touched by one warp.
+        // Units (class, bra shell pair) in class order; most expensive shell pairs first inside a class.
+        //   Schwarz pass: dealt round-robin (static), so the table is bitwise reproducible and
+        //                 identical on every rank (the tile list is derived from it);
+        //   energy pass : handed out through a shared counter (dynamic), which keeps all warps busy
+        //                 until the tile is done; rows of Hs are accumulated with shared atomics.
         constexpr int NT = GEN ? NPTYPE : 3;
-        for (int tb = 0; tb < NT; ++tb) {
-            const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb];
-            if (nspb == 0) continue;
-            for (int tk = 0; tk < NT; ++tk) {
-                const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-                if (nket == 0 || !(P.kwmax[tb] * Q.kwmax[tk] >= A.tau)) continue;   // nothing in this class can matter
-                const int cls = tb * NPTYPE + tk;
-                unsigned long long npq = 0ull;
-                for (int i = warp; i < nspb; i += nw) {
-                    const SPRec sp = spss[P.sp_beg[tb] - P.sp_beg[0] + i];
-                    const PrimPair* bpp = bpps + (sp.pp_beg - P.pp_beg[0]);
-                    const PrimPair* kpp = kpps + (Q.pp_beg[tk] - Q.pp_beg[0]);
-                    if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
-                    double H[HM];
-#pragma unroll
-                    for (int e = 0; e < HM; ++e) H[e] = 0.0;
-                    unsigned long long n0 = npq;
-                    for (int base = 0; base < nket; base += 32) {
-                        // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
-                        if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
-                        switch (cls) {
-#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, npq); break;
-                            VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
-                            VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
-                            VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
-#undef VB_CASE
-                            default:
-                                if constexpr (GEN) batch_generic(A, tb, tk, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, scratch, npq);
-                                break;
-                        }
-                    }
-                    if (__shfl_sync(0xffffffffu, npq != n0 ? 1 : 0, 0) && lane < Q.np) {
-                        switch (pt_ne(tb)) {
-                            case 1: add_rows<1>(Hs, sp.eoff, H, lane); break;
-                            case 3: add_rows<3>(Hs, sp.eoff, H, lane); break;
-                            case 9: add_rows<9>(Hs, sp.eoff, H, lane); break;
-                            default:
-                                if constexpr (GEN)
-                                    for (int e = 0; e < pt_ne(tb); ++e) Hs[(sp.eoff + e) * 32 + lane] += H[e];
-                                break;
-                        }
-                    }
+        if (tid == 0) {
+            int n = 0;
+            for (int tb = 0; tb < NT; ++tb)
+                for (int tk = 0; tk < NT; ++tk) {
+                    const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb], nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+                    s_cum[tb * NT + tk] = n;
+                    if (nspb > 0 && nket > 0 && P.kwmax[tb] * Q.kwmax[tk] >= A.tau) n += nspb;
                 }
-                if (lane == 0 && npq) atomicAdd(&s_pq[cls], npq);
+            s_cum[NT * NT] = n;
+            s_unit = 0;
+        }
+        __syncthreads();
+        const int nunits = s_cum[NT * NT];
+        const bool dynamic = A.mode != 0;
+        int ustat = warp;
+        for (;;) {
+            int u;
+            if (dynamic) {
+                u = 0;
+                if (lane == 0) u = atomicAdd(&s_unit, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+            } else {
+                u = ustat;
+                ustat += nw;
+            }
+            if (u >= nunits) break;
+            int c = 0;
+            while (s_cum[c + 1] <= u) ++c;
+            const int tb = c / NT, tk = c - tb * NT;
+            const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+            const int cls = tb * NPTYPE + tk;
+            const SPRec sp = spss[P.sp_beg[tb] - P.sp_beg[0] + (u - s_cum[c])];
+            if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
+            const PrimPair* bpp = bpps + (sp.pp_beg - P.pp_beg[0]);
+            const PrimPair* kpp = kpps + (Q.pp_beg[tk] - Q.pp_beg[0]);
+            double H[HM];
+#pragma unroll
+            for (int e = 0; e < HM; ++e) H[e] = 0.0;
+            unsigned long long npq = 0ull;
+            for (int base = 0; base < nket; base += 32) {
+                // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
+                if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
+                switch (cls) {
+#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, npq); break;
+                    VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
+                    VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
+                    VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
+#undef VB_CASE
+                    default:
+                        if constexpr (GEN) batch_generic(A, tb, tk, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, scratch, npq);
+                        break;
+                }
+            }
+            npq = __shfl_sync(0xffffffffu, npq, 0);
+            if (npq == 0ull) continue;
+            if (lane == 0) atomicAdd(&s_pq[cls], npq);
+            if (lane < Q.np) {
+                switch (pt_ne(tb)) {
+                    case 1: add_rows<1>(Hs, sp.eoff, H, lane); break;
+                    case 3: add_rows<3>(Hs, sp.eoff, H, lane); break;
+                    case 9: add_rows<9>(Hs, sp.eoff, H, lane); break;
+                    default:
+                        if constexpr (GEN)
+                            for (int e = 0; e < pt_ne(tb); ++e) atomicAdd(&Hs[(sp.eoff + e) * 32 + lane], H[e]);
+                        break;
+                }
             }
         }
         __syncthreads();
