@@ -378,11 +378,13 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     build_tiles(in, bas, wf, orbs2e, tau_diag, &ts);
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
+    const bool gen = ts.lmax >= 2;
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
     const int dq_cap2 = (dq_cap + 1) & ~1, hs_cap = ts.max_ne * 32, sp_cap = std::max(1, ts.max_nsp);
     int pp_cap = std::max(1, ts.max_npp);
     size_t smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
-    if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
+    const size_t smem_budget = gen ? 225 * 1024 : (225 * 1024) / VB_MINBLOCKS;
+    if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= smem_budget) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
     else pp_cap = 0;   // primitive tables stay in global memory
     if (smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
@@ -393,7 +395,6 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
     pps.upload(ts.pps, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
-    const bool gen = ts.lmax >= 2;
     int grid_cap = nsm * VB_MINBLOCKS;
     if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
     if (gen) CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -132,10 +132,9 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
     PrimPair b = kpp[base + (active ? lane : 0)];
     int seg = active ? b.eoff : -1 - lane;
     if (!active) { b.Kp = 0.0; b.w = 0.0; }
-    // largest ket weight of the batch -> how many (sorted) bra primitives can still matter
-    double wq = b.w;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wq = fmax(wq, __shfl_xor_sync(0xffffffffu, wq, o));
+    // upper bound of the ket weights of this batch (shell pairs are sorted by weight) -> how many
+    // (sorted) bra primitives can still matter
+    const double wq = kpp[base].wseg;
     int nbra = 0;
     for (int ip = 0; ip < sp.pp_cnt; ++ip) {
         const PrimPair a = bpp[ip];
@@ -159,6 +158,7 @@ __device__ __forceinline__ void batch_unrolled(const TileArgs& A, const SPRec& s
     for (int o = 1; o < 32; o <<= 1) {
         const int so = __shfl_down_sync(0xffffffffu, seg, o);
         const bool take = (lane + o < 32) && (so == seg);
+        if (!__any_sync(0xffffffffu, take)) break;     // no run is longer than the stride: done
 #pragma unroll
         for (int i = 0; i < NE * NF; ++i) {
             const double v = __shfl_down_sync(0xffffffffu, acc[i], o);
