@@ -86,6 +86,9 @@ int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out);
  * norbas x norbas column-major matrices <Psi[chi_ib]|H_el|Psi[chi_jb]>, <Psi[chi_ib]|Psi[chi_jb]>
  * (numerators: not divided by the norm, no nuclear repulsion); cap = doubles available in each. */
 int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int cap, int* norbas, vb_energy_result* stats);
+/* calculate_vsvb_energy (valence.F90:28-302): guess energy and, if the input asks for it, the
+ * first-order orbital optimisation + spin-coupling optimisation of minimize_energy (:2744-2885) */
+int vb_engine_run(vb_engine* e, int print, double* enucrep, double* guess_energy, double* total_energy, int* converged, int* iterations);
 double* vb_engine_accum_device(const vb_engine* e);
 int vb_engine_accum_len(const vb_engine* e);
 void* vb_engine_stream(const vb_engine* e);

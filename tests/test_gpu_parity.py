@@ -237,3 +237,29 @@ def test_first_order_matrices_match_oracle(name, iorb, write_input):
     assert np.abs(Hg - Ho).max() < 1e-8
     assert np.abs(Sg - So).max() < 1e-8
     assert np.allclose(Hg, Hg.T, atol=0) and np.allclose(Sg, Sg.T, atol=0)
+
+
+OPT_CASES = ["examples__li_opt", "testing__be", "testing__he", "testing__h2-dz", "testing__h2-sz", "testing__be+ndf",
+             "testing__he1s2s", "testing__he3s-1s3s", "testing__be3s2", "testing__h2o-vdz", "testing__lih-sv",
+             "testing__be-sc", "testing__be-scv3s+2sc", "testing__h2o-vdz-sc1"]
+
+
+@pytest.mark.parametrize("name", OPT_CASES)
+def test_orbital_and_spin_optimisation_matches_reference_golden(name, write_input):
+    """minimize_energy (first-order method, valence.F90:2744-2885) and spin_opt (:850-936) driven by
+    the GPU engine, against the reference's converged energies (its own tolerance: 1e-6) and the
+    oracle's run of the same loop."""
+    from valence_b200 import api
+    from oracle.oracle import Oracle
+    path, gold = write_input(name)
+    eng = api.Engine(path)
+    r = eng.run()
+    eng.close()
+    o = Oracle(path)
+    ro = o.run()
+    o.close()
+    assert r["converged"] == gold["converges"] == ro["converged"]
+    assert abs(r["guess_energy"] - gold["guess_energy"]) < 1e-8
+    assert abs(r["total_energy"] - gold["total_energy"]) < 1e-7
+    assert abs(r["total_energy"] - ro["total_energy"]) < 1e-8
+    assert r["iterations"] == ro["iterations"]

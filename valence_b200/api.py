@@ -75,6 +75,7 @@ def load(build_if_needed: bool = True):
     L.vb_engine_stream.restype = C.c_void_p
     L.vb_engine_stream.argtypes = [C.c_void_p]
     L.vb_engine_first_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(CEnergyResult)]
+    L.vb_engine_run.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int)] * 2
     L.vb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -142,6 +143,13 @@ class Engine:
         self._check(self.L.vb_engine_first_order(self.h, iorb, ham.ctypes.data, ovl.ctypes.data, cap, C.byref(n), C.byref(r)))
         k = n.value
         return ham[:k * k].reshape(k, k).T.copy(), ovl[:k * k].reshape(k, k).T.copy(), r.asdict()
+
+    def run(self, print_output: bool = False) -> dict:
+        """calculate_vsvb_energy: guess energy + (if requested by the input) orbital / spin optimisation."""
+        nuc, g, t = C.c_double(0), C.c_double(0), C.c_double(0)
+        conv, it = C.c_int(0), C.c_int(0)
+        self._check(self.L.vb_engine_run(self.h, 1 if print_output else 0, C.byref(nuc), C.byref(g), C.byref(t), C.byref(conv), C.byref(it)))
+        return {"enucrep": nuc.value, "guess_energy": g.value, "total_energy": t.value, "converged": bool(conv.value), "iterations": it.value}
 
     # --- sharded form (one process per GPU) ---------------------------------
     def energy_partial(self, rank: int, nranks: int) -> CEnergyResult:

@@ -49,7 +49,6 @@ int guarded(F&& f)
 
 // one live instance per process, like the reference's module globals (valence_finalize_module.F90:23-52)
 std::unique_ptr<vb::Engine> g_api;
-vb::EnergyResult g_last;   // kept for resume across calculate calls
 
 // xm_abort (xm_module.F90:942-950): `error` line from this rank, then stop
 [[noreturn]] void api_abort(const std::string& msg)
@@ -166,6 +165,16 @@ int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int 
     });
 }
 
+int vb_engine_run(vb_engine* e, int print, double* enucrep, double* guess_energy, double* total_energy, int* converged, int* iterations)
+{
+    return guarded([&] {
+        vb::Engine::RunResult r;
+        e->eng->run(&r, print != 0);
+        *enucrep = r.enucrep; *guess_energy = r.guess_energy; *total_energy = r.total_energy;
+        *converged = r.converged; *iterations = r.iterations;
+    });
+}
+
 double* vb_engine_accum_device(const vb_engine* e) { return e->eng->accum_device(); }
 int vb_engine_accum_len(const vb_engine* e) { return e->eng->accum_len(); }
 void* vb_engine_stream(const vb_engine* e) { return e->eng->stream(); }
@@ -201,16 +210,10 @@ void valence_api_calculate_energy_(double* x, double* v)
     if (!g_api) api_abort("valence_api_calculate_energy before valence_api_initialize");
     try {
         g_api->set_coords_angstrom(x);                                   // valence_api.F90:57-63
-        vb::EnergyResult r;
-        g_api->energy(&r);
-        g_last = r;
-        if (g_api->input().natom > 1) std::printf(" %-32s  %24.16f\n", "nuclear repulsion", r.enucrep);   // valence.F90:92
-        std::printf(" %-32s  %24.16f\n", "guess energy", r.energy);                                      // valence.F90:191
-        std::fflush(stdout);
-        write_orbitals_file(g_api->input(), nullptr, r.energy);                                          // valence.F90:192
-        if (g_api->input().max_iter > 0)
-            api_abort("orbital optimisation is not available in this build");
-        *v = r.energy;
+        vb::Engine::RunResult r;
+        g_api->run(&r, true);                                            // calculate_vsvb_energy, valence_api.F90:96-97
+        write_orbitals_file(g_api->input(), &g_api->weights(), r.total_energy);   // valence.F90:192,2823,2882
+        *v = r.total_energy;
     } catch (const std::exception& ex) {
         api_abort(ex.what());
     }

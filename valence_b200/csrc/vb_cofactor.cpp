@@ -74,7 +74,9 @@ void factor_block(int n, const std::vector<double>& M, BlockCof* out)
     }
     std::vector<int> Z;
     for (int p = 0; p < n; ++p) {
-        if (sig[p] > 1e-12 * smax && sig[p] > 0.0) {
+        // overlaps are O(1) quantities: a singular value below 1e-12 (absolute or relative) is treated
+        // through the explicit null-vector terms, which stay exact because sigma_z itself is kept
+        if (sig[p] > 1e-12 * std::max(smax, 1.0) && sig[p] > 0.0) {
             for (int r = 0; r < n; ++r) U[r * n + p] = W[r * n + p] / sig[p];
         } else {
             Z.push_back(p);
@@ -136,7 +138,7 @@ void factor_block(int n, const std::vector<double>& M, BlockCof* out)
 
 }  // namespace
 
-void build_cofactors(const Input& in, const Wavefunction& wf, const std::vector<double>& Se, CofactorSet* out)
+void build_cofactors(const Input& in, const Wavefunction& wf, const std::vector<double>& Se, CofactorSet* out, int only_isc, int only_jsc)
 {
     CofactorSet& cs = *out;
     cs = CofactorSet();
@@ -155,7 +157,8 @@ void build_cofactors(const Input& in, const Wavefunction& wf, const std::vector<
     for (int d = 0; d < ndocc; ++d) { a_fixed.push_back(2 * npair + nunpd + 2 * d); b_fixed.push_back(2 * npair + nunpd + 2 * d + 1); }
     BlockCof Ba, Bb;
     for (int isc = 0; isc < nsc; ++isc)
-        for (int jsc = 0; jsc < nsc; ++jsc)
+        for (int jsc = 0; jsc < nsc; ++jsc) {
+            if (only_isc >= 0 && (isc != only_isc || jsc != only_jsc)) continue;
             for (long long bm = 0; bm < nmask; ++bm)
                 for (long long km = 0; km < nmask; ++km) {
                     std::vector<int> abra, bbra, aket, bket;
@@ -198,8 +201,10 @@ void build_cofactors(const Input& in, const Wavefunction& wf, const std::vector<
                         for (int r = 0; r < na; ++r) { uza[z * nso + entry_of_slot[abra[r]]] += Ba.uz[z][r]; vza[z * nso + entry_of_slot[aket[r]]] += Ba.vz[z][r]; }
                     for (int z = 0; z < Bb.nz; ++z)
                         for (int r = 0; r < nb; ++r) { uzb[z * nso + entry_of_slot[bbra[r]]] += Bb.uz[z][r]; vzb[z * nso + entry_of_slot[bket[r]]] += Bb.vz[z][r]; }
+                    if (only_isc >= 0) D[0] = 1.0;
                     cs.ndp++;
                 }
+        }
 }
 
 void one_electron_from_cofactors(const CofactorSet& cs, const std::vector<double>& Se, const std::vector<double>& He, int nelec,

@@ -41,7 +41,10 @@ struct CofactorSet {
 };
 
 // Se: entry-level overlaps <bra_s|ket_t>, row-major nso x nso.
-void build_cofactors(const Input& in, const Wavefunction& wf, const std::vector<double>& Se, CofactorSet* out);
+// only_isc/only_jsc >= 0 restrict the sum to one (bra coupling, ket coupling) pair with unit weight
+// (the spin-coupling Hamiltonian of spin_opt, valence.F90:1549-1569)
+void build_cofactors(const Input& in, const Wavefunction& wf, const std::vector<double>& Se, CofactorSet* out,
+                     int only_isc = -1, int only_jsc = -1);
 
 // one- electron numerator and norm from the cofactors (valence.F90:1072-1106):
 //   e1 = sum_dp w sum_st He[s][t] C1tot(s,t),  wfnorm = sum_dp w sum_st Se[s][t] C1tot(s,t) / nelec

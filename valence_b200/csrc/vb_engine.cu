@@ -7,6 +7,7 @@
 #include <array>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -120,6 +121,8 @@ struct Engine::Impl {
     void prepare(const Input& in, int subject);
     void evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only, int rank, int nranks,
                   EnergyResult* out, std::vector<double>* sch_out);
+    int only_isc = -1, only_jsc = -1;                 // spin_opt: restrict the cofactors to one coupling pair
+    std::vector<double> coeff_sc;                    // current spin-coupling weights
     double enuc = 0, e1 = 0, wfnorm = 0;
     double tau = 1e-22;   // primitive-quartet magnitude cut; VB_PRIM_TAU overrides
     int launches = 0;
@@ -145,6 +148,7 @@ Engine::Engine(const Input& in, int device) : in_(in), impl_(new Impl)
     boys_make_table(tab.data());
     I.boys.upload(tab, I.st);
     I.xyz_angs = in.coords;
+    I.coeff_sc = in.coeff_sc;
     if (const char* t = std::getenv("VB_PRIM_TAU")) I.tau = std::atof(t);
     reset_orbitals();
     I.accum.alloc(1 + CNT_N);
@@ -361,7 +365,9 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             std::vector<double> hSe, hHe;
             Se.download(hSe, st); He.download(hHe, st);
             CofactorSet cs;
-            build_cofactors(in, wf, hSe, &cs);
+            Input in2 = in;
+            if (!coeff_sc.empty()) in2.coeff_sc = coeff_sc;
+            build_cofactors(in2, wf, hSe, &cs, only_isc, only_jsc);
             one_electron_from_cofactors(cs, hSe, hHe, nelec, &e1, &wfnorm);
             out->min_pivot_ratio = cs.min_sigma_ratio;
             cof.upload(cs.data, st);
@@ -408,6 +414,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
+    A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;
     auto launch = [&](int ntiles_mine) {
         int grid = std::max(1, std::min(grid_cap, ntiles_mine));
         if (gen) k_tile<true><<<grid, TILE_THREADS, smem, st>>>(A);
@@ -597,6 +604,17 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
                 CK(cudaMemcpyAsync(a.data(), I.accum.p, a.size() * sizeof(double), cudaMemcpyDeviceToHost, I.st));
                 CK(cudaStreamSynchronize(I.st));
                 const double num = r.e1 + a[0];
+                if (std::getenv("VB_DEBUG_FO")) {
+                    std::printf("---- end of evaluation ib %d jb %d\n", ib + 1, jb + 1);
+                    Wavefunction w3 = w2;
+                    std::swap(w3.bra[es], w3.ket[es]);
+                    EnergyResult r3;
+                    I.evaluate(in, w3, &sch, false, 0, 1, &r3, nullptr);
+                    std::vector<double> a3(1);
+                    CK(cudaMemcpyAsync(a3.data(), I.accum.p, sizeof(double), cudaMemcpyDeviceToHost, I.st));
+                    CK(cudaStreamSynchronize(I.st));
+                    std::printf("FO ib %d jb %d : e1 %.10f e2 %.10f N %.10f | swapped e1 %.10f e2 %.10f N %.10f\n", ib + 1, jb + 1, r.e1, a[0], r.wfnorm, r3.e1, a3[0], r3.wfnorm);
+                }
                 (*ham)[(size_t)jb * norbas + ib] += num;
                 (*ovl)[(size_t)jb * norbas + ib] += r.wfnorm;
                 acc.t_tiles += r.t_tiles; acc.flops_model += r.flops_model; acc.n_prim_quartets += r.n_prim_quartets;
@@ -616,6 +634,189 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
     acc.h2d_bytes = g_h2d_bytes; acc.d2h_bytes = g_d2h_bytes;
     if (stats) *stats = acc;
     return norbas;
+}
+
+namespace {
+
+// Generalised symmetric eigenproblem A x = lambda B x (column-major, lower triangles used): Cholesky
+// reduction + cyclic Jacobi; eigenvalues ascending, eigenvectors B-orthonormal.  Stands in for
+// EISPACK rsg (/root/reference/src/rsg.F:1, called at valence.F90:771,912); returns 7n+1 when B is
+// not positive definite, like rsg.
+int gen_eig(int n, const std::vector<double>& A, const std::vector<double>& B, std::vector<double>* w, std::vector<double>* Z)
+{
+    std::vector<double> L((size_t)n * n, 0.0), C((size_t)n * n, 0.0), T((size_t)n * n, 0.0), V((size_t)n * n, 0.0);
+    auto a = [&](int i, int j) { return i >= j ? A[(size_t)j * n + i] : A[(size_t)i * n + j]; };
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = B[(size_t)j * n + i];
+            for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
+            if (i == j) { if (s <= 0.0) return 7 * n + 1; L[i * n + i] = std::sqrt(s); }
+            else L[i * n + j] = s / L[j * n + j];
+        }
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            double s = a(i, j);
+            for (int k = 0; k < i; ++k) s -= L[i * n + k] * T[k * n + j];
+            T[i * n + j] = s / L[i * n + i];
+        }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double s = T[i * n + j];
+            for (int k = 0; k < j; ++k) s -= C[i * n + k] * L[j * n + k];
+            C[i * n + j] = s / L[j * n + j];
+        }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) { double s = 0.5 * (C[i * n + j] + C[j * n + i]); C[i * n + j] = s; C[j * n + i] = s; }
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int i = 0; i < n; ++i) { dg += C[i * n + i] * C[i * n + i]; for (int j = 0; j < i; ++j) off += C[i * n + j] * C[i * n + j]; }
+        if (off <= 1e-34 * (dg + 1e-300)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                double apq = C[p * n + q];
+                if (apq == 0.0) continue;
+                double th = (C[q * n + q] - C[p * n + p]) / (2.0 * apq);
+                double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+                double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < n; ++k) { double x = C[k * n + p], y = C[k * n + q]; C[k * n + p] = cs * x - sn * y; C[k * n + q] = sn * x + cs * y; }
+                for (int k = 0; k < n; ++k) { double x = C[p * n + k], y = C[q * n + k]; C[p * n + k] = cs * x - sn * y; C[q * n + k] = sn * x + cs * y; }
+                for (int k = 0; k < n; ++k) { double x = V[k * n + p], y = V[k * n + q]; V[k * n + p] = cs * x - sn * y; V[k * n + q] = sn * x + cs * y; }
+            }
+    }
+    std::vector<int> ord(n);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return C[x * n + x] < C[y * n + y]; });
+    w->assign(n, 0.0);
+    Z->assign((size_t)n * n, 0.0);
+    for (int e = 0; e < n; ++e) {
+        (*w)[e] = C[ord[e] * n + ord[e]];
+        for (int i = n - 1; i >= 0; --i) {
+            double s = V[i * n + ord[e]];
+            for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * (*Z)[(size_t)e * n + k];
+            (*Z)[(size_t)e * n + i] = s / L[i * n + i];
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+const std::vector<std::vector<double>>& Engine::weights() const { return impl_->coeff; }
+const std::vector<double>& Engine::coupling_weights() const { return impl_->coeff_sc; }
+
+void Engine::run(RunResult* out, bool print)
+{
+    Impl& I = *impl_;
+    const Input& in = in_;
+    const double tokcal = 627.509469;
+    *out = RunResult();
+    EnergyResult r;
+    energy(&r);
+    out->enucrep = r.enucrep;
+    out->guess_energy = r.energy;
+    double energy_now = r.energy;
+    if (print) {
+        if (in.natom > 1) std::printf(" %-32s  %24.16f\n", "nuclear repulsion", r.enucrep);   // valence.F90:92
+        std::printf(" %-32s  %24.16f\n", "guess energy", r.energy);                          // valence.F90:191
+        std::fflush(stdout);
+    }
+    out->total_energy = energy_now;
+    if (in.max_iter <= 0) return;
+    if (in.ptbnmax > 0.0 && in.nxorb == 0)
+        throw std::runtime_error("direct energy minimisation (demgs_opt) is not supported (under development in the reference, README.md:108)");
+    if (print) {
+        std::printf(" %-71s\n\n", "orbital optimization");
+        std::printf(" %-71s\n\n", "(full) first-order method");
+        std::printf(" %-71s\n", "cycle  orbital   relaxation(kCal)   (..per orb.)/tol");
+    }
+    const int nsc = in.nspinc;
+    double etol = 0.0, eprev = 0.0, eprv_sc = 0.0, eprv_orb = 0.0, cumulx = 0.0;
+    int num_iter = 0;
+    for (int ntol = in.ntol_e_min; ntol <= in.ntol_e_max; ++ntol) {
+        etol = std::pow(10.0, -ntol);
+        bool finished = false;
+        while (!finished) {
+            eprv_sc = energy_now;
+            bool orbconv = false;
+            while (!orbconv && num_iter < in.max_iter) {
+                eprv_orb = energy_now;
+                for (int iset = 0; iset < in.nset; ++iset) {
+                    bool setconv = false;
+                    while (!setconv && num_iter < in.max_iter) {
+                        const double eprv_set = energy_now;
+                        ++num_iter;
+                        for (int iorb = in.orbset[2 * iset]; iorb <= in.orbset[2 * iset + 1]; ++iorb) {
+                            eprev = energy_now;
+                            std::vector<double> ham, ovl, w, Z;
+                            EnergyResult st;
+                            const int n = first_order(iorb - 1, &ham, &ovl, &st);
+                            if (gen_eig(n, ham, ovl, &w, &Z) != 0) throw std::runtime_error("solver failed");   // valence.F90:786
+                            int rootsel = 0;
+                            for (int k = 0; k < in.nxorb; ++k) if (in.xorb[k] == iorb) rootsel = in.root[k];
+                            energy_now = w[rootsel] + st.enucrep;                                          // valence.F90:791-795
+                            for (int i = 0; i < n; ++i) I.coeff[iorb - 1][i] = Z[(size_t)rootsel * n + i];  // valence.F90:797-803
+                            const double relaxn = (energy_now - eprev) * tokcal;
+                            cumulx += relaxn;
+                            if (print) { std::printf("%5d  %4d      %14.6f      %12.4E\n", num_iter, iorb, cumulx, relaxn / etol); std::fflush(stdout); }
+                        }
+                        setconv = std::fabs(energy_now - eprv_set) * tokcal < etol;
+                    }
+                }
+                orbconv = std::fabs(energy_now - eprv_orb) * tokcal < etol;
+                if (in.nset == 1) { orbconv = true; eprv_orb = energy_now; }
+            }
+            if (nsc > 1) {
+                // spin_opt (valence.F90:850-936): Hamiltonian / overlap between spin couplings
+                if (print) std::printf(" %-71s\n", "spin optimization");
+                ++num_iter;
+                eprev = energy_now;
+                std::vector<double> ham((size_t)nsc * nsc, 0.0), ovl((size_t)nsc * nsc, 0.0), w, Z;
+                Wavefunction wf;
+                wf.nnd = in.nnd(); wf.nso = wf.nnd + in.ndocc; wf.sym = false; wf.subject = -1;
+                for (int i = 0; i < wf.nnd; ++i) { wf.bra.push_back(i); wf.ket.push_back(i); }
+                for (int d = 0; d < in.ndocc; ++d) for (int k = 0; k < 2; ++k) { wf.bra.push_back(wf.nnd + d); wf.ket.push_back(wf.nnd + d); }
+                I.launches = 0;
+                I.prepare(in, -1);
+                double enuc = I.enuc;
+                for (int isc = 0; isc < nsc; ++isc)
+                    for (int jsc = 0; jsc <= isc; ++jsc) {
+                        I.only_isc = isc; I.only_jsc = jsc;
+                        EnergyResult e2;
+                        I.evaluate(in, wf, nullptr, false, 0, 1, &e2, nullptr);
+                        std::vector<double> acc(1);
+                        CK(cudaMemcpyAsync(acc.data(), I.accum.p, sizeof(double), cudaMemcpyDeviceToHost, I.st));
+                        CK(cudaStreamSynchronize(I.st));
+                        ham[(size_t)jsc * nsc + isc] = e2.e1 + acc[0];
+                        ovl[(size_t)jsc * nsc + isc] = e2.wfnorm;
+                    }
+                I.only_isc = -1; I.only_jsc = -1;
+                if (gen_eig(nsc, ham, ovl, &w, &Z) != 0) throw std::runtime_error("solver failed");
+                energy_now = w[0] + enuc;
+                for (int i = 0; i < nsc; ++i) I.coeff_sc[i] = Z[i];
+                const double relaxn = (energy_now - eprev) * tokcal;
+                cumulx += relaxn;
+                if (print) { std::printf("%5d  %4d      %14.6f      %12.4E\n", num_iter, 0, cumulx, relaxn / etol); std::fflush(stdout); }
+                finished = std::fabs(energy_now - eprv_sc) * tokcal < etol;
+            } else {
+                finished = true;
+            }
+            if (num_iter >= in.max_iter) finished = true;
+        }
+    }
+    eprev = nsc > 1 ? eprv_sc : eprv_orb;
+    out->iterations = num_iter;
+    out->total_energy = energy_now;
+    if (num_iter >= in.max_iter) {
+        if (print) std::printf("\n %-71s\n\n", "reached maximum number of iterations");
+    } else if (std::fabs(energy_now - eprev) * tokcal < etol) {
+        out->converged = 1;
+        if (print) {
+            std::printf("\n %-71s\n\n", "calculation converged");
+            std::printf(" %-32s  %24.16f\n", "total energy", energy_now);
+        }
+    }
+    if (print) std::fflush(stdout);
 }
 
 // FP64 FMA peak of this GPU, measured: 8 independent DFMA chains per thread, full occupancy.

@@ -59,6 +59,7 @@ struct TileArgs {
     double* gfull;                   // mode 2: dense G over ordered pairs
     const int* pair_index;           // mode 2: (s*nso+t) -> dense pair index, or -1
     int npairs_total;
+    int debug;                       // print every contracted entry (tiny inputs only)
     double* gen_scratch;             // generic (d-shell) path scratch, GEN_SCRATCH doubles per thread
 };
 

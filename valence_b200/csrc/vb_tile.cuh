@@ -51,7 +51,7 @@ __device__ __forceinline__ double w_term(const double* __restrict__ Pa, const do
 {
     double ast = Pa[s * nso + t], bst = Pb[s * nso + t], auv = Pa[u * nso + v], buv = Pb[u * nso + v];
     double asv = Pa[s * nso + v], bsv = Pb[s * nso + v], aut = Pa[u * nso + t], but = Pb[u * nso + t];
-    return (ast + bst) * (auv + buv) - asv * aut - bsv * but;
+    return __dmul_rn(ast + bst, auv + buv) - __dmul_rn(asv, aut) - __dmul_rn(bsv, but);
 }
 
 #ifndef VB_TILE_THREADS
@@ -82,7 +82,8 @@ __device__ __forceinline__ double cof_c1(const CofBlock& B, int nso, int s, int 
 __device__ __forceinline__ double cof_c2(const CofBlock& B, int nso, int s, int t, int u, int v)
 {
     const double gst = B.G[s * nso + t], guv = B.G[u * nso + v], gsv = B.G[s * nso + v], gut = B.G[u * nso + t];
-    double r = B.pZ * (gst * guv - gsv * gut);
+    // products rounded separately (no FMA contraction): identical operands must cancel exactly
+    double r = B.pZ * (__dmul_rn(gst, guv) - __dmul_rn(gsv, gut));
     for (int z = 0; z < B.nz; ++z) {
         const double* uz = B.uz + z * nso;
         const double* vz = B.vz + z * nso;
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
                     cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
                 }
                 if (ssig && shortcut && vd) cnt[CNT_SHORTCUT]++;
+                if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
                 if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
             }
             (void)stab;
