@@ -218,21 +218,35 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         return v;
     };
     auto nao_of = [&](const std::vector<int>& sh) { int n = 0; for (int s : sh) n += ncart(bas.shells[s].l); return n; };
+    // Entries whose orbital basis sets live on nested atom sets share a group (e.g. the five orbitals
+    // of one water molecule, whatever shells the weight screen left them): every AO quartet of a
+    // molecule quartet is then generated once for all of their orbital pairs.
+    auto atoms_of = [&](const std::vector<int>& sh) {
+        std::vector<int> a;
+        for (int s : sh) a.push_back(bas.shells[s].atom);
+        std::sort(a.begin(), a.end());
+        a.erase(std::unique(a.begin(), a.end()), a.end());
+        return a;
+    };
+    std::vector<std::vector<int>> group_atoms;
     for (int s = 0; s < nso; ++s) {
         std::vector<int> sh = entry_shells(s);
+        std::vector<int> at = atoms_of(sh);
         int placed = -1;
         int lo = std::max(0, (int)ts.groups.size() - 16);
         for (int g = (int)ts.groups.size() - 1; g >= lo && placed < 0; --g) {
             EntryGroup& G = ts.groups[g];
             if ((int)G.entries.size() >= NG_MAX) continue;
+            std::vector<int> ua;
+            std::set_union(group_atoms[g].begin(), group_atoms[g].end(), at.begin(), at.end(), std::back_inserter(ua));
+            if (ua.size() != std::max(group_atoms[g].size(), at.size())) continue;   // atom sets must be nested
             std::vector<int> un;
             std::set_union(G.shells.begin(), G.shells.end(), sh.begin(), sh.end(), std::back_inserter(un));
-            // only merge when one set contains the other (no padding beyond the larger OBS)
-            if (un.size() != std::max(G.shells.size(), sh.size())) continue;
             if (nao_of(un) * ((int)G.entries.size() + 1) > AO_BUDGET) continue;
             G.shells = un;
             G.nao = nao_of(un);
             G.entries.push_back(s);
+            group_atoms[g] = ua;
             placed = g;
         }
         if (placed < 0) {
@@ -241,6 +255,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             G.shells = sh;
             G.nao = nao_of(sh);
             ts.groups.push_back(G);
+            group_atoms.push_back(at);
         }
     }
     // --- pair groups --------------------------------------------------------
