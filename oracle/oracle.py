@@ -56,6 +56,7 @@ def lib():
         L.vo_guess_energy.argtypes = [C.c_void_p, C.c_int, C.POINTER(Result)]
         L.vo_first_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(Counters)]
         L.vo_run.argtypes = [C.c_void_p, C.POINTER(RunResult)]
+        L.vo_count_tasks.argtypes = [C.c_void_p, C.POINTER(Counters)]
         L.vo_set_quiet.argtypes = [C.c_void_p, C.c_int]
         L.vo_set_memo.argtypes = [C.c_void_p, C.c_int]
         L.vo_set_coords.argtypes = [C.c_void_p, C.c_void_p]
@@ -111,6 +112,12 @@ class Oracle:
         self.L.vo_guess_energy(self.h, nrank, C.byref(r))
         return {"enucrep": r.enucrep, "energy": r.energy, "wfnorm": r.wfnorm,
                 "numerator": r.numerator, "counters": r.cnt.asdict()}
+
+    def count_tasks(self) -> dict:
+        """Screening / task counters of guess_energy without the 2e integrals and determinants."""
+        cnt = Counters()
+        self.L.vo_count_tasks(self.h, C.byref(cnt))
+        return cnt.asdict()
 
     def wdet(self) -> np.ndarray:
         n = self.nelec

@@ -84,6 +84,7 @@ typedef struct vo_ctx {
     /* oracle extras */
     int *atom_alias;               /* dummy atom -> real atom (memo key) */
     int in2e;                      /* inside the 2e loop of vsvb_energy */
+    int count_only;                /* vo_count_tasks: the 2e loop only counts what int2e would evaluate */
     vo_counters cnt;
     memo_t *memo, *memo2;
     int memo_on;
@@ -553,6 +554,29 @@ static void int2e(vo_ctx *c, int io, int jo, int ko, int lo)
     if (c->deadline > 0.0 && !c->expired && mono_now() > c->deadline) c->expired = 1;
     if (c->expired) { c->gint = 0.0; return; }
     scatter(c, io, c->coeffi); scatter(c, jo, c->coeffj); scatter(c, ko, c->coeffk); scatter(c, lo, c->coeffl);
+    if (c->count_only && c->in2e) {
+        /* the shell quartets the four nested weight screens below would let through */
+        long long prod = 1;
+        const int orb[4] = {io, jo, ko, lo};
+        const double *cf[4] = {c->coeffi, c->coeffj, c->coeffk, c->coeffl};
+        for (int q = 0; q < 4; ++q) {
+            long long n = 0;
+            int beg = 1;
+            for (int ia = 1; ia <= c->orbas_atnum[orb[q]]; ++ia) {
+                int it = c->atom_t[ATSET(c, ia, orb[q])];
+                for (int ii = c->map_atom2shell[it]; ii <= c->map_atom2shell[it] + c->num_shell_atom[it] - 1; ++ii) {
+                    double sum = 0.0;
+                    for (int i = beg; i <= beg + shell_size(c->ang_mom[ii]) - 1; ++i) sum = sum + cf[q][i] * cf[q][i];
+                    if (sum > c->dtol) ++n;
+                    beg = beg + shell_size(c->ang_mom[ii]);
+                }
+            }
+            prod *= n;
+        }
+        c->cnt.shell_quartets += prod; c->cnt.shell_quartets_2e += prod;
+        c->gint = 0.0;
+        return;
+    }
     double gint = 0.0;
     int ish_beg = 1;
     for (int ia = 1; ia <= c->orbas_atnum[io]; ++ia) {
@@ -966,7 +990,7 @@ static void vsvb_energy(vo_ctx *c, int iorb, int num_non_docc, int num_spatial_o
     int nelec = c->nelec;
     set_up_unpaired_docc(c);
 
-    for (int i = 1; i <= nelec; ++i) {
+    for (int i = 1; i <= nelec && !c->count_only; ++i) {
         int i_is_docc = i > num_non_docc;
         for (int j = 1; j <= nelec; ++j) {
             int j_is_docc = j > num_non_docc;
@@ -1221,6 +1245,29 @@ int vo_guess_energy(vo_ctx *c, int nrank, vo_result *out)
     out->enucrep = c->enucrep; out->numerator = esum; out->wfnorm = wsum;
     out->energy = esum / wsum + c->enucrep;
     out->cnt = c->cnt;
+    return 0;
+}
+
+/* Task bookkeeping of guess_energy without the integrals and determinants of the 2e loop: the
+ * Schwarz table is computed for real (schwarz_ints), then the task loop of vsvb_energy runs with
+ * int2e only counting the shell quartets it would evaluate.  Valid counters: ntasks, same_orb_skip,
+ * schwarz_*, shortcut, int2e_calls, shell_quartets_2e (the value_* screens need the integrals).
+ * Lets the tests check the engine's screening counters at sizes the full oracle cannot reach. */
+int vo_count_tasks(vo_ctx *c, vo_counters *out)
+{
+    setup_energy(c);
+    memset(&c->cnt, 0, sizeof c->cnt);
+    c->nrank = 1; c->irank = 0;
+    int nnd = 2 * c->npair + c->nunpd;
+    default_lists(c, nnd);
+    int nso = nnd + c->ndocc;
+    schwarz_ints(c, nso, nnd);
+    c->store_eri = 0;
+    c->count_only = 1;
+    double e, w;
+    vsvb_energy(c, 0, nnd, nso, &e, &w, 0, 1);
+    c->count_only = 0;
+    *out = c->cnt;
     return 0;
 }
 

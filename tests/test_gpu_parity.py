@@ -70,6 +70,24 @@ def test_water_clusters_match_oracle(n, rotate, write_input):
         assert r["counters"][k] == ro["counters"][k], k
 
 
+def test_screening_counters_match_reference_task_loop_on_16_waters(write_input):
+    """(H2O)_16 is beyond the full oracle (O(n^3) determinants per task), but the reference's task
+    bookkeeping only needs the Schwarz table: the oracle's count-only pass (real schwarz_ints, then
+    the task loop of vsvb_energy with int2e counting the shell quartets it would evaluate,
+    valence.F90:1153-1216, 3296-3398) must agree bit for bit with the engine's counters."""
+    from valence_b200 import api, inputs
+    from oracle.oracle import Oracle
+    path, _ = write_input(inputs.water_cluster(16, tol=(10, 20, 10)))
+    eng = api.Engine(path)
+    r = eng.energy()
+    eng.close()
+    o = Oracle(path)
+    c = o.count_tasks()
+    o.close()
+    for k in EXACT:
+        assert r["counters"][k] == c[k], k
+
+
 def test_loose_dtol_deviation_is_the_references_givens_skip(write_input):
     """With dtol = 1e-10 the reference's determinants are approximate (rotations with
     c^2+s^2 <= dtol are skipped, givens.F90:245); the engine stays within 1e-5 of it and agrees

@@ -101,7 +101,7 @@ struct Engine::Impl {
     std::vector<std::vector<double>> coeff;          // current orbital weights (normalised in energy())
     std::vector<double> xyz_angs;
     // device data
-    DBuf<double> boys, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
+    DBuf<double> boys, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket, gj_n;
     DBuf<long long> gj_off, gj_poff;
@@ -234,8 +234,8 @@ void Engine::Impl::prepare(const Input& in, int subject)
     S.alloc((size_t)nao * nao); H.alloc((size_t)nao * nao);
     {
         long long npair = (long long)nshell * (nshell + 1) / 2;
-        int bs = 64;
-        k_ao_1e<<<(unsigned)((npair + bs - 1) / bs), bs, 0, st>>>(shells.p, nshell, exps.p, coefs.p, this->nuc.p, in.natom, boys.p, nao, S.p, H.p);
+        const int wpb = 4;   // warps (= shell pairs) per block
+        k_ao_1e<<<(unsigned)((npair + wpb - 1) / wpb), 32 * wpb, 0, st>>>(shells.p, nshell, exps.p, coefs.p, this->nuc.p, in.natom, boys.p, nao, 1e-30, S.p, H.p);
         CK(cudaGetLastError());
         launches++;
     }
@@ -331,17 +331,24 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             ea_bra.upload(ea, st); eb_bra.upload(eb, st); posa_bra.upload(posa, st); posb_bra.upload(posb, st);
             Ma.alloc((size_t)na * na + 1); Mb.alloc((size_t)nb * nb + 1);
             if (na) { k_gather_block<<<(na * na + 255) / 256, 256, 0, st>>>(Se.p, nso, ea_bra.p, ea_bra.p, na, Ma.p); launches++; }
-            if (nb) { k_gather_block<<<(nb * nb + 255) / 256, 256, 0, st>>>(Se.p, nso, eb_bra.p, eb_bra.p, nb, Mb.p); launches++; }
+            if (nb && !(wf.nnd == 0 && na == nb)) { k_gather_block<<<(nb * nb + 255) / 256, 256, 0, st>>>(Se.p, nso, eb_bra.p, eb_bra.p, nb, Mb.p); launches++; }
             CK(cudaGetLastError());
-            std::vector<long long> z = {0};
-            gj_off.upload(z, st); gj_poff.upload(z, st);
-            piv.alloc((size_t)std::max(na, nb) * 2 + 2);
+            // one inverse when both spin blocks hold the same entries (closed shell)
+            const bool same = wf.nnd == 0 && na == nb;
             gjout.alloc(4);
-            gj_n.upload(std::vector<int>{na, nb}, st);
-            k_gj_inverse<<<1, 1024, 0, st>>>(Ma.p, gj_n.p, gj_off.p, piv.p, gj_poff.p, gjout.p);
-            k_gj_inverse<<<1, 1024, 0, st>>>(Mb.p, gj_n.p + 1, gj_off.p, piv.p + std::max(na, nb) + 1, gj_poff.p, gjout.p + 2);
-            CK(cudaGetLastError());
-            launches += 2;
+            auto invert = [&](DBuf<double>& M, DBuf<double>& Minv, int n, double* res) {
+                Minv.alloc((size_t)n * n + 1);
+                if (n == 0) { const double one[2] = {1.0, 1.0}; CK(cudaMemcpyAsync(res, one, sizeof one, cudaMemcpyHostToDevice, st)); return; }
+                gj_ws.alloc(2 * (size_t)n); piv.alloc(2 * (size_t)n + 2);
+                int grid = std::max(1, std::min(nsm, n / 4));
+                double* Ap = M.p; double* Ip = Minv.p; double* wsp = gj_ws.p; int* iwp = piv.p; int nn = n;
+                void* args[] = {&Ap, &nn, &Ip, &wsp, &iwp, &res};
+                CK(cudaLaunchCooperativeKernel((void*)k_gj_inverse_grid, dim3(grid), dim3(1024), args, 0, st));
+                launches++;
+            };
+            invert(Ma, Mai, na, gjout.p);
+            if (same) CK(cudaMemcpyAsync(gjout.p + 2, gjout.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            else invert(Mb, Mbi, nb, gjout.p + 2);
             std::vector<double> g;
             gjout.download(g, st);
             out->min_pivot_ratio = std::min(g[1], g[3]);
@@ -349,8 +356,8 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
                 throw std::runtime_error("valence_b200: singular spin-block overlap matrix (linearly dependent orbitals)");
             c0 = g[0] * g[2];
             Pa.alloc((size_t)nso * nso); Pb.alloc((size_t)nso * nso);
-            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Ma.p, na, posa_bra.p, posa_bra.p, nso, Pa.p);
-            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mb.p, nb, posb_bra.p, posb_bra.p, nso, Pb.p);
+            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mai.p, na, posa_bra.p, posa_bra.p, nso, Pa.p);
+            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(same ? Mai.p : Mbi.p, nb, posb_bra.p, posb_bra.p, nso, Pb.p);
             one_e.alloc(2);
             k_one_electron_energy<<<1, 1024, 0, st>>>(Se.p, He.p, Pa.p, Pb.p, nso * nso, one_e.p);
             CK(cudaGetLastError());

@@ -11,6 +11,7 @@
 //                  orbital-pair basis + contraction with the cofactor densities
 //                  (replaces int2e :3184-3438 and the 2e loop of vsvb_energy :1153-1433)
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "vb_eri.cuh"
@@ -73,12 +74,69 @@ __device__ __forceinline__ double dev_binom(int n, int k)
     return r;
 }
 
-__global__ void k_ao_1e(const DevShell* __restrict__ sh, int nshell, const double* __restrict__ exps,
-                        const double* __restrict__ coefs, const double* __restrict__ nuc /* x,y,z,Z per atom */, int natom,
-                        const double* __restrict__ boys_tab, int nao, double* __restrict__ S, double* __restrict__ H)
+// Contracted nuclear-attraction auxiliaries sum_{prim pairs, nuclei} [e|C], e <= L on centre A, for one
+// shell pair: lanes stride over the nuclei, the primitive pairs are walked by the whole warp.
+template <int L>
+__device__ __forceinline__ void nuc_aux(const DevShell& A, const DevShell& B, double AB2, const double* __restrict__ exps,
+                                        const double* __restrict__ coefs, const double* __restrict__ nuc, int natom,
+                                        const double* __restrict__ boys_tab, int lane, double kcut, double* __restrict__ out /* ncum(L) */)
 {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long npair = (long long)nshell * (nshell + 1) / 2;
+    constexpr int NE = ncum(L);
+    double acc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc[e] = 0.0;
+    for (int ia = 0; ia < A.nprim; ++ia)
+        for (int ib = 0; ib < B.nprim; ++ib) {
+            const double a = exps[A.prim_off + ia], b = exps[B.prim_off + ib], p = a + b, ip = 1.0 / p, h2p = 0.5 * ip;
+            const double K = coefs[A.prim_off + ia] * coefs[B.prim_off + ib] * exp(-a * b * ip * AB2);
+            if (!(fabs(K) > kcut)) continue;
+            const double P[3] = {(a * A.x + b * B.x) * ip, (a * A.y + b * B.y) * ip, (a * A.z + b * B.z) * ip};
+            const double PA[3] = {P[0] - A.x, P[1] - A.y, P[2] - A.z};
+            const double pk = -K * 2.0 * PI * ip;
+            for (int c = lane; c < natom; c += 32) {
+                const double Z = nuc[4 * c + 3];
+                if (!(fabs(Z) > 1.0e-12)) continue;     // valence.F90:3149
+                const double PC[3] = {P[0] - nuc[4 * c], P[1] - nuc[4 * c + 1], P[2] - nuc[4 * c + 2]};
+                const double U = p * (PC[0] * PC[0] + PC[1] * PC[1] + PC[2] * PC[2]);
+                double F[L + 1];
+                boys<L>(boys_tab, U, F);
+                double R[L + 1][NE];
+                const double pv = Z * pk;
+#pragma unroll
+                for (int m = 0; m <= L; ++m) R[m][0] = pv * F[m];
+                sfor<1, NE>([&](auto EI) {
+                    constexpr int e = EI, d = c_dir(e), e1 = c_dec(e, d), n1 = c_l(e1, d), Le = c_L(e);
+                    sfor<0, L + 1 - Le>([&](auto M) {
+                        constexpr int m = M;
+                        double v = PA[d] * R[m][e1] - PC[d] * R[m + 1][e1];
+                        if constexpr (n1 > 0) {
+                            constexpr int e2 = c_dec(e1, d);
+                            v += n1 * h2p * (R[m][e2] - R[m + 1][e2]);
+                        }
+                        R[m][e] = v;
+                    });
+                });
+#pragma unroll
+                for (int e = 0; e < NE; ++e) acc[e] += R[0][e];
+            }
+        }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        double v = acc[e];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        out[e] = v;
+    }
+}
+
+// One warp per AO shell pair (i >= j).  Primitive pairs whose Gaussian-product prefactor is below
+// kcut (1e-30: far below anything that reaches 1e-10 Eh) are skipped.
+__global__ void __launch_bounds__(128) k_ao_1e(const DevShell* __restrict__ sh, int nshell, const double* __restrict__ exps,
+                        const double* __restrict__ coefs, const double* __restrict__ nuc /* x,y,z,Z per atom */, int natom,
+                        const double* __restrict__ boys_tab, int nao, double kcut, double* __restrict__ S, double* __restrict__ H)
+{
+    const int lane = threadIdx.x & 31;
+    const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long npair = (long long)nshell * (nshell + 1) / 2;
     if (idx >= npair) return;
     int i = (int)floor(sqrt(2.0 * (double)idx + 0.25) - 0.5);
     while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
@@ -87,15 +145,25 @@ __global__ void k_ao_1e(const DevShell* __restrict__ sh, int nshell, const doubl
     DevShell A = sh[i], B = sh[j];
     if (A.l < B.l) { DevShell t = A; A = B; B = t; }   // A carries la >= lb
     const int la = A.l, lb = B.l, L = la + lb, na = ncart(la), nb = ncart(lb);
-    double AB[3] = {A.x - B.x, A.y - B.y, A.z - B.z};
-    double AB2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+    const double AB[3] = {A.x - B.x, A.y - B.y, A.z - B.z};
+    const double AB2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+    // nuclear attraction auxiliaries, all lanes
+    double Raux[ncum(EMAX)];
+    switch (L) {
+        case 0: nuc_aux<0>(A, B, AB2, exps, coefs, nuc, natom, boys_tab, lane, kcut, Raux); break;
+        case 1: nuc_aux<1>(A, B, AB2, exps, coefs, nuc, natom, boys_tab, lane, kcut, Raux); break;
+        case 2: nuc_aux<2>(A, B, AB2, exps, coefs, nuc, natom, boys_tab, lane, kcut, Raux); break;
+        case 3: nuc_aux<3>(A, B, AB2, exps, coefs, nuc, natom, boys_tab, lane, kcut, Raux); break;
+        default: nuc_aux<4>(A, B, AB2, exps, coefs, nuc, natom, boys_tab, lane, kcut, Raux); break;
+    }
+    if (lane != 0) return;
     double Sb[36], Hb[36];
     for (int n = 0; n < na * nb; ++n) { Sb[n] = 0.0; Hb[n] = 0.0; }
     for (int ia = 0; ia < A.nprim; ++ia)
         for (int ib = 0; ib < B.nprim; ++ib) {
             double a = exps[A.prim_off + ia], b = exps[B.prim_off + ib], p = a + b, ip = 1.0 / p, h2p = 0.5 * ip;
             double K = coefs[A.prim_off + ia] * coefs[B.prim_off + ib] * exp(-a * b * ip * AB2);
-            if (K == 0.0) continue;
+            if (!(fabs(K) > kcut)) continue;
             double P[3] = {(a * A.x + b * B.x) * ip, (a * A.y + b * B.y) * ip, (a * A.z + b * B.z) * ip};
             double PA[3] = {P[0] - A.x, P[1] - A.y, P[2] - A.z};
             double PB[3] = {P[0] - B.x, P[1] - B.y, P[2] - B.z};
@@ -128,41 +196,21 @@ __global__ void k_ao_1e(const DevShell* __restrict__ sh, int nshell, const doubl
                     Hb[ca * nb + cb] += pref * (tx[0] * sx[1] * sx[2] + sx[0] * tx[1] * sx[2] + sx[0] * sx[1] * tx[2]);
                 }
             }
-            // nuclear attraction: [e|C]^(m), e <= L, bra-only vertical recurrence, then HRR by binomials
-            for (int c = 0; c < natom; ++c) {
-                double Z = nuc[4 * c + 3];
-                if (!(fabs(Z) > 1.0e-12)) continue;     // valence.F90:3149
-                double PC[3] = {P[0] - nuc[4 * c], P[1] - nuc[4 * c + 1], P[2] - nuc[4 * c + 2]};
-                double U = p * (PC[0] * PC[0] + PC[1] * PC[1] + PC[2] * PC[2]);
-                double F[EMAX + 1];
-                boys_rt(L, boys_tab, U, F);
-                double R[EMAX + 1][ncum(EMAX)];
-                double pv = -Z * K * 2.0 * PI * ip;
-                for (int m = 0; m <= L; ++m) R[m][0] = pv * F[m];
-                for (int e = 1; e < ncum(L); ++e) {
-                    int d = c_dir(e), e1 = c_dec(e, d), n1 = c_l(e1, d), Le = c_L(e);
-                    int e2 = n1 > 0 ? c_dec(e1, d) : 0;
-                    for (int m = 0; m <= L - Le; ++m) {
-                        double v = PA[d] * R[m][e1] - PC[d] * R[m + 1][e1];
-                        if (n1 > 0) v += n1 * h2p * (R[m][e2] - R[m + 1][e2]);
-                        R[m][e] = v;
-                    }
-                }
-                for (int ca = 0; ca < na; ++ca) {
-                    int c1 = coff(la) + ca, ax = c_lx(c1), ay = c_ly(c1), az = c_lz(c1);
-                    for (int cb = 0; cb < nb; ++cb) {
-                        int c2 = coff(lb) + cb, bx = c_lx(c2), by = c_ly(c2), bz = c_lz(c2);
-                        double v = 0.0;
-                        for (int kx = 0; kx <= bx; ++kx)
-                            for (int ky = 0; ky <= by; ++ky)
-                                for (int kz = 0; kz <= bz; ++kz)
-                                    v += dev_binom(bx, kx) * dev_binom(by, ky) * dev_binom(bz, kz) * pow(AB[0], (double)(bx - kx)) *
-                                         pow(AB[1], (double)(by - ky)) * pow(AB[2], (double)(bz - kz)) * R[0][cidx(ax + kx, ay + ky, az + kz)];
-                        Hb[ca * nb + cb] += v;
-                    }
-                }
-            }
         }
+    // horizontal shift of the contracted [e|V|0] to (a|V|b) by binomials in A - B
+    for (int ca = 0; ca < na; ++ca) {
+        int c1 = coff(la) + ca, ax = c_lx(c1), ay = c_ly(c1), az = c_lz(c1);
+        for (int cb = 0; cb < nb; ++cb) {
+            int c2 = coff(lb) + cb, bx = c_lx(c2), by = c_ly(c2), bz = c_lz(c2);
+            double v = 0.0;
+            for (int kx = 0; kx <= bx; ++kx)
+                for (int ky = 0; ky <= by; ++ky)
+                    for (int kz = 0; kz <= bz; ++kz)
+                        v += dev_binom(bx, kx) * dev_binom(by, ky) * dev_binom(bz, kz) * pow(AB[0], (double)(bx - kx)) *
+                             pow(AB[1], (double)(by - ky)) * pow(AB[2], (double)(bz - kz)) * Raux[cidx(ax + kx, ay + ky, az + kz)];
+            Hb[ca * nb + cb] += v;
+        }
+    }
     for (int ca = 0; ca < na; ++ca)
         for (int cb = 0; cb < nb; ++cb) {
             size_t r = (size_t)A.ao_off + ca, c = (size_t)B.ao_off + cb;
@@ -269,6 +317,103 @@ __global__ void k_gj_inverse(double* __restrict__ Ms, const int* __restrict__ ns
         __syncthreads();
     }
     if (tid == 0) { out[0] = s_det; out[1] = s_max > 0.0 ? s_min / s_max : 0.0; }
+}
+
+// Multi-CTA in-place Gauss-Jordan inverse for large blocks (cooperative launch, grid-wide barriers).
+// Implicit partial pivoting: column k takes its pivot from the not-yet-used row with the largest
+// |A[r][k]| (rows are never moved; prow/colf hold the scaled pivot row and the eliminated column so
+// that no CTA reads data another CTA is overwriting).  With p(k) the pivot row of column k, the
+// storage ends up holding S[p(i)][c] = (A^-1)[i][p(c)]; Ainv receives the un-permuted inverse.
+// ws: prow[n] colf[n]; iws: prow_of_col[n], used[n], pivot_row (1).  out[0] = det, out[1] = min|piv|/max|piv|.
+__global__ void __launch_bounds__(1024) k_gj_inverse_grid(double* __restrict__ A, int n, double* __restrict__ Ainv,
+                                                          double* __restrict__ ws, int* __restrict__ iws, double* __restrict__ out)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    double* prow = ws;
+    double* colf = ws + n;
+    int* pcol = iws;            // pcol[k] = pivot row of column k
+    int* used = iws + n;
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_det, s_min, s_max;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (blockIdx.x == 0) {
+        for (int r = tid; r < n; r += nt) used[r] = 0;
+        if (tid == 0) { s_det = 1.0; s_min = 1e300; s_max = 0.0; }
+    }
+    __threadfence();
+    grid.sync();
+    for (int k = 0; k < n; ++k) {
+        if (blockIdx.x == 0) {
+            double best = -1.0; int bi = n;
+            for (int r = tid; r < n; r += nt) {
+                if (used[r]) continue;
+                double v = fabs(A[(size_t)r * n + k]);
+                if (v > best || (v == best && r < bi)) { best = v; bi = r; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_down_sync(0xffffffffu, best, o); int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid < 32) {
+                best = tid < (nt >> 5) ? s_val[tid] : -1.0; bi = tid < (nt >> 5) ? s_idx[tid] : n;
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_down_sync(0xffffffffu, best, o); int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                if (tid == 0) { s_idx[0] = bi; }
+            }
+            __syncthreads();
+            const int pr = s_idx[0];
+            const double pv = A[(size_t)pr * n + k];
+            const double ipv = pv != 0.0 ? 1.0 / pv : 0.0;
+            for (int c = tid; c < n; c += nt) {
+                prow[c] = (c == k) ? ipv : A[(size_t)pr * n + c] * ipv;
+                colf[c] = (c == pr) ? 0.0 : A[(size_t)c * n + k];
+            }
+            if (tid == 0) {
+                pcol[k] = pr; used[pr] = 1; iws[2 * n] = pr;
+                s_det *= pv;
+                s_min = fmin(s_min, fabs(pv)); s_max = fmax(s_max, fabs(pv));
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        grid.sync();
+        const int pr = iws[2 * n];
+        for (int r = blockIdx.x; r < n; r += gridDim.x) {
+            double* row = A + (size_t)r * n;
+            if (r == pr) {
+                for (int c = tid; c < n; c += nt) row[c] = prow[c];
+            } else {
+                const double f = colf[r];
+                if (f == 0.0) continue;
+                for (int c = tid; c < n; c += nt) row[c] = (c == k) ? -f * prow[k] : row[c] - f * prow[c];
+            }
+        }
+        __threadfence();
+        grid.sync();
+    }
+    // un-permute: Ainv[i][p(c)] = S[p(i)][c]
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const double* src = A + (size_t)pcol[i] * n;
+        for (int c = tid; c < n; c += nt) Ainv[(size_t)i * n + pcol[c]] = src[c];
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        // sign of the permutation k -> p(k) by cycle counting (used[] is reused as the visited flag)
+        int sign = 1;
+        for (int r = 0; r < n; ++r) used[r] = 0;
+        for (int r = 0; r < n; ++r) {
+            if (used[r]) continue;
+            int len = 0, x = r;
+            while (!used[x]) { used[x] = 1; x = pcol[x]; ++len; }
+            if ((len & 1) == 0) sign = -sign;
+        }
+        out[0] = sign * s_det;
+        out[1] = s_max > 0.0 ? s_min / s_max : 0.0;
+    }
 }
 
 // entry-level density of one spin block: P[s][t] = Minv[pos_ket(t)][pos_bra(s)], 0 when an entry has no slot of this spin

@@ -1,10 +1,13 @@
 #include "vb_setup.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 
 namespace vb {
 
@@ -162,19 +165,19 @@ ExpOrb expand_orbital(const Input& in, const Basis& bas, const std::vector<std::
 }
 
 // ---------------------------------------------------------------------------
-static double binom(int n, int k)
-{
-    double r = 1.0;
-    for (int i = 0; i < k; ++i) r = r * (n - i) / (i + 1);
-    return r;
-}
-
 // Fold the horizontal recurrence into a cartesian pair density d[a][b]
 // (shell A carries la >= lb):  sum_ab d[a][b] (ab| = sum_e dt[e] (e0|,
 //   (x-B)^b = sum_k C(b,k) (A-B)^(b-k) (x-A)^k   per cartesian direction.
 static void hrr_fold(int la, int lb, const double* AB, const double* d /*[na][nb]*/, double* dt /*[pt_ne]*/)
 {
     const int na = ncart(la), nb = ncart(lb), e0 = coff(la);
+    if (lb == 0) {                       // nothing to shift: e = a
+        for (int a = 0; a < na; ++a) dt[a] += d[a];
+        return;
+    }
+    static const double BIN[3][3] = {{1, 0, 0}, {1, 1, 0}, {1, 2, 1}};
+    double pw[3][3];
+    for (int k = 0; k < 3; ++k) { pw[k][0] = 1.0; pw[k][1] = AB[k]; pw[k][2] = AB[k] * AB[k]; }
     for (int a = 0; a < na; ++a) {
         int ca = coff(la) + a, ax = c_lx(ca), ay = c_ly(ca), az = c_lz(ca);
         for (int b = 0; b < nb; ++b) {
@@ -184,8 +187,7 @@ static void hrr_fold(int la, int lb, const double* AB, const double* d /*[na][nb
             for (int kx = 0; kx <= bx; ++kx)
                 for (int ky = 0; ky <= by; ++ky)
                     for (int kz = 0; kz <= bz; ++kz) {
-                        double f = binom(bx, kx) * binom(by, ky) * binom(bz, kz) * std::pow(AB[0], bx - kx) *
-                                   std::pow(AB[1], by - ky) * std::pow(AB[2], bz - kz);
+                        double f = BIN[bx][kx] * BIN[by][ky] * BIN[bz][kz] * pw[0][bx - kx] * pw[1][by - ky] * pw[2][bz - kz];
                         dt[cidx(ax + kx, ay + ky, az + kz) - e0] += v * f;
                     }
         }
@@ -261,6 +263,38 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
     // --- pair groups --------------------------------------------------------
     const double SQ2PI54 = std::sqrt(2.0) * std::pow(PI, 1.25);
     const int ng = (int)ts.groups.size();
+    const int nshell = (int)bas.shells.size();
+    // per shell: most diffuse exponent, largest |contraction weight| (cheap far-field bound)
+    std::vector<double> sh_emin(nshell), sh_cmax(nshell);
+    for (int s = 0; s < nshell; ++s) {
+        const GShell& g = bas.shells[s];
+        double em = 1e300, cm = 0.0;
+        for (int k = 0; k < g.nprim; ++k) { em = std::min(em, bas.exps[g.prim_off + k]); cm = std::max(cm, std::fabs(bas.coefs[g.prim_off + k])); }
+        sh_emin[s] = em; sh_cmax[s] = cm;
+    }
+    // per orbital: largest sum_c |weight * angn| over its shells (bounds any cartesian pair density)
+    std::vector<double> orb_cabs(orbs.size(), 0.0);
+    for (size_t o = 0; o < orbs.size(); ++o)
+        for (const OrbShell& x : orbs[o].sh) {
+            const int l = bas.shells[x.gshell].l;
+            double a = 0.0;
+            for (int c = 0; c < ncart(l); ++c) a += std::fabs(x.c[c] * bas.angn[coff(l) + c]);
+            orb_cabs[o] = std::max(orb_cabs[o], a);
+        }
+    // per group, entry and group shell: the entry's bra / ket orbital on that shell (or null)
+    std::vector<std::vector<const OrbShell*>> grp_bra(ng), grp_ket(ng);
+    for (int g = 0; g < ng; ++g) {
+        const EntryGroup& G = ts.groups[g];
+        const size_t nsh = G.shells.size();
+        grp_bra[g].assign(G.entries.size() * nsh, nullptr);
+        grp_ket[g].assign(G.entries.size() * nsh, nullptr);
+        for (size_t ei = 0; ei < G.entries.size(); ++ei)
+            for (size_t xi = 0; xi < nsh; ++xi) {
+                const int sl = wf.slot(G.entries[ei], 0);
+                grp_bra[g][ei * nsh + xi] = find_shell(orbs[wf.bra[sl]], G.shells[xi]);
+                grp_ket[g][ei * nsh + xi] = find_shell(orbs[wf.ket[sl]], G.shells[xi]);
+            }
+    }
     struct TmpSP {
         int type, A, B;
         bool swapped;
@@ -268,23 +302,42 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         std::vector<PrimPair> pp;
         std::vector<double> dt;   // folded density [nE][np]
     };
-    std::vector<double> dcart(36), dfold(64);
+    struct PGOut {                // one pair group with offsets relative to its own arrays
+        bool used = false;
+        PGDesc pg;
+        std::vector<int> pairs;
+        std::vector<SPRec> sps;
+        std::vector<PrimPair> pps;
+        std::vector<double> dmat;
+        double wmax = 0.0;
+    };
     // one pair group; pass 0 only measures the largest primitive weight, pass 1 emits
-    auto do_pair_group = [&](int g, int h, int pass, double wcut) {
+    auto do_pair_group = [&](int g, int h, int pass, double wcut, PGOut& out) {
         const EntryGroup& G = ts.groups[g];
         const EntryGroup& H = ts.groups[h];
-        std::vector<int> pairs;
-        for (int s : G.entries)
-            for (int t : H.entries) {
+        std::vector<double> dcart(36), dfold(64);
+        std::vector<int>& pairs = out.pairs;
+        std::vector<int> pair_ei, pair_ti;   // positions of the pair's entries inside their groups
+        pairs.clear();
+        double dsum = 0.0;        // bound on sum_ab |d_ab| of any orbital pair of this group pair
+        for (size_t ei = 0; ei < G.entries.size(); ++ei)
+            for (size_t ti = 0; ti < H.entries.size(); ++ti) {
+                const int s = G.entries[ei], t = H.entries[ti];
                 if (wf.sym && g == h && t > s) continue;
                 pairs.push_back(s);
                 pairs.push_back(t);
+                pair_ei.push_back((int)ei);
+                pair_ti.push_back((int)ti);
+                dsum = std::max(dsum, orb_cabs[wf.bra[wf.slot(s, 0)]] * orb_cabs[wf.ket[wf.slot(t, 0)]]);
+                dsum = std::max(dsum, orb_cabs[wf.ket[wf.slot(s, 0)]] * orb_cabs[wf.bra[wf.slot(t, 0)]]);
             }
         const int np = (int)pairs.size() / 2;
         if (np == 0) return;
         std::vector<TmpSP> tsp;
-        for (int X : G.shells)
-            for (int Y : H.shells) {
+        const size_t nshG = G.shells.size(), nshH = H.shells.size();
+        for (size_t xi = 0; xi < nshG; ++xi)
+            for (size_t yi = 0; yi < nshH; ++yi) {
+                const int X = G.shells[xi], Y = H.shells[yi];
                 TmpSP sp;
                 sp.swapped = bas.shells[X].l < bas.shells[Y].l;
                 sp.A = sp.swapped ? Y : X;
@@ -295,18 +348,31 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                 const int na = ncart(sa.l), nb = ncart(sb.l), nE = pt_ne(sp.type), EA = pt_E(sp.type);
                 double AB[3] = {sa.r[0] - sb.r[0], sa.r[1] - sb.r[1], sa.r[2] - sb.r[2]};
                 double AB2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+                if (pass == 1) {
+                    // far-field rejection before any density is folded: every primitive weight of this
+                    // shell pair is below the bound built from the most diffuse primitives
+                    const double amin = sh_emin[sp.A], bmin = sh_emin[sp.B], pmin = amin + bmin;
+                    const double kb = sh_cmax[sp.A] * sh_cmax[sp.B] * std::exp(-amin * bmin / pmin * AB2) * SQ2PI54 / pmin;
+                    const double len = std::sqrt(AB2) + 1.0 / std::sqrt(pmin);
+                    const double abm = 1.0 + std::max(std::fabs(AB[0]), std::max(std::fabs(AB[1]), std::fabs(AB[2])));
+                    double db = dsum;
+                    for (int k = 0; k < sb.l; ++k) db *= abm;
+                    double poly = 0.0, lp = 1.0;
+                    for (int L = 0; L <= EA; ++L) { if (L >= sa.l) poly += db * lp * ncart(L); lp *= 2.0 * len; }
+                    if (!(kb * std::pow(2.0 * pmin, -0.25) * poly * wcut * 1.0001 >= tau)) continue;
+                }
                 // folded densities of every orbital pair on this shell pair
                 sp.dt.assign((size_t)nE * np, 0.0);
                 double dmaxL[EMAX + 1] = {0, 0, 0, 0, 0};   // max |folded density| per angular momentum of e
                 bool any = false;
                 for (int ip = 0; ip < np; ++ip) {
-                    int s = pairs[2 * ip], t = pairs[2 * ip + 1];
-                    const ExpOrb& ob = orbs[wf.bra[wf.slot(s, 0)]];   // bra-side orbital of the pair
-                    const ExpOrb& ok = orbs[wf.ket[wf.slot(t, 0)]];   // ket-side orbital
-                    // original orientation: X from group g (orbital ob), Y from group h (orbital ok)
-                    const OrbShell* cA = find_shell(sp.swapped ? ok : ob, sp.A);
-                    const OrbShell* cB = find_shell(sp.swapped ? ob : ok, sp.B);
-                    if (!cA || !cB) continue;
+                    // original orientation: X from group g (bra-side orbital of s), Y from group h (ket-side
+                    // orbital of t); A is whichever of the two carries the larger angular momentum
+                    const OrbShell* cX = grp_bra[g][pair_ei[ip] * nshG + xi];
+                    const OrbShell* cY = grp_ket[h][pair_ti[ip] * nshH + yi];
+                    if (!cX || !cY) continue;
+                    const OrbShell* cA = sp.swapped ? cY : cX;
+                    const OrbShell* cB = sp.swapped ? cX : cY;
                     bool nz = false;
                     for (int a = 0; a < na; ++a)
                         for (int b = 0; b < nb; ++b) {
@@ -346,12 +412,12 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                         double len = std::sqrt(pp.PAx * pp.PAx + pp.PAy * pp.PAy + pp.PAz * pp.PAz) + 1.0 / std::sqrt(p);
                         double poly = 0.0, lp = 1.0;
                         for (int L = 0; L <= EA; ++L) { if (L >= sa.l) poly += dmaxL[L] * lp * ncart(L); lp *= 2.0 * len; }
-                        pp.w = std::fabs(pp.Kp) * std::pow(2.0 * p, -0.25) * poly;
+                        pp.w = std::fabs(pp.Kp) / std::sqrt(std::sqrt(2.0 * p)) * poly;
                         if (pass == 1 && !(pp.w * wcut >= tau)) continue;
                         sp.wmax = std::max(sp.wmax, pp.w);
                         if (pass == 1) sp.pp.push_back(pp);
                     }
-                if (pass == 0) { ts.wmax = std::max(ts.wmax, sp.wmax); continue; }
+                if (pass == 0) { out.wmax = std::max(out.wmax, sp.wmax); continue; }
                 if (sp.pp.empty()) continue;
                 std::stable_sort(sp.pp.begin(), sp.pp.end(), [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
                 tsp.push_back(std::move(sp));
@@ -361,53 +427,95 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         std::stable_sort(tsp.begin(), tsp.end(), [](const TmpSP& a, const TmpSP& b) {
             return a.type != b.type ? a.type < b.type : a.wmax > b.wmax;
         });
-        PGDesc pg;
+        PGDesc& pg = out.pg;
         std::memset(&pg, 0, sizeof pg);
-        pg.g = g; pg.h = h; pg.np = np; pg.pair_beg = (int)ts.pg_pairs.size() / 2;
-        ts.pg_pairs.insert(ts.pg_pairs.end(), pairs.begin(), pairs.end());
+        pg.g = g; pg.h = h; pg.np = np; pg.pair_beg = 0;
         int ne = 0;
         for (const TmpSP& sp : tsp) ne += pt_ne(sp.type);
         pg.ne = ne;
-        pg.d_off = (long long)ts.dmat.size();
-        ts.dmat.resize(ts.dmat.size() + (((size_t)ne * np + 1) & ~(size_t)1), 0.0);   // keep blocks 16-byte aligned
-        double* D = ts.dmat.data() + pg.d_off;
+        pg.d_off = 0;
+        out.dmat.assign((((size_t)ne * np + 1) & ~(size_t)1), 0.0);   // keep blocks 16-byte aligned
+        double* D = out.dmat.data();
         int t_cur = 0, eoff = 0;
-        const int sp_base = (int)ts.sps.size();
-        std::vector<SPRec> recs;
+        std::vector<SPRec>& recs = out.sps;
+        recs.clear();
+        out.pps.clear();
         for (size_t k = 0; k < tsp.size(); ++k) {
             const TmpSP& sp = tsp[k];
-            while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
+            while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)out.pps.size(); ++t_cur; }
             const int nE = pt_ne(sp.type);
-            recs.push_back({sp.type, eoff, (int)ts.pps.size(), (int)sp.pp.size(), sp.wmax, 0.0});
+            recs.push_back({sp.type, eoff, (int)out.pps.size(), (int)sp.pp.size(), sp.wmax, 0.0});
             pg.kwmax[sp.type] = std::max(pg.kwmax[sp.type], sp.wmax);
-            for (PrimPair pp : sp.pp) { pp.eoff = eoff; pp.pad = 0; pp.wseg = sp.wmax; ts.pps.push_back(pp); }
+            for (PrimPair pp : sp.pp) { pp.eoff = eoff; pp.pad = 0; pp.wseg = sp.wmax; out.pps.push_back(pp); }
             std::copy(sp.dt.begin(), sp.dt.end(), D + (size_t)eoff * np);
             eoff += nE;
         }
-        while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)ts.pps.size(); ++t_cur; }
+        while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)out.pps.size(); ++t_cur; }
         // per type, most expensive shell pairs first (they are dealt round-robin to the warps)
         std::stable_sort(recs.begin(), recs.end(), [](const SPRec& a, const SPRec& b) {
             return a.type != b.type ? a.type < b.type : a.pp_cnt > b.pp_cnt;
         });
-        ts.sps.insert(ts.sps.end(), recs.begin(), recs.end());
         {
             int k = 0;
             for (int t = 0; t <= NPTYPE; ++t) {
                 while (k < (int)recs.size() && recs[k].type < t) ++k;
-                pg.sp_beg[t] = sp_base + k;
+                pg.sp_beg[t] = k;
             }
         }
-        ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
-        ts.max_nsp = std::max(ts.max_nsp, (int)recs.size());
-        ts.max_ne = std::max(ts.max_ne, ne);
-        ts.max_np = std::max(ts.max_np, np);
-        ts.pgs.push_back(pg);
+        out.used = true;
     };
     // pass 0: the largest weights live in the one-group pair groups
-    for (int g = 0; g < ng; ++g) do_pair_group(g, g, 0, 0.0);
+    for (int g = 0; g < ng; ++g) { PGOut o; do_pair_group(g, g, 0, 0.0, o); ts.wmax = std::max(ts.wmax, o.wmax); }
     const double wcut = ts.wmax;
+    // pass 1 over all group pairs, on the host cores; merged in (g,h) order so the layout (and with it
+    // every reduction order on the device) does not depend on the thread count
+    std::vector<std::pair<int, int>> gh;
     for (int g = 0; g < ng; ++g)
-        for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h) do_pair_group(g, h, 1, wcut);
+        for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h) gh.emplace_back(g, h);
+    std::vector<PGOut> outs(gh.size());
+    {
+        int nthr = (int)std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("VB_HOST_THREADS")) nthr = std::atoi(e);
+        nthr = std::max(1, std::min(nthr, 32));
+        if (gh.size() < 64) nthr = 1;
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                size_t i0 = next.fetch_add(16);
+                if (i0 >= gh.size()) break;
+                for (size_t i = i0; i < std::min(gh.size(), i0 + 16); ++i) do_pair_group(gh[i].first, gh[i].second, 1, wcut, outs[i]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread& t : pool) t.join();
+    }
+    {
+        size_t n_pairs = 0, n_sps = 0, n_pps = 0, n_d = 0, n_pg = 0;
+        for (const PGOut& o : outs)
+            if (o.used) { n_pairs += o.pairs.size(); n_sps += o.sps.size(); n_pps += o.pps.size(); n_d += o.dmat.size(); ++n_pg; }
+        ts.pg_pairs.reserve(n_pairs); ts.sps.reserve(n_sps); ts.pps.reserve(n_pps); ts.dmat.reserve(n_d); ts.pgs.reserve(n_pg);
+    }
+    for (PGOut& o : outs) {
+        if (!o.used) continue;
+        PGDesc pg = o.pg;
+        const int pp0 = (int)ts.pps.size(), sp0 = (int)ts.sps.size();
+        pg.pair_beg = (int)ts.pg_pairs.size() / 2;
+        pg.d_off = (long long)ts.dmat.size();
+        for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += pp0; pg.sp_beg[t] += sp0; }
+        for (SPRec& r : o.sps) r.pp_beg += pp0;
+        ts.pg_pairs.insert(ts.pg_pairs.end(), o.pairs.begin(), o.pairs.end());
+        ts.sps.insert(ts.sps.end(), o.sps.begin(), o.sps.end());
+        ts.pps.insert(ts.pps.end(), o.pps.begin(), o.pps.end());
+        ts.dmat.insert(ts.dmat.end(), o.dmat.begin(), o.dmat.end());
+        ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
+        ts.max_nsp = std::max(ts.max_nsp, (int)o.sps.size());
+        ts.max_ne = std::max(ts.max_ne, pg.ne);
+        ts.max_np = std::max(ts.max_np, pg.np);
+        ts.pgs.push_back(pg);
+        PGOut().pairs.swap(o.pairs); std::vector<double>().swap(o.dmat); std::vector<PrimPair>().swap(o.pps);
+    }
     for (const GShell& s : bas.shells) ts.lmax = std::max(ts.lmax, s.l);
 }
 
