@@ -393,9 +393,13 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
     const bool gen = ts.lmax >= 2;
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
-    const int dq_cap2 = (dq_cap + 1) & ~1, hs_cap = ts.max_ne * 32, sp_cap = std::max(1, ts.max_nsp);
+    const int hs_ld = std::max(1, ts.max_np) | 1;
+    const int dq_cap2 = (dq_cap + 1) & ~1, hs_cap = (ts.max_ne * hs_ld + 1) & ~1, sp_cap = std::max(1, ts.max_nsp);
     int pp_cap = std::max(1, ts.max_npp);
+    int strip_ld = (std::max(4, ts.max_ks) + 3) & ~3;
+    while (strip_ld % 16 != 4) strip_ld += 4;          // A-fragment loads of 8 rows x 4 columns hit distinct banks
     size_t smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
+    if (!gen) smem += (size_t)(TILE_THREADS / 32) * STRIP_ROWS * strip_ld * sizeof(double);
     const size_t smem_budget = gen ? 225 * 1024 : (225 * 1024) / VB_MINBLOCKS;
     if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= smem_budget) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
     else pp_cap = 0;   // primitive tables stay in global memory
@@ -418,7 +422,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
-    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = strip_ld; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;

@@ -511,6 +511,11 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         ts.dmat.insert(ts.dmat.end(), o.dmat.begin(), o.dmat.end());
         ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
         ts.max_nsp = std::max(ts.max_nsp, (int)o.sps.size());
+        {
+            int ks[NPTYPE] = {0, 0, 0, 0, 0, 0};
+            for (const SPRec& r : o.sps) ks[r.type] += pt_ne(r.type);
+            for (int t = 0; t < NPTYPE; ++t) ts.max_ks = std::max(ts.max_ks, ks[t]);
+        }
         ts.max_ne = std::max(ts.max_ne, pg.ne);
         ts.max_np = std::max(ts.max_np, pg.np);
         ts.pgs.push_back(pg);

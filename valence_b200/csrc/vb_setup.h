@@ -79,6 +79,7 @@ struct TileSetup {
     double wmax = 0.0;              // largest primitive-pair magnitude bound (for pruning)
     std::vector<double> dmat;       // folded densities, per pair group [e][p]
     int max_ne = 0, max_np = 0, max_npp = 0, max_nsp = 0;
+    int max_ks = 0;                 // widest e-range of one pair type inside a pair group
     int lmax = 0;
 };
 
