@@ -15,6 +15,7 @@
 
 #include "vb_cofactor.h"
 #include "vb_kernels.cuh"
+#include "vb_ptile.cuh"
 #include "vb_tile.cuh"
 
 namespace vb {
@@ -387,22 +388,29 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     // magnitude cuts: the Schwarz (diagonal) pass must resolve (st|st) down to itol^2, the energy pass
     // needs the integrals to ~itol; never looser than the configured tau
     const double tau_diag = std::min(tau, 0.01 * itol * itol), tau_energy = std::min(tau, 0.01 * itol);
+    int bas_lmax = 0;
+    for (const GShell& gs : bas.shells) bas_lmax = std::max(bas_lmax, gs.l);
+    const bool gen = bas_lmax >= 2;   // d shells: shell-pair kernel with the loop-based recurrence (k_tile<true>)
     TileSetup ts;
-    build_tiles(in, bas, wf, orbs2e, tau_diag, &ts);
+    build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts);
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
-    const bool gen = ts.lmax >= 2;
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
     const int hs_ld = std::max(1, ts.max_np) | 1;
     const int dq_cap2 = (dq_cap + 1) & ~1, hs_cap = (ts.max_ne * hs_ld + 1) & ~1, sp_cap = std::max(1, ts.max_nsp);
+    const int g_cap = (ts.max_np * ts.max_np + 1) & ~1;
     int pp_cap = std::max(1, ts.max_npp);
-    int strip_ld = (std::max(4, ts.max_ks) + 3) & ~3;
-    while (strip_ld % 16 != 4) strip_ld += 4;          // A-fragment loads of 8 rows x 4 columns hit distinct banks
-    size_t smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
-    if (!gen) smem += (size_t)(TILE_THREADS / 32) * STRIP_ROWS * strip_ld * sizeof(double);
-    const size_t smem_budget = gen ? 225 * 1024 : (225 * 1024) / VB_MINBLOCKS;
-    if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= smem_budget) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
-    else pp_cap = 0;   // primitive tables stay in global memory
+    size_t smem;
+    if (gen) {
+        smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
+        if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
+        else pp_cap = 0;   // primitive tables stay in global memory
+    } else {
+        constexpr int nw = TILE_THREADS / 32;
+        smem = (2 * (size_t)dq_cap2 + (size_t)nw * g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double);
+        if (smem + (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += (size_t)pp_cap * sizeof(PrimPair);
+        else pp_cap = 0;
+    }
     if (smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
     for (int s = 0; s < nso; ++s) {
@@ -412,24 +420,24 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
     pps.upload(ts.pps, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
-    int grid_cap = nsm * VB_MINBLOCKS;
+    int grid_cap = nsm;
     if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
     if (gen) CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(k_ptile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
     A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
-    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = strip_ld; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = 0; A.g_cap = g_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;
     auto launch = [&](int ntiles_mine) {
         int grid = std::max(1, std::min(grid_cap, ntiles_mine));
         if (gen) k_tile<true><<<grid, TILE_THREADS, smem, st>>>(A);
-        else k_tile<false><<<grid, TILE_THREADS, smem, st>>>(A);
+        else k_ptile<<<grid, TILE_THREADS, smem, st>>>(A);
         CK(cudaGetLastError());
         launches++;
     };

@@ -45,6 +45,7 @@ struct TileArgs {
     int dq_cap;                      // doubles reserved for the staged ket density
     int hs_cap, pp_cap, sp_cap;      // shared-memory capacities: H tile (doubles), primitive pairs per side, shell pairs
     int hs_ld, strip_ld;             // row strides of the H tile and of the per-warp integral strips
+    int g_cap;                       // k_ptile: doubles per warp-private G[q][p] partial
     double* diag;                    // mode 0: (s,t) -> (st|st)
     const double* sch;               // mode 1: Schwarz table as the reference indexes it, nso*nso
     double itol;

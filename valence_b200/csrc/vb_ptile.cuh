@@ -1,0 +1,339 @@
+// The fused hot kernel for s/p basis sets (every class up to (pp|pp)), primitive-level formulation.
+//
+// For one tile (bra pair group P, ket pair group Q) the orbital-level integrals are
+//     G[q][p] = sum_{k,f} sum_{b,e}  Dq[e_k + f][q] * [b,e | k,f] * Dp[e_b + e][p]
+// with b / k running over the *primitive* pairs of P / Q (flat lists per pair type, sorted by
+// magnitude) and Dp / Dq the HRR-folded pair densities of the primitive's shell pair.  Written like
+// this the contraction of primitives into shells, and both density transformations, are two dense
+// matrix products around the matrix of primitive integrals -- and they run on the FP64 tensor cores:
+//
+//   lane (g = lane/4, t = lane%4) of a warp evaluates ONE primitive quartet (ket primitive g of an
+//   octet, bra primitive t of a quad) by the Obara-Saika recurrence and feeds each component
+//   straight into DMMA m8n8k4 as the A fragment  A[g][t];  B[t][n] = Dp[e_b + e][n] comes from the
+//   staged bra densities, and X_f[k][p] (8 ket primitives x 32 orbital pairs) accumulates in the
+//   C fragments while the warp walks all bra primitives.  No shuffles, no per-shell reductions,
+//   no divergence; pruning by magnitude works at (octet x quad) granularity.
+//   After the bra loop a second DMMA product folds the 8 ket primitives with Dq into G.
+//
+// (replaces int2e, valence.F90:3184-3438, and the 2e loop of vsvb_energy, :1153-1433; the screening
+// and bookkeeping of the contraction phase follow the reference line by line, see below)
+#pragma once
+#include "vb_tile.cuh"
+
+namespace vb {
+
+constexpr int PT_SLD = 33;                      // row stride of the per-warp X scratch (8 x 32 doubles)
+constexpr int PT_SCRATCH = 8 * PT_SLD + 1;      // doubles per warp (odd row stride, even total keeps the next region aligned)
+
+// one primitive quartet per lane, results consumed by the tensor cores
+template <int TB, int TK>
+__device__ __forceinline__ void pstep(const double* __restrict__ boys_tab, const PrimPair& a, const PrimPair& b,
+                                      const double* __restrict__ Dp_s, int npP, int g, double (&X)[pt_ne(TK)][4][2])
+{
+    constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
+    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    QuartetGeom geo;
+    double T, pref;
+    quartet_geom(a, b, geo, T, pref);
+    double F[M + 1];
+    boys<M>(boys_tab, T, F);
+#pragma unroll
+    for (int m = 0; m <= M; ++m) F[m] *= pref;
+    double acc[NE * NF];
+#pragma unroll
+    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+    if constexpr (M == 0) acc[0] = F[0];
+    else vrr_unrolled<LA, EA, LC, EC>(geo, F, acc);
+    const double* drow = Dp_s + a.eoff * npP + g;      // B[t][n = 8j + g] = Dp[e_b + e][8j + g]
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double bf = drow[e * npP + 8 * j];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) dmma_884(X[f][j][0], X[f][j][1], acc[e * NF + f], bf);
+        }
+}
+
+// One warp task: a ket octet of pair type TK against every bra primitive of P.
+template <int TK>
+__device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const PGDesc& Q, int oct, const PrimPair* __restrict__ bpps,
+                                      const double* __restrict__ Dp_s, const double* __restrict__ Dq_s, double* __restrict__ scratch,
+                                      double* __restrict__ Gw, int lane, unsigned long long* __restrict__ s_pq)
+{
+    constexpr int NF = pt_ne(TK);
+    const int g = lane >> 2, t = lane & 3;
+    const int nk = Q.pp_beg[TK + 1] - Q.pp_beg[TK];
+    const PrimPair* __restrict__ kl = A.pps + Q.pp_beg[TK];
+    const int k0 = 8 * oct;
+    const bool kact = k0 + g < nk;
+    PrimPair b = kl[k0 + (kact ? g : 0)];
+    if (!kact) b.Kp = 0.0;
+    const double wk = kl[k0].w;                        // the octet's largest magnitude (lists are sorted)
+    const int nkact = min(8, nk - k0);
+    double X[NF][4][2];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { X[f][j][0] = 0.0; X[f][j][1] = 0.0; }
+    bool any = false;
+    sfor<0, 3>([&](auto TBc) {
+        constexpr int TB = TBc;
+        const int nb = P.pp_beg[TB + 1] - P.pp_beg[TB];
+        const PrimPair* __restrict__ bl = bpps + (P.pp_beg[TB] - P.pp_beg[0]);
+        unsigned long long npq = 0ull;
+        for (int b0 = 0; b0 < nb; b0 += 4) {
+            if (!(bl[b0].w * wk >= A.tau)) break;      // sorted by magnitude: nothing below matters either
+            const bool bact = b0 + t < nb;
+            PrimPair a = bl[b0 + (bact ? t : 0)];
+            if (!bact) a.Kp = 0.0;
+            pstep<TB, TK>(A.boys, a, b, Dp_s, P.np, g, X);
+            npq += (unsigned long long)(min(4, nb - b0) * nkact);
+        }
+        if (npq) {
+            any = true;
+            if (lane == 0) atomicAdd(&s_pq[TB * NPTYPE + TK], npq);
+        }
+    });
+    if (!any) return;
+    // G[q][p] += sum_{k,f} Dq[e_k + f][q] X_f[k][p]:  A'[q][k] from the staged ket densities, B'[k][p] = X_f
+    // re-laid out through the warp's scratch (C fragment -> B fragment).
+    double C[4][4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
+    const int eo_own = b.eoff;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            scratch[g * PT_SLD + 8 * j + 2 * t] = X[f][j][0];
+            scratch[g * PT_SLD + 8 * j + 2 * t + 1] = X[f][j][1];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int kk = 4 * s + t;                                   // ket primitive this lane supplies
+            const int eo = __shfl_sync(0xffffffffu, eo_own, 4 * kk);    // lane 4*kk evaluates primitive kk
+            double bfr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bfr[j] = scratch[kk * PT_SLD + 8 * j + g];
+            const double* arow = Dq_s + (eo + f) * Q.np + g;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const double af = arow[8 * m];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_884(C[m][j][0], C[m][j][1], af, bfr[j]);
+            }
+        }
+    }
+    // warp-private accumulation (fixed order inside a warp; the warps are summed in fixed order later)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int q = 8 * m + g;
+        if (q >= Q.np) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int p = 8 * j + 2 * t + i;
+                if (p < P.np) Gw[q * P.np + p] += C[m][j][i];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int nw = TILE_THREADS / 32;
+    double* Dp_s = smem;                                        // [P.ne][P.np]
+    double* Dq_s = Dp_s + A.dq_cap;                             // [Q.ne][Q.np]
+    double* Gws = Dq_s + A.dq_cap;                              // per-warp G[q][p] partials, nw x g_cap
+    double* scr = Gws + nw * A.g_cap;                           // per-warp X scratch
+    PrimPair* bpp_s = reinterpret_cast<PrimPair*>(scr + nw * PT_SCRATCH);   // bra primitive pairs of P (when they fit)
+    __shared__ unsigned long long s_bar;
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __shared__ int s_tile, s_unit;
+    __shared__ int s_cum[4];
+    __shared__ double s_red[nw];
+    __shared__ unsigned long long s_cnt[CNT_N];
+    __shared__ unsigned long long s_pq[NPTYPE * NPTYPE];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < CNT_N) s_cnt[tid] = 0ull;
+    if (tid < NPTYPE * NPTYPE) s_pq[tid] = 0ull;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
+        __syncthreads();
+        const long long tl = (long long)A.tile_first + (long long)s_tile * A.tile_stride;
+        if (tl >= A.ntiles) break;
+        const int2 tq = A.tiles[tl];
+        const PGDesc P = A.pgs[tq.x];
+        const PGDesc Q = A.pgs[tq.y];
+        const int nbpp = P.pp_beg[NPTYPE] - P.pp_beg[0];
+        if (tid == 0) {
+            // the buffers were last read through the generic proxy (previous tile): order before async writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned bp = (unsigned)((((size_t)P.ne * P.np + 1) & ~(size_t)1) * sizeof(double));
+            const unsigned bq = (unsigned)((((size_t)Q.ne * Q.np + 1) & ~(size_t)1) * sizeof(double));
+            const unsigned bb = A.pp_cap ? (unsigned)(nbpp * sizeof(PrimPair)) : 0u;
+            mbar_expect_tx(&s_bar, bp + bq + bb);
+            tma_bulk_g2s(Dp_s, A.dmat + P.d_off, bp, &s_bar);
+            tma_bulk_g2s(Dq_s, A.dmat + Q.d_off, bq, &s_bar);
+            if (A.pp_cap) tma_bulk_g2s(bpp_s, A.pps + P.pp_beg[0], bb, &s_bar);
+            int n = 0;
+            for (int tk = 0; tk < 3; ++tk) {
+                s_cum[tk] = n;
+                const int nk = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+                if (nk > 0) n += (nk + 7) >> 3;
+            }
+            s_cum[3] = n;
+            s_unit = 0;
+        }
+        const PrimPair* bpps = A.pp_cap ? bpp_s : A.pps + P.pp_beg[0];
+        const int gsz = P.np * Q.np;
+        for (int i = tid; i < nw * A.g_cap; i += TILE_THREADS) Gws[i] = 0.0;
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        __syncthreads();
+
+        // ---- primitive integrals + both density transformations (tensor cores) ----------------
+        //   energy pass : ket octets are handed out through a shared counter (dynamic);
+        //   Schwarz pass: dealt round-robin (static), so the table is bitwise reproducible and
+        //                 identical on every rank (the tile list is derived from it).
+        const int nunits = s_cum[3];
+        const bool dynamic = A.mode != 0;
+        double* Gw = Gws + warp * A.g_cap;
+        double* scratch = scr + warp * PT_SCRATCH;
+        int ustat = warp - nw;
+        for (;;) {
+            int u;
+            if (dynamic) {
+                u = 0;
+                if (lane == 0) u = atomicAdd(&s_unit, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+            } else {
+                ustat += nw;
+                u = ustat;
+            }
+            if (u >= nunits) break;
+            const int tk = u >= s_cum[2] ? 2 : (u >= s_cum[1] ? 1 : 0);
+            const int oct = u - s_cum[tk];
+            switch (tk) {
+                case 0: ptask<0>(A, P, Q, oct, bpps, Dp_s, Dq_s, scratch, Gw, lane, s_pq); break;
+                case 1: ptask<1>(A, P, Q, oct, bpps, Dp_s, Dq_s, scratch, Gw, lane, s_pq); break;
+                default: ptask<2>(A, P, Q, oct, bpps, Dp_s, Dq_s, scratch, Gw, lane, s_pq); break;
+            }
+        }
+        __syncthreads();
+        // fixed-order sum of the warp partials -> Gws[0 .. gsz)
+        for (int i = tid; i < gsz; i += TILE_THREADS) {
+            double v = Gws[i];
+#pragma unroll
+            for (int w = 1; w < nw; ++w) v += Gws[w * A.g_cap + i];
+            Gws[i] = v;
+        }
+        __syncthreads();
+
+        // ---- contraction with the cofactor densities --------------------------------------
+        double epart = 0.0;
+        unsigned long long cnt[CNT_N];
+#pragma unroll
+        for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
+        const bool diag_tile = tq.x == tq.y;
+        const int nso = A.nso;
+        for (int idx = tid; idx < gsz; idx += TILE_THREADS) {
+            const int p = idx / Q.np, q = idx % Q.np;
+            if (diag_tile && q > p) continue;
+            const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
+            const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
+            if (A.mode == 0) {
+                if (diag_tile && p == q) {
+                    const double G = Gws[q * P.np + p];
+                    A.diag[(size_t)s * nso + t] = G;
+                    if (A.sym) A.diag[(size_t)t * nso + s] = G;
+                }
+                continue;
+            }
+            // reference screen on the Schwarz product (valence.F90:1189-1190); screened entries
+            // contribute nothing and are counted nowhere
+            const bool ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
+            if (!ssig) continue;
+            const double G = Gws[q * P.np + p];
+            // images of (s,t,u,v) under the integral's permutational symmetry
+            int im[8][4];
+            int nim = 0;
+            {
+                const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
+                for (int k = 0; k < 2; ++k) {
+                    const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
+                    im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
+                    if (A.sym) {
+                        im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
+                        im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
+                        im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
+                    }
+                }
+            }
+            double wsum = 0.0;
+            cnt[CNT_ENTRIES]++;
+            for (int k = 0; k < nim; ++k) {
+                const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
+                bool dup = false;
+                for (int k2 = 0; k2 < k; ++k2)
+                    dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
+                if (dup) continue;
+                // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
+                const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
+                const double val = shortcut ? A.sch[a * nso + b] * A.sch[a * nso + b] : G;
+                const bool vsig = fabs(val) > A.itol;
+                // as the direct integral of task io=a, ko=b, jo=c, lo=d
+                bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+                if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
+                // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
+                bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+                if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
+                if (vd) { cnt[CNT_SCHWARZ_EREP]++; cnt[CNT_VALUE_EREP] += vsig; }
+                if (vx) { cnt[CNT_SCHWARZ_EXCH]++; cnt[CNT_VALUE_EXCH] += vsig; }
+                if (!shortcut) {
+                    const int calls = (vd ? 1 : 0) + ((vx && b != d) ? 1 : 0);
+                    cnt[CNT_INT2E] += calls;
+                    cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
+                }
+                if (shortcut && vd) cnt[CNT_SHORTCUT]++;
+                if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
+                if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
+            }
+            epart += 0.5 * wsum;
+        }
+        if (A.mode == 1) {
+            // deterministic block reduction of the tile's energy; counters: one shared atomic per warp
+            for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
+            if (lane == 0) s_red[warp] = epart;
+#pragma unroll
+            for (int i = 0; i < CNT_N; ++i) {
+                unsigned long long c = cnt[i];
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+                if (lane == 0 && c) atomicAdd(&s_cnt[i], c);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double e = 0.0;
+                for (int w = 0; w < nw; ++w) e += s_red[w];
+                A.tileE[tl] = e * A.c0;
+            }
+        }
+    }
+    // one flush per CTA (same-address global atomics per tile would serialise in L2)
+    __syncthreads();
+    if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
+    if (tid < NPTYPE * NPTYPE && s_pq[tid]) atomicAdd(&A.pq_counters[tid], s_pq[tid]);
+}
+
+}  // namespace vb

@@ -202,7 +202,7 @@ static const OrbShell* find_shell(const ExpOrb& o, int gshell)
 }
 
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs,
-                 double tau, TileSetup* out)
+                 double tau, bool flat, TileSetup* out)
 {
     (void)in;
     TileSetup& ts = *out;
@@ -451,6 +451,10 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             eoff += nE;
         }
         while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)out.pps.size(); ++t_cur; }
+        if (flat)   // one magnitude-sorted list per pair type (each primitive carries its shell pair's e-offset)
+            for (int t = 0; t < NPTYPE; ++t)
+                std::stable_sort(out.pps.begin() + pg.pp_beg[t], out.pps.begin() + pg.pp_beg[t + 1],
+                                 [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
         // per type, most expensive shell pairs first (they are dealt round-robin to the warps)
         std::stable_sort(recs.begin(), recs.end(), [](const SPRec& a, const SPRec& b) {
             return a.type != b.type ? a.type < b.type : a.pp_cnt > b.pp_cnt;

@@ -95,7 +95,9 @@ bool obs_position(const Input& in, const Basis& bas, int orb, int pos, int* gshe
 
 // tau: primitive pairs whose largest possible contribution to any orbital-level integral stays
 // below tau are dropped at set-up (0 keeps everything the reference computes)
+// flat: primitive pairs of a pair group sorted by magnitude inside each pair type, across shell pairs
+// (k_ptile); otherwise grouped by shell pair (k_tile, d shells)
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs2e,
-                 double tau, TileSetup* out);
+                 double tau, bool flat, TileSetup* out);
 
 }  // namespace vb
