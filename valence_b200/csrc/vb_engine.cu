@@ -102,12 +102,12 @@ struct Engine::Impl {
     std::vector<std::vector<double>> coeff;          // current orbital weights (normalised in energy())
     std::vector<double> xyz_angs;
     // device data
-    DBuf<double> boys, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
+    DBuf<double> boys, boys_small, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket, gj_n;
     DBuf<long long> gj_off, gj_poff;
     DBuf<double> oc;
-    DBuf<int2> opairs, tiles;
+    DBuf<int2> opairs, tiles, items;
     DBuf<PGDesc> pgs;
     DBuf<SPRec> sps;
         DBuf<PrimPair> pps;
@@ -148,6 +148,9 @@ Engine::Engine(const Input& in, int device) : in_(in), impl_(new Impl)
     std::vector<double> tab((size_t)BOYS_ROWS * BOYS_COLS);
     boys_make_table(tab.data());
     I.boys.upload(tab, I.st);
+    std::vector<double> tabs(BOYS_S_SIZE, 0.0);
+    boys_make_table_small(tabs.data());
+    I.boys_small.upload(tabs, I.st);
     I.xyz_angs = in.coords;
     I.coeff_sc = in.coeff_sc;
     if (const char* t = std::getenv("VB_PRIM_TAU")) I.tau = std::atof(t);
@@ -401,15 +404,17 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     const int g_cap = (ts.max_np * ts.max_np + 1) & ~1;
     int pp_cap = std::max(1, ts.max_npp);
     size_t smem;
+    int boys_cap = 0;
     if (gen) {
         smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
         if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
         else pp_cap = 0;   // primitive tables stay in global memory
     } else {
         constexpr int nw = TILE_THREADS / 32;
-        smem = (2 * (size_t)dq_cap2 + (size_t)nw * g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double);
+        smem = ((size_t)dq_cap2 + (size_t)PT_MAXQ * g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double);
         if (smem + (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += (size_t)pp_cap * sizeof(PrimPair);
         else pp_cap = 0;
+        if (smem + BOYS_S_SIZE * sizeof(double) <= 225 * 1024) { boys_cap = BOYS_S_SIZE; smem += BOYS_S_SIZE * sizeof(double); }
     }
     if (smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
@@ -430,7 +435,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
-    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = 0; A.g_cap = g_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = 0; A.g_cap = g_cap; A.boys_small = boys_small.p; A.boys_cap = boys_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;
@@ -448,12 +453,12 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         sch = *sch_in;
     } else {
         std::vector<double> dg;
-        std::vector<int2> dt(npg);
-        for (int i = 0; i < npg; ++i) dt[i] = make_int2(i, i);
-        tiles.upload(dt, st);
+        std::vector<int2> dt(npg), di(npg);
+        for (int i = 0; i < npg; ++i) { dt[i] = make_int2(i, i); di[i] = make_int2(i, 1); }
+        tiles.upload(dt, st); items.upload(di, st);
         diag.alloc((size_t)nso * nso);
         diag.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-        A.tiles = tiles.p; A.ntiles = npg; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
+        A.tiles = tiles.p; A.ntiles = npg; A.items = items.p; A.nitems = npg; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
         CK(cudaEventRecord(ev0, st));
         launch(npg);
         CK(cudaEventRecord(ev1, st));
@@ -483,25 +488,39 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     std::vector<int> order(npg);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ts.pgs[a].smax > ts.pgs[b].smax; });
+    // grouped by the bra pair group (the larger index), partners in order of decreasing Schwarz bound
     std::vector<int2> tl;
-    for (int i = 0; i < npg; ++i) {
-        const double si = ts.pgs[order[i]].smax;
-        for (int j = i; j < npg; ++j) {
-            if (!(si * ts.pgs[order[j]].smax > itol)) break;
-            int a = order[i], b = order[j];
-            tl.push_back(make_int2(std::max(a, b), std::min(a, b)));
+    std::vector<long long> run_beg;            // first tile of every bra pair group's run
+    for (int a = 0; a < npg; ++a) {
+        const double sa = ts.pgs[a].smax;
+        run_beg.push_back((long long)tl.size());
+        for (int j = 0; j < npg; ++j) {
+            const int b = order[j];
+            if (!(sa * ts.pgs[b].smax > itol)) break;
+            if (b <= a) tl.push_back(make_int2(a, b));
         }
     }
+    run_beg.push_back((long long)tl.size());
     const long long ntiles = (long long)tl.size();
+    if (ntiles > 2000000000LL) throw std::runtime_error("valence_b200: tile list too long");
+    // work items of the s/p kernel: runs of <= m tiles sharing the bra pair group; the d-shell kernel takes single tiles
+    std::vector<int2> itl;
+    if (!gen) {
+        const long long m = std::max<long long>(1, std::min<long long>(PT_MAXQ, ntiles / ((long long)nsm * nranks * 16)));
+        for (int a = 0; a < npg; ++a)
+            for (long long k = run_beg[a]; k < run_beg[a + 1]; k += m)
+                itl.push_back(make_int2((int)k, (int)std::min<long long>(m, run_beg[a + 1] - k)));
+    }
+    const long long nunits_total = gen ? ntiles : (long long)itl.size();
     long long mine = 0;
-    for (long long k = rank; k < ntiles; k += nranks) mine++;
+    for (long long k = rank; k < nunits_total; k += nranks) mine++;
     double t4 = now_ms();
     // ---- energy pass ---------------------------------------------------------------------------------
     this->sch.upload(sch, st);
-    tiles.upload(tl, st);
+    tiles.upload(tl, st); items.upload(itl, st);
     tileE.alloc((size_t)std::max<long long>(ntiles, 1));
     tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-    A.tiles = tiles.p; A.ntiles = (int)ntiles; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
+    A.tiles = tiles.p; A.ntiles = (int)ntiles; A.items = items.p; A.nitems = (int)itl.size(); A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
     A.sch = this->sch.p; A.tileE = tileE.p;
     CK(cudaEventRecord(ev2, st));
     if (mine > 0) launch((int)mine);

@@ -125,6 +125,56 @@ VB_HD void boys(const double* __restrict__ tab, double T, double* F)   // F[0..M
     }
 }
 
+// Compact table for the s/p kernel (orders <= 4), small enough to live in shared memory:
+// step 1/8, T < 40, 9-term Taylor series (|dT| <= 1/16 -> remainder < 3e-18), F_0 .. F_12 per row.
+constexpr int BOYS_S_COLS = 13;
+constexpr double BOYS_S_STEP = 0.125, BOYS_S_TMAX = 40.0;
+constexpr int BOYS_S_ROWS = 321;
+constexpr int BOYS_S_SIZE = (BOYS_S_ROWS * BOYS_S_COLS + 1) & ~1;
+
+inline void boys_make_table_small(double* tab)
+{
+    for (int k = 0; k < BOYS_S_ROWS; ++k) boys_reference(BOYS_S_COLS - 1, k * BOYS_S_STEP, tab + (size_t)k * BOYS_S_COLS);
+}
+
+VB_HD double boys_taylor9(const double* __restrict__ r, double d)   // sum_j r[j] d^j / j!, j < 9
+{
+    double f = r[8] * (1.0 / 40320.0);
+    f = f * d + r[7] * (1.0 / 5040.0);
+    f = f * d + r[6] * (1.0 / 720.0);
+    f = f * d + r[5] * (1.0 / 120.0);
+    f = f * d + r[4] * (1.0 / 24.0);
+    f = f * d + r[3] * (1.0 / 6.0);
+    f = f * d + r[2] * 0.5;
+    f = f * d + r[1];
+    return f * d + r[0];
+}
+
+template <int M>
+VB_HD void boys_s(const double* __restrict__ tab, double T, double* F)   // F[0..M], M <= 4
+{
+    static_assert(M + 9 <= BOYS_S_COLS, "compact Boys table too narrow");
+    if (T < BOYS_S_TMAX) {
+        const int k = (int)(T * (1.0 / BOYS_S_STEP) + 0.5);
+        const double d = k * BOYS_S_STEP - T;
+        const double* r = tab + k * BOYS_S_COLS;
+        if constexpr (M <= 2) {
+#pragma unroll
+            for (int m = 0; m <= M; ++m) F[m] = boys_taylor9(r + m, d);
+        } else {
+            F[M] = boys_taylor9(r + M, d);
+            const double eT = exp(-T), t2 = 2.0 * T;
+#pragma unroll
+            for (int m = M; m > 0; --m) F[m - 1] = (t2 * F[m] + eT) * (1.0 / (2.0 * m - 1.0));
+        }
+    } else {
+        const double r = rsqrt(T), rt = r * r;
+        F[0] = 0.88622692545275801365 * r;            // sqrt(pi)/2 / sqrt(T); exp(-T) < 5e-18 is dropped
+#pragma unroll
+        for (int m = 0; m < M; ++m) F[m + 1] = (m + 0.5) * F[m] * rt;
+    }
+}
+
 VB_HD void boys_rt(int M, const double* __restrict__ tab, double T, double* F)   // runtime order
 {
     if (T < BOYS_TMAX) {

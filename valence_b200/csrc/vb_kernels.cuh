@@ -38,6 +38,8 @@ struct TileArgs {
     const double* boys;
     const int2* tiles;
     int ntiles;
+    const int2* items;               // k_ptile work items: (first tile, # tiles) runs of tiles sharing the bra pair group
+    int nitems;
     int tile_first, tile_stride;     // static block-cyclic shard of this rank; work stealing inside
     unsigned int* counter;
     int mode;                        // 0 = diagonal (Schwarz) pass, 1 = energy, 2 = export G
@@ -46,6 +48,8 @@ struct TileArgs {
     int hs_cap, pp_cap, sp_cap;      // shared-memory capacities: H tile (doubles), primitive pairs per side, shell pairs
     int hs_ld, strip_ld;             // row strides of the H tile and of the per-warp integral strips
     int g_cap;                       // k_ptile: doubles per warp-private G[q][p] partial
+    const double* boys_small;        // compact Boys table (vb_eri.cuh, boys_s)
+    int boys_cap;                    // BOYS_S_SIZE when the table is staged in shared memory, else 0
     double* diag;                    // mode 0: (s,t) -> (st|st)
     const double* sch;               // mode 1: Schwarz table as the reference indexes it, nso*nso
     double itol;

@@ -36,7 +36,7 @@ __device__ __forceinline__ void pstep(const double* __restrict__ boys_tab, const
     double T, pref;
     quartet_geom(a, b, geo, T, pref);
     double F[M + 1];
-    boys<M>(boys_tab, T, F);
+    boys_s<M>(boys_tab, T, F);
 #pragma unroll
     for (int m = 0; m <= M; ++m) F[m] *= pref;
     double acc[NE * NF];
@@ -58,8 +58,9 @@ __device__ __forceinline__ void pstep(const double* __restrict__ boys_tab, const
 // One warp task: a ket octet of pair type TK against every bra primitive of P.
 template <int TK>
 __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const PGDesc& Q, int oct, const PrimPair* __restrict__ bpps,
-                                      const double* __restrict__ Dp_s, const double* __restrict__ Dq_s, double* __restrict__ scratch,
-                                      double* __restrict__ Gw, int lane, unsigned long long* __restrict__ s_pq)
+                                      const double* __restrict__ Dp_s, const double* __restrict__ Dq_g, const double* __restrict__ boys_tab,
+                                      double* __restrict__ scratch, double* __restrict__ Gw, bool priv, int lane,
+                                      unsigned long long* __restrict__ s_pq)
 {
     constexpr int NF = pt_ne(TK);
     const int g = lane >> 2, t = lane & 3;
@@ -87,7 +88,7 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
             const bool bact = b0 + t < nb;
             PrimPair a = bl[b0 + (bact ? t : 0)];
             if (!bact) a.Kp = 0.0;
-            pstep<TB, TK>(A.boys, a, b, Dp_s, P.np, g, X);
+            pstep<TB, TK>(boys_tab, a, b, Dp_s, P.np, g, X);
             npq += (unsigned long long)(min(4, nb - b0) * nkact);
         }
         if (npq) {
@@ -120,16 +121,18 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
             double bfr[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) bfr[j] = scratch[kk * PT_SLD + 8 * j + g];
-            const double* arow = Dq_s + (eo + f) * Q.np + g;
+            const double* arow = Dq_g + (eo + f) * Q.np;                // read once per task: straight from L2
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                const double af = arow[8 * m];
+                const int q = 8 * m + g;
+                const double af = q < Q.np ? arow[q] : 0.0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma_884(C[m][j][0], C[m][j][1], af, bfr[j]);
             }
         }
     }
-    // warp-private accumulation (fixed order inside a warp; the warps are summed in fixed order later)
+    // Schwarz pass: warp-private partials (fixed order inside a warp; the warps are summed in fixed order
+    // later); energy pass: the tile's shared G through shared-memory atomics
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int q = 8 * m + g;
@@ -139,82 +142,108 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int p = 8 * j + 2 * t + i;
-                if (p < P.np) Gw[q * P.np + p] += C[m][j][i];
+                if (p < P.np) {
+                    if (priv) Gw[q * P.np + p] += C[m][j][i];
+                    else atomicAdd(&Gw[q * P.np + p], C[m][j][i]);
+                }
             }
     }
 }
 
+constexpr int PT_MAXQ = 8;     // ket pair groups processed together against one staged bra pair group
+
+// Persistent kernel.  One work item = a bra pair group P with up to PT_MAXQ ket pair groups (tiles
+// (P,Q_i), consecutive in the tile list): P's densities and primitive pairs are staged once (TMA bulk),
+// the ket octets of all Q_i form one task pool (heaviest pair types first), and the contraction phase
+// runs over all of the item's tiles.
 __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
 {
     extern __shared__ __align__(16) double smem[];
     constexpr int nw = TILE_THREADS / 32;
     double* Dp_s = smem;                                        // [P.ne][P.np]
-    double* Dq_s = Dp_s + A.dq_cap;                             // [Q.ne][Q.np]
-    double* Gws = Dq_s + A.dq_cap;                              // per-warp G[q][p] partials, nw x g_cap
-    double* scr = Gws + nw * A.g_cap;                           // per-warp X scratch
-    PrimPair* bpp_s = reinterpret_cast<PrimPair*>(scr + nw * PT_SCRATCH);   // bra primitive pairs of P (when they fit)
+    double* Gs = Dp_s + A.dq_cap;                               // G[q][p] per tile (energy pass) / per warp (Schwarz pass), 8 x g_cap
+    double* scr = Gs + PT_MAXQ * A.g_cap;                       // per-warp X scratch
+    double* boys_sm = scr + nw * PT_SCRATCH;                    // compact Boys table (when it fits)
+    PrimPair* bpp_s = reinterpret_cast<PrimPair*>(boys_sm + A.boys_cap);     // bra primitive pairs of P (when they fit)
+    static_assert(PT_MAXQ >= nw, "the G region doubles as the per-warp partials of the Schwarz pass");
+    for (int i = threadIdx.x; i < A.boys_cap; i += TILE_THREADS) boys_sm[i] = A.boys_small[i];
+    const double* boys_tab = A.boys_cap ? boys_sm : A.boys_small;
     __shared__ unsigned long long s_bar;
     unsigned phase = 0;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __shared__ int s_tile, s_unit;
-    __shared__ int s_cum[4];
-    __shared__ double s_red[nw];
+    __shared__ int s_item, s_unit;
+    __shared__ int s_cum[3 * PT_MAXQ + 1];
+    __shared__ double s_red[nw][PT_MAXQ];
     __shared__ unsigned long long s_cnt[CNT_N];
     __shared__ unsigned long long s_pq[NPTYPE * NPTYPE];
+    __shared__ PGDesc s_P, s_Q[PT_MAXQ];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < CNT_N) s_cnt[tid] = 0ull;
     if (tid < NPTYPE * NPTYPE) s_pq[tid] = 0ull;
+    const bool priv = A.mode == 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_tile = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
+        if (tid == 0) s_item = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
         __syncthreads();
-        const long long tl = (long long)A.tile_first + (long long)s_tile * A.tile_stride;
-        if (tl >= A.ntiles) break;
-        const int2 tq = A.tiles[tl];
-        const PGDesc P = A.pgs[tq.x];
-        const PGDesc Q = A.pgs[tq.y];
+        const long long it = (long long)A.tile_first + (long long)s_item * A.tile_stride;
+        if (it >= A.nitems) break;
+        const int2 item = A.items[it];                          // first tile, # tiles
+        const int tl0 = item.x, ntl = item.y;
+        {
+            // descriptors: P once, Q_i per tile (word-wise copy by the first warps)
+            constexpr int W = sizeof(PGDesc) / 4;
+            const int2 t0 = A.tiles[tl0];
+            if (warp == 0)
+                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_P)[i] = reinterpret_cast<const int*>(A.pgs + t0.x)[i];
+            for (int qi = warp; qi < ntl; qi += nw) {
+                const int y = A.tiles[tl0 + qi].y;
+                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_Q[qi])[i] = reinterpret_cast<const int*>(A.pgs + y)[i];
+            }
+        }
+        __syncthreads();
+        const PGDesc& P = s_P;
         const int nbpp = P.pp_beg[NPTYPE] - P.pp_beg[0];
         if (tid == 0) {
-            // the buffers were last read through the generic proxy (previous tile): order before async writes
+            // the buffers were last read through the generic proxy (previous item): order before async writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const unsigned bp = (unsigned)((((size_t)P.ne * P.np + 1) & ~(size_t)1) * sizeof(double));
-            const unsigned bq = (unsigned)((((size_t)Q.ne * Q.np + 1) & ~(size_t)1) * sizeof(double));
             const unsigned bb = A.pp_cap ? (unsigned)(nbpp * sizeof(PrimPair)) : 0u;
-            mbar_expect_tx(&s_bar, bp + bq + bb);
+            mbar_expect_tx(&s_bar, bp + bb);
             tma_bulk_g2s(Dp_s, A.dmat + P.d_off, bp, &s_bar);
-            tma_bulk_g2s(Dq_s, A.dmat + Q.d_off, bq, &s_bar);
             if (A.pp_cap) tma_bulk_g2s(bpp_s, A.pps + P.pp_beg[0], bb, &s_bar);
+            // task pool: (pair type, tile, octet), heaviest pair type first so the tail of the item is made of light tasks
             int n = 0;
-            for (int tk = 0; tk < 3; ++tk) {
-                s_cum[tk] = n;
-                const int nk = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-                if (nk > 0) n += (nk + 7) >> 3;
-            }
-            s_cum[3] = n;
+            for (int r = 0; r < 3; ++r)
+                for (int qi = 0; qi < PT_MAXQ; ++qi) {
+                    s_cum[r * PT_MAXQ + qi] = n;
+                    if (qi < ntl) {
+                        const int tk = 2 - r, nk = s_Q[qi].pp_beg[tk + 1] - s_Q[qi].pp_beg[tk];
+                        if (nk > 0) n += (nk + 7) >> 3;
+                    }
+                }
+            s_cum[3 * PT_MAXQ] = n;
             s_unit = 0;
         }
         const PrimPair* bpps = A.pp_cap ? bpp_s : A.pps + P.pp_beg[0];
-        const int gsz = P.np * Q.np;
-        for (int i = tid; i < nw * A.g_cap; i += TILE_THREADS) Gws[i] = 0.0;
+        for (int i = tid; i < (priv ? nw : ntl) * A.g_cap; i += TILE_THREADS) Gs[i] = 0.0;
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
         __syncthreads();
 
         // ---- primitive integrals + both density transformations (tensor cores) ----------------
-        //   energy pass : ket octets are handed out through a shared counter (dynamic);
-        //   Schwarz pass: dealt round-robin (static), so the table is bitwise reproducible and
-        //                 identical on every rank (the tile list is derived from it).
-        const int nunits = s_cum[3];
-        const bool dynamic = A.mode != 0;
-        double* Gw = Gws + warp * A.g_cap;
+        //   energy pass : tasks are handed out through a shared counter (dynamic), G through shared atomics;
+        //   Schwarz pass: one tile per item, tasks dealt round-robin (static) into warp-private partials, so
+        //                 the table is bitwise reproducible and identical on every rank (the tile list is
+        //                 derived from it).
+        const int nunits = s_cum[3 * PT_MAXQ];
         double* scratch = scr + warp * PT_SCRATCH;
         int ustat = warp - nw;
         for (;;) {
             int u;
-            if (dynamic) {
+            if (!priv) {
                 u = 0;
                 if (lane == 0) u = atomicAdd(&s_unit, 1);
                 u = __shfl_sync(0xffffffffu, u, 0);
@@ -223,99 +252,112 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
                 u = ustat;
             }
             if (u >= nunits) break;
-            const int tk = u >= s_cum[2] ? 2 : (u >= s_cum[1] ? 1 : 0);
-            const int oct = u - s_cum[tk];
+            int c = 0;
+            while (s_cum[c + 1] <= u) ++c;
+            const int tk = 2 - c / PT_MAXQ, qi = c % PT_MAXQ, oct = u - s_cum[c];
+            const PGDesc& Q = s_Q[qi];
+            double* Gw = Gs + (priv ? warp : qi) * A.g_cap;
+            const double* Dq_g = A.dmat + Q.d_off;
             switch (tk) {
-                case 0: ptask<0>(A, P, Q, oct, bpps, Dp_s, Dq_s, scratch, Gw, lane, s_pq); break;
-                case 1: ptask<1>(A, P, Q, oct, bpps, Dp_s, Dq_s, scratch, Gw, lane, s_pq); break;
-                default: ptask<2>(A, P, Q, oct, bpps, Dp_s, Dq_s, scratch, Gw, lane, s_pq); break;
+                case 0: ptask<0>(A, P, Q, oct, bpps, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                case 1: ptask<1>(A, P, Q, oct, bpps, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                default: ptask<2>(A, P, Q, oct, bpps, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
             }
         }
         __syncthreads();
-        // fixed-order sum of the warp partials -> Gws[0 .. gsz)
-        for (int i = tid; i < gsz; i += TILE_THREADS) {
-            double v = Gws[i];
+        if (priv) {
+            // fixed-order sum of the warp partials -> Gs[0 .. gsz)
+            const int gsz = P.np * s_Q[0].np;
+            for (int i = tid; i < gsz; i += TILE_THREADS) {
+                double v = Gs[i];
 #pragma unroll
-            for (int w = 1; w < nw; ++w) v += Gws[w * A.g_cap + i];
-            Gws[i] = v;
+                for (int w = 1; w < nw; ++w) v += Gs[w * A.g_cap + i];
+                Gs[i] = v;
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---- contraction with the cofactor densities --------------------------------------
-        double epart = 0.0;
         unsigned long long cnt[CNT_N];
 #pragma unroll
         for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
-        const bool diag_tile = tq.x == tq.y;
         const int nso = A.nso;
-        for (int idx = tid; idx < gsz; idx += TILE_THREADS) {
-            const int p = idx / Q.np, q = idx % Q.np;
-            if (diag_tile && q > p) continue;
-            const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
-            const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
-            if (A.mode == 0) {
-                if (diag_tile && p == q) {
-                    const double G = Gws[q * P.np + p];
-                    A.diag[(size_t)s * nso + t] = G;
-                    if (A.sym) A.diag[(size_t)t * nso + s] = G;
+        for (int qi = 0; qi < ntl; ++qi) {
+            const PGDesc& Q = s_Q[qi];
+            const double* G_s = Gs + qi * A.g_cap;
+            const bool diag_tile = P.pair_beg == Q.pair_beg;
+            double epart = 0.0;
+            for (int idx = tid; idx < P.np * Q.np; idx += TILE_THREADS) {
+                const int p = idx / Q.np, q = idx % Q.np;
+                if (diag_tile && q > p) continue;
+                const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
+                const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
+                if (A.mode == 0) {
+                    if (diag_tile && p == q) {
+                        const double G = G_s[q * P.np + p];
+                        A.diag[(size_t)s * nso + t] = G;
+                        if (A.sym) A.diag[(size_t)t * nso + s] = G;
+                    }
+                    continue;
                 }
-                continue;
-            }
-            // reference screen on the Schwarz product (valence.F90:1189-1190); screened entries
-            // contribute nothing and are counted nowhere
-            const bool ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
-            if (!ssig) continue;
-            const double G = Gws[q * P.np + p];
-            // images of (s,t,u,v) under the integral's permutational symmetry
-            int im[8][4];
-            int nim = 0;
-            {
-                const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
-                for (int k = 0; k < 2; ++k) {
-                    const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
-                    im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
-                    if (A.sym) {
-                        im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
-                        im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
-                        im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
+                // reference screen on the Schwarz product (valence.F90:1189-1190); screened entries
+                // contribute nothing and are counted nowhere
+                const bool ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
+                if (!ssig) continue;
+                const double G = G_s[q * P.np + p];
+                // images of (s,t,u,v) under the integral's permutational symmetry
+                int im[8][4];
+                int nim = 0;
+                {
+                    const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
+                    for (int k = 0; k < 2; ++k) {
+                        const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
+                        im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
+                        if (A.sym) {
+                            im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
+                            im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
+                            im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
+                        }
                     }
                 }
-            }
-            double wsum = 0.0;
-            cnt[CNT_ENTRIES]++;
-            for (int k = 0; k < nim; ++k) {
-                const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
-                bool dup = false;
-                for (int k2 = 0; k2 < k; ++k2)
-                    dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
-                if (dup) continue;
-                // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
-                const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
-                const double val = shortcut ? A.sch[a * nso + b] * A.sch[a * nso + b] : G;
-                const bool vsig = fabs(val) > A.itol;
-                // as the direct integral of task io=a, ko=b, jo=c, lo=d
-                bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
-                if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
-                // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
-                bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
-                if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
-                if (vd) { cnt[CNT_SCHWARZ_EREP]++; cnt[CNT_VALUE_EREP] += vsig; }
-                if (vx) { cnt[CNT_SCHWARZ_EXCH]++; cnt[CNT_VALUE_EXCH] += vsig; }
-                if (!shortcut) {
-                    const int calls = (vd ? 1 : 0) + ((vx && b != d) ? 1 : 0);
-                    cnt[CNT_INT2E] += calls;
-                    cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
+                double wsum = 0.0;
+                cnt[CNT_ENTRIES]++;
+                for (int k = 0; k < nim; ++k) {
+                    const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
+                    bool dup = false;
+                    for (int k2 = 0; k2 < k; ++k2)
+                        dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
+                    if (dup) continue;
+                    // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
+                    const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
+                    const double val = shortcut ? A.sch[a * nso + b] * A.sch[a * nso + b] : G;
+                    const bool vsig = fabs(val) > A.itol;
+                    // as the direct integral of task io=a, ko=b, jo=c, lo=d
+                    bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+                    if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
+                    // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
+                    bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+                    if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
+                    if (vd) { cnt[CNT_SCHWARZ_EREP]++; cnt[CNT_VALUE_EREP] += vsig; }
+                    if (vx) { cnt[CNT_SCHWARZ_EXCH]++; cnt[CNT_VALUE_EXCH] += vsig; }
+                    if (!shortcut) {
+                        const int calls = (vd ? 1 : 0) + ((vx && b != d) ? 1 : 0);
+                        cnt[CNT_INT2E] += calls;
+                        cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
+                    }
+                    if (shortcut && vd) cnt[CNT_SHORTCUT]++;
+                    if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
+                    if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
                 }
-                if (shortcut && vd) cnt[CNT_SHORTCUT]++;
-                if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
-                if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
+                epart += 0.5 * wsum;
             }
-            epart += 0.5 * wsum;
+            if (A.mode == 1) {
+                for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
+                if (lane == 0) s_red[warp][qi] = epart;
+            }
         }
         if (A.mode == 1) {
-            // deterministic block reduction of the tile's energy; counters: one shared atomic per warp
-            for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
-            if (lane == 0) s_red[warp] = epart;
+            // deterministic block reduction of the tile energies; counters: one shared atomic per warp
 #pragma unroll
             for (int i = 0; i < CNT_N; ++i) {
                 unsigned long long c = cnt[i];
@@ -323,10 +365,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
                 if (lane == 0 && c) atomicAdd(&s_cnt[i], c);
             }
             __syncthreads();
-            if (tid == 0) {
+            if (tid < ntl) {
                 double e = 0.0;
-                for (int w = 0; w < nw; ++w) e += s_red[w];
-                A.tileE[tl] = e * A.c0;
+                for (int w = 0; w < nw; ++w) e += s_red[w][tid];
+                A.tileE[tl0 + tid] = e * A.c0;
             }
         }
     }
