@@ -110,7 +110,7 @@ struct Engine::Impl {
     DBuf<int2> opairs, tiles, items;
     DBuf<PGDesc> pgs;
     DBuf<SPRec> sps;
-        DBuf<PrimPair> pps;
+    DBuf<PrimPair> pps, pps_flat;
     DBuf<unsigned int> counter;
     DBuf<unsigned long long> counters, pq_counters;
     // state carried from energy_partial to energy_finish
@@ -411,7 +411,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         else pp_cap = 0;   // primitive tables stay in global memory
     } else {
         constexpr int nw = TILE_THREADS / 32;
-        smem = ((size_t)dq_cap2 + (size_t)PT_MAXQ * g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double);
+        smem = ((size_t)dq_cap2 + (size_t)PT_MAXQ * g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
         if (smem + (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += (size_t)pp_cap * sizeof(PrimPair);
         else pp_cap = 0;
         if (smem + BOYS_S_SIZE * sizeof(double) <= 225 * 1024) { boys_cap = BOYS_S_SIZE; smem += BOYS_S_SIZE * sizeof(double); }
@@ -423,7 +423,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         nshk[s] = (int)orbs2e[wf.ket[wf.slot(s, 0)]].sh.size();
     }
     pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
-    pps.upload(ts.pps, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
+    pps.upload(ts.pps, st); pps_flat.upload(ts.pps_flat, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
     int grid_cap = nsm;
     if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
@@ -432,7 +432,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
-    A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.tau = tau_diag;
+    A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pps_flat = pps_flat.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
     A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = 0; A.g_cap = g_cap; A.boys_small = boys_small.p; A.boys_cap = boys_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;

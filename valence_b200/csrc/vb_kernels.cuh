@@ -31,7 +31,8 @@ struct TileArgs {
     const PGDesc* pgs;
     const int* pg_pairs;
     const SPRec* sps;
-    const PrimPair* pps;
+    const PrimPair* pps;             // grouped by shell pair (bra side)
+    const PrimPair* pps_flat;        // k_ptile: per pair type sorted by magnitude across shell pairs (ket side)
     double tau;                      // primitive-quartet magnitude cut (0 = none)
     unsigned long long* pq_counters; // primitive quartets evaluated, per class tb*NPTYPE+tk
     const double* dmat;

@@ -7,12 +7,15 @@
 // this the contraction of primitives into shells, and both density transformations, are two dense
 // matrix products around the matrix of primitive integrals -- and they run on the FP64 tensor cores:
 //
-//   lane (g = lane/4, t = lane%4) of a warp evaluates ONE primitive quartet (ket primitive g of an
-//   octet, bra primitive t of a quad) by the Obara-Saika recurrence and feeds each component
-//   straight into DMMA m8n8k4 as the A fragment  A[g][t];  B[t][n] = Dp[e_b + e][n] comes from the
-//   staged bra densities, and X_f[k][p] (8 ket primitives x 32 orbital pairs) accumulates in the
-//   C fragments while the warp walks all bra primitives.  No shuffles, no per-shell reductions,
-//   no divergence; pruning by magnitude works at (octet x quad) granularity.
+//   lane (g = lane/4, t = lane%4) of a warp owns ket primitive g of an octet and bra shell pair t of a
+//   quad (shell pairs sorted by contraction length, so the four lanes run nearly equal trip counts):
+//   it sums the Obara-Saika values of its ket primitive against the primitives of its bra shell pair
+//   and feeds each component straight into DMMA m8n8k4 as the A fragment A[g][t];
+//   B[t][n] = Dp[e_sp + e][n] comes from the staged bra densities, and X_f[k][p] (8 ket primitives x
+//   32 orbital pairs) accumulates in the C fragments while the warp walks all bra shell pairs.
+//   No shuffles, no segmented reductions; pruning by magnitude is per lane.  (FP64 DMMA shares the
+//   FP64 pipe with DFMA on B200 -- one m8n8k4 costs 8 DFMA issue slots -- hence the contraction over
+//   the bra primitives happens in the lane *before* the tensor-core product.)
 //   After the bra loop a second DMMA product folds the 8 ket primitives with Dq into G.
 //
 // (replaces int2e, valence.F90:3184-3438, and the 2e loop of vsvb_energy, :1153-1433; the screening
@@ -22,13 +25,16 @@
 
 namespace vb {
 
+#ifndef VB_PAIR_MAXM
+#define VB_PAIR_MAXM -1
+#endif
 constexpr int PT_SLD = 33;                      // row stride of the per-warp X scratch (8 x 32 doubles)
 constexpr int PT_SCRATCH = 8 * PT_SLD + 1;      // doubles per warp (odd row stride, even total keeps the next region aligned)
 
-// one primitive quartet per lane, results consumed by the tensor cores
+// one primitive quartet per lane: acc += [e0|f0] for e in the kept bra range, f in the kept ket range
 template <int TB, int TK>
-__device__ __forceinline__ void pstep(const double* __restrict__ boys_tab, const PrimPair& a, const PrimPair& b,
-                                      const double* __restrict__ Dp_s, int npP, int g, double (&X)[pt_ne(TK)][4][2])
+__device__ __forceinline__ void quartet_values(const double* __restrict__ boys_tab, const PrimPair& a, const PrimPair& b,
+                                               double (&acc)[pt_ne(TB) * pt_ne(TK)])
 {
     constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
     constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
@@ -39,12 +45,17 @@ __device__ __forceinline__ void pstep(const double* __restrict__ boys_tab, const
     boys_s<M>(boys_tab, T, F);
 #pragma unroll
     for (int m = 0; m <= M; ++m) F[m] *= pref;
-    double acc[NE * NF];
-#pragma unroll
-    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
-    if constexpr (M == 0) acc[0] = F[0];
+    if constexpr (M == 0) acc[0] += F[0];
     else vrr_unrolled<LA, EA, LC, EC>(geo, F, acc);
-    const double* drow = Dp_s + a.eoff * npP + g;      // B[t][n = 8j + g] = Dp[e_b + e][8j + g]
+}
+
+// the quartet values go straight into the tensor cores: X_f[k][p] += sum_b A[k][b] Dp[e_b + e][p]
+template <int TB, int TK>
+__device__ __forceinline__ void feed_dmma(const double (&acc)[pt_ne(TB) * pt_ne(TK)], int eoff, const double* __restrict__ Dp_s,
+                                          int npP, int g, double (&X)[pt_ne(TK)][4][2])
+{
+    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    const double* drow = Dp_s + eoff * npP + g;        // B[t][n = 8j + g] = Dp[e_sp + e][8j + g]
 #pragma unroll
     for (int e = 0; e < NE; ++e)
 #pragma unroll
@@ -58,6 +69,7 @@ __device__ __forceinline__ void pstep(const double* __restrict__ boys_tab, const
 // One warp task: a ket octet of pair type TK against every bra primitive of P.
 template <int TK>
 __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const PGDesc& Q, int oct, const PrimPair* __restrict__ bpps,
+                                      const SPRec* __restrict__ spss,
                                       const double* __restrict__ Dp_s, const double* __restrict__ Dq_g, const double* __restrict__ boys_tab,
                                       double* __restrict__ scratch, double* __restrict__ Gw, bool priv, int lane,
                                       unsigned long long* __restrict__ s_pq)
@@ -65,13 +77,12 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
     constexpr int NF = pt_ne(TK);
     const int g = lane >> 2, t = lane & 3;
     const int nk = Q.pp_beg[TK + 1] - Q.pp_beg[TK];
-    const PrimPair* __restrict__ kl = A.pps + Q.pp_beg[TK];
+    const PrimPair* __restrict__ kl = A.pps_flat + Q.pp_beg[TK];
     const int k0 = 8 * oct;
     const bool kact = k0 + g < nk;
     PrimPair b = kl[k0 + (kact ? g : 0)];
     if (!kact) b.Kp = 0.0;
     const double wk = kl[k0].w;                        // the octet's largest magnitude (lists are sorted)
-    const int nkact = min(8, nk - k0);
     double X[NF][4][2];
 #pragma unroll
     for (int f = 0; f < NF; ++f)
@@ -80,20 +91,35 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
     bool any = false;
     sfor<0, 3>([&](auto TBc) {
         constexpr int TB = TBc;
-        const int nb = P.pp_beg[TB + 1] - P.pp_beg[TB];
-        const PrimPair* __restrict__ bl = bpps + (P.pp_beg[TB] - P.pp_beg[0]);
-        unsigned long long npq = 0ull;
-        for (int b0 = 0; b0 < nb; b0 += 4) {
-            if (!(bl[b0].w * wk >= A.tau)) break;      // sorted by magnitude: nothing below matters either
-            const bool bact = b0 + t < nb;
-            PrimPair a = bl[b0 + (bact ? t : 0)];
-            if (!bact) a.Kp = 0.0;
-            pstep<TB, TK>(boys_tab, a, b, Dp_s, P.np, g, X);
-            npq += (unsigned long long)(min(4, nb - b0) * nkact);
+        constexpr int NE = pt_ne(TB);
+        const int nsp = P.sp_beg[TB + 1] - P.sp_beg[TB];
+        const SPRec* __restrict__ sl = spss + (P.sp_beg[TB] - P.sp_beg[0]);
+        if (!(nsp > 0 && P.kwmax[TB] * wk >= A.tau)) return;
+        unsigned nq = 0;                                // primitive quartets evaluated by this lane
+        for (int q0 = 0; q0 < nsp; q0 += 4) {
+            const bool sact = q0 + t < nsp;
+            const SPRec sp = sl[q0 + (sact ? t : 0)];
+            const int cnt = sact ? sp.pp_cnt : 0;
+            const PrimPair* __restrict__ bl = bpps + (sp.pp_beg - P.pp_beg[0]);
+            double acc[NE * NF];
+#pragma unroll
+            for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+            int ip = 0;
+            for (;; ++ip) {
+                // primitives of a shell pair are sorted by magnitude: a lane that stops stays stopped
+                PrimPair a = bl[ip < cnt ? ip : 0];
+                const bool act = ip < cnt && a.w * wk >= A.tau;
+                if (!__any_sync(0xffffffffu, act)) break;
+                if (!act) a.Kp = 0.0;
+                quartet_values<TB, TK>(boys_tab, a, b, acc);
+                nq += (act && kact) ? 1u : 0u;
+            }
+            if (ip > 0) feed_dmma<TB, TK>(acc, sp.eoff, Dp_s, P.np, g, X);
         }
-        if (npq) {
+        for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
+        if (nq) {
             any = true;
-            if (lane == 0) atomicAdd(&s_pq[TB * NPTYPE + TK], npq);
+            if (lane == 0) atomicAdd(&s_pq[TB * NPTYPE + TK], (unsigned long long)nq);
         }
     });
     if (!any) return;
@@ -164,7 +190,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
     double* Gs = Dp_s + A.dq_cap;                               // G[q][p] per tile (energy pass) / per warp (Schwarz pass), 8 x g_cap
     double* scr = Gs + PT_MAXQ * A.g_cap;                       // per-warp X scratch
     double* boys_sm = scr + nw * PT_SCRATCH;                    // compact Boys table (when it fits)
-    PrimPair* bpp_s = reinterpret_cast<PrimPair*>(boys_sm + A.boys_cap);     // bra primitive pairs of P (when they fit)
+    SPRec* sps_s = reinterpret_cast<SPRec*>(boys_sm + A.boys_cap);           // bra shell pairs of P
+    PrimPair* bpp_s = reinterpret_cast<PrimPair*>(sps_s + A.sp_cap);         // bra primitive pairs of P (when they fit)
     static_assert(PT_MAXQ >= nw, "the G region doubles as the per-warp partials of the Schwarz pass");
     for (int i = threadIdx.x; i < A.boys_cap; i += TILE_THREADS) boys_sm[i] = A.boys_small[i];
     const double* boys_tab = A.boys_cap ? boys_sm : A.boys_small;
@@ -211,8 +238,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const unsigned bp = (unsigned)((((size_t)P.ne * P.np + 1) & ~(size_t)1) * sizeof(double));
             const unsigned bb = A.pp_cap ? (unsigned)(nbpp * sizeof(PrimPair)) : 0u;
-            mbar_expect_tx(&s_bar, bp + bb);
+            const unsigned bs = (unsigned)((P.sp_beg[NPTYPE] - P.sp_beg[0]) * sizeof(SPRec));
+            mbar_expect_tx(&s_bar, bp + bb + bs);
             tma_bulk_g2s(Dp_s, A.dmat + P.d_off, bp, &s_bar);
+            tma_bulk_g2s(sps_s, A.sps + P.sp_beg[0], bs, &s_bar);
             if (A.pp_cap) tma_bulk_g2s(bpp_s, A.pps + P.pp_beg[0], bb, &s_bar);
             // task pool: (pair type, tile, octet), heaviest pair type first so the tail of the item is made of light tasks
             int n = 0;
@@ -259,9 +288,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
             double* Gw = Gs + (priv ? warp : qi) * A.g_cap;
             const double* Dq_g = A.dmat + Q.d_off;
             switch (tk) {
-                case 0: ptask<0>(A, P, Q, oct, bpps, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
-                case 1: ptask<1>(A, P, Q, oct, bpps, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
-                default: ptask<2>(A, P, Q, oct, bpps, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                case 0: ptask<0>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                case 1: ptask<1>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                default: ptask<2>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
             }
         }
         __syncthreads();

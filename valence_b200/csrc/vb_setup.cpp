@@ -451,10 +451,6 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             eoff += nE;
         }
         while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)out.pps.size(); ++t_cur; }
-        if (flat)   // one magnitude-sorted list per pair type (each primitive carries its shell pair's e-offset)
-            for (int t = 0; t < NPTYPE; ++t)
-                std::stable_sort(out.pps.begin() + pg.pp_beg[t], out.pps.begin() + pg.pp_beg[t + 1],
-                                 [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
         // per type, most expensive shell pairs first (they are dealt round-robin to the warps)
         std::stable_sort(recs.begin(), recs.end(), [](const SPRec& a, const SPRec& b) {
             return a.type != b.type ? a.type < b.type : a.pp_cnt > b.pp_cnt;
@@ -499,7 +495,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         size_t n_pairs = 0, n_sps = 0, n_pps = 0, n_d = 0, n_pg = 0;
         for (const PGOut& o : outs)
             if (o.used) { n_pairs += o.pairs.size(); n_sps += o.sps.size(); n_pps += o.pps.size(); n_d += o.dmat.size(); ++n_pg; }
-        ts.pg_pairs.reserve(n_pairs); ts.sps.reserve(n_sps); ts.pps.reserve(n_pps); ts.dmat.reserve(n_d); ts.pgs.reserve(n_pg);
+        ts.pg_pairs.reserve(n_pairs); ts.sps.reserve(n_sps); ts.pps.reserve(n_pps); if (flat) ts.pps_flat.reserve(n_pps); ts.dmat.reserve(n_d); ts.pgs.reserve(n_pg);
     }
     for (PGOut& o : outs) {
         if (!o.used) continue;
@@ -512,6 +508,12 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         ts.pg_pairs.insert(ts.pg_pairs.end(), o.pairs.begin(), o.pairs.end());
         ts.sps.insert(ts.sps.end(), o.sps.begin(), o.sps.end());
         ts.pps.insert(ts.pps.end(), o.pps.begin(), o.pps.end());
+        if (flat) {   // one magnitude-sorted list per pair type (each primitive carries its shell pair's e-offset)
+            ts.pps_flat.insert(ts.pps_flat.end(), o.pps.begin(), o.pps.end());
+            for (int t = 0; t < NPTYPE; ++t)
+                std::stable_sort(ts.pps_flat.begin() + pg.pp_beg[t], ts.pps_flat.begin() + pg.pp_beg[t + 1],
+                                 [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
+        }
         ts.dmat.insert(ts.dmat.end(), o.dmat.begin(), o.dmat.end());
         ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
         ts.max_nsp = std::max(ts.max_nsp, (int)o.sps.size());

@@ -75,7 +75,8 @@ struct TileSetup {
     std::vector<PGDesc> pgs;
     std::vector<int> pg_pairs;      // 2 ints (s,t) per pair
     std::vector<SPRec> sps;
-    std::vector<PrimPair> pps;
+    std::vector<PrimPair> pps;      // grouped by shell pair
+    std::vector<PrimPair> pps_flat; // same ranges per (pair group, type), sorted by magnitude (flat mode only)
     double wmax = 0.0;              // largest primitive-pair magnitude bound (for pruning)
     std::vector<double> dmat;       // folded densities, per pair group [e][p]
     int max_ne = 0, max_np = 0, max_npp = 0, max_nsp = 0;
@@ -95,8 +96,8 @@ bool obs_position(const Input& in, const Basis& bas, int orb, int pos, int* gshe
 
 // tau: primitive pairs whose largest possible contribution to any orbital-level integral stays
 // below tau are dropped at set-up (0 keeps everything the reference computes)
-// flat: primitive pairs of a pair group sorted by magnitude inside each pair type, across shell pairs
-// (k_ptile); otherwise grouped by shell pair (k_tile, d shells)
+// flat: also emit pps_flat, the primitive pairs of a pair group sorted by magnitude inside each pair
+// type across shell pairs (ket side of k_ptile)
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs2e,
                  double tau, bool flat, TileSetup* out);
 
