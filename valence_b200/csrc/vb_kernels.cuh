@@ -39,8 +39,10 @@ struct TileArgs {
     const double* boys;
     const int2* tiles;
     int ntiles;
-    const int2* items;               // k_ptile work items: (first tile, # tiles) runs of tiles sharing the bra pair group
+    const int4* items;               // k_ptile work items: (first tile, # tiles, G slot, -) runs of tiles sharing the bra pair group
     int nitems;
+    double* gbuf;                    // hand-over of the heavy classes' share of G, g_cap doubles per tile slot
+    long long gslot_base;            // slot of the first tile of the current chunk
     int tile_first, tile_stride;     // static block-cyclic shard of this rank; work stealing inside
     unsigned int* counter;
     int mode;                        // 0 = diagonal (Schwarz) pass, 1 = energy, 2 = export G

@@ -25,9 +25,28 @@
 
 namespace vb {
 
-#ifndef VB_PAIR_MAXM
-#define VB_PAIR_MAXM -1
+// The classes are split over two launches so that each gets the register budget it needs:
+//   PART_HEAVY : every class with a pp pair on either side (up to 81 components per quartet), 8 warps x 255 registers,
+//                leaves its share of G in a global buffer;
+//   PART_LIGHT : (ss|ss) (ps|ss) (ss|ps) (ps|ps) -- 77 % of the flops, 90 % of the primitive quartets of a water
+//                cluster -- 16 warps x 128 registers, starts from the heavy share and runs the contraction;
+//   PART_ALL   : everything in one launch (Schwarz pass).
+enum { PART_ALL = 0, PART_HEAVY = 1, PART_LIGHT = 2 };
+#ifndef VB_PT_LIGHT_THREADS
+#define VB_PT_LIGHT_THREADS 512
 #endif
+#ifndef VB_PT_ALL_THREADS
+#define VB_PT_ALL_THREADS 384
+#endif
+__host__ __device__ constexpr int pt_threads(int part)
+{
+    return part == PART_LIGHT ? VB_PT_LIGHT_THREADS : (part == PART_ALL ? VB_PT_ALL_THREADS : 256);
+}
+constexpr int PT_MAX_WARPS = (VB_PT_LIGHT_THREADS > VB_PT_ALL_THREADS ? VB_PT_LIGHT_THREADS : VB_PT_ALL_THREADS) / 32;
+__host__ __device__ constexpr bool pt_class_in_part(int part, int tb, int tk)
+{
+    return part == PART_ALL || ((tb < 2 && tk < 2) == (part == PART_LIGHT));
+}
 constexpr int PT_SLD = 33;                      // row stride of the per-warp X scratch (8 x 32 doubles)
 constexpr int PT_SCRATCH = 8 * PT_SLD + 1;      // doubles per warp (odd row stride, even total keeps the next region aligned)
 
@@ -67,7 +86,7 @@ __device__ __forceinline__ void feed_dmma(const double (&acc)[pt_ne(TB) * pt_ne(
 }
 
 // One warp task: a ket octet of pair type TK against every bra primitive of P.
-template <int TK>
+template <int PART, int TK>
 __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const PGDesc& Q, int oct, const PrimPair* __restrict__ bpps,
                                       const SPRec* __restrict__ spss,
                                       const double* __restrict__ Dp_s, const double* __restrict__ Dq_g, const double* __restrict__ boys_tab,
@@ -92,6 +111,7 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
     sfor<0, 3>([&](auto TBc) {
         constexpr int TB = TBc;
         constexpr int NE = pt_ne(TB);
+        if constexpr (!pt_class_in_part(PART, TB, TK)) return;
         const int nsp = P.sp_beg[TB + 1] - P.sp_beg[TB];
         const SPRec* __restrict__ sl = spss + (P.sp_beg[TB] - P.sp_beg[0]);
         if (!(nsp > 0 && P.kwmax[TB] * wk >= A.tau)) return;
@@ -182,18 +202,20 @@ constexpr int PT_MAXQ = 8;     // ket pair groups processed together against one
 // (P,Q_i), consecutive in the tile list): P's densities and primitive pairs are staged once (TMA bulk),
 // the ket octets of all Q_i form one task pool (heaviest pair types first), and the contraction phase
 // runs over all of the item's tiles.
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
+template <int PART>
+__global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
 {
     extern __shared__ __align__(16) double smem[];
-    constexpr int nw = TILE_THREADS / 32;
+    constexpr int PT_THREADS = pt_threads(PART);
+    constexpr int nw = PT_THREADS / 32;
     double* Dp_s = smem;                                        // [P.ne][P.np]
     double* Gs = Dp_s + A.dq_cap;                               // G[q][p] per tile (energy pass) / per warp (Schwarz pass), 8 x g_cap
     double* scr = Gs + PT_MAXQ * A.g_cap;                       // per-warp X scratch
-    double* boys_sm = scr + nw * PT_SCRATCH;                    // compact Boys table (when it fits)
+    double* boys_sm = scr + PT_MAX_WARPS * PT_SCRATCH;                    // compact Boys table (when it fits)
     SPRec* sps_s = reinterpret_cast<SPRec*>(boys_sm + A.boys_cap);           // bra shell pairs of P
     PrimPair* bpp_s = reinterpret_cast<PrimPair*>(sps_s + A.sp_cap);         // bra primitive pairs of P (when they fit)
-    static_assert(PT_MAXQ >= nw, "the G region doubles as the per-warp partials of the Schwarz pass");
-    for (int i = threadIdx.x; i < A.boys_cap; i += TILE_THREADS) boys_sm[i] = A.boys_small[i];
+    constexpr int nwp = nw < PT_MAXQ ? nw : PT_MAXQ;            // warps that take tasks in the Schwarz pass (the G region holds their partials)
+    for (int i = threadIdx.x; i < A.boys_cap; i += PT_THREADS) boys_sm[i] = A.boys_small[i];
     const double* boys_tab = A.boys_cap ? boys_sm : A.boys_small;
     __shared__ unsigned long long s_bar;
     unsigned phase = 0;
@@ -217,8 +239,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
         __syncthreads();
         const long long it = (long long)A.tile_first + (long long)s_item * A.tile_stride;
         if (it >= A.nitems) break;
-        const int2 item = A.items[it];                          // first tile, # tiles
+        const int4 item = A.items[it];                          // first tile, # tiles, slot of the first tile in the G hand-over buffer
         const int tl0 = item.x, ntl = item.y;
+        double* gbuf = A.gbuf + ((size_t)item.z - A.gslot_base) * A.g_cap;
         {
             // descriptors: P once, Q_i per tile (word-wise copy by the first warps)
             constexpr int W = sizeof(PGDesc) / 4;
@@ -245,11 +268,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
             if (A.pp_cap) tma_bulk_g2s(bpp_s, A.pps + P.pp_beg[0], bb, &s_bar);
             // task pool: (pair type, tile, octet), heaviest pair type first so the tail of the item is made of light tasks
             int n = 0;
+            const bool bra_pp = P.sp_beg[3] > P.sp_beg[2];
             for (int r = 0; r < 3; ++r)
                 for (int qi = 0; qi < PT_MAXQ; ++qi) {
                     s_cum[r * PT_MAXQ + qi] = n;
-                    if (qi < ntl) {
-                        const int tk = 2 - r, nk = s_Q[qi].pp_beg[tk + 1] - s_Q[qi].pp_beg[tk];
+                    const int tk = 2 - r;
+                    bool wanted = qi < ntl;
+                    if (PART == PART_LIGHT && tk == 2) wanted = false;
+                    if (PART == PART_HEAVY && tk < 2 && !bra_pp) wanted = false;
+                    if (wanted) {
+                        const int nk = s_Q[qi].pp_beg[tk + 1] - s_Q[qi].pp_beg[tk];
                         if (nk > 0) n += (nk + 7) >> 3;
                     }
                 }
@@ -257,7 +285,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
             s_unit = 0;
         }
         const PrimPair* bpps = A.pp_cap ? bpp_s : A.pps + P.pp_beg[0];
-        for (int i = tid; i < (priv ? nw : ntl) * A.g_cap; i += TILE_THREADS) Gs[i] = 0.0;
+        if (PART == PART_LIGHT) {
+            for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) Gs[i] = gbuf[i];        // the heavy classes' share
+        } else {
+            for (int i = tid; i < (priv ? nwp : ntl) * A.g_cap; i += PT_THREADS) Gs[i] = 0.0;
+        }
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
         __syncthreads();
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
         //                 derived from it).
         const int nunits = s_cum[3 * PT_MAXQ];
         double* scratch = scr + warp * PT_SCRATCH;
-        int ustat = warp - nw;
+        int ustat = warp - nwp;
         for (;;) {
             int u;
             if (!priv) {
@@ -277,8 +309,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
                 if (lane == 0) u = atomicAdd(&s_unit, 1);
                 u = __shfl_sync(0xffffffffu, u, 0);
             } else {
-                ustat += nw;
+                ustat += nwp;
                 u = ustat;
+                if (warp >= nwp) break;
             }
             if (u >= nunits) break;
             int c = 0;
@@ -288,19 +321,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
             double* Gw = Gs + (priv ? warp : qi) * A.g_cap;
             const double* Dq_g = A.dmat + Q.d_off;
             switch (tk) {
-                case 0: ptask<0>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
-                case 1: ptask<1>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
-                default: ptask<2>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                case 0: ptask<PART, 0>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                case 1: ptask<PART, 1>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                default: ptask<PART, 2>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
             }
         }
         __syncthreads();
+        if (PART == PART_HEAVY) {
+            for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) gbuf[i] = Gs[i];
+            continue;
+        }
         if (priv) {
             // fixed-order sum of the warp partials -> Gs[0 .. gsz)
             const int gsz = P.np * s_Q[0].np;
-            for (int i = tid; i < gsz; i += TILE_THREADS) {
+            for (int i = tid; i < gsz; i += PT_THREADS) {
                 double v = Gs[i];
 #pragma unroll
-                for (int w = 1; w < nw; ++w) v += Gs[w * A.g_cap + i];
+                for (int w = 1; w < nwp; ++w) v += Gs[w * A.g_cap + i];
                 Gs[i] = v;
             }
             __syncthreads();
@@ -316,7 +353,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_ptile(const TileArgs A)
             const double* G_s = Gs + qi * A.g_cap;
             const bool diag_tile = P.pair_beg == Q.pair_beg;
             double epart = 0.0;
-            for (int idx = tid; idx < P.np * Q.np; idx += TILE_THREADS) {
+            for (int idx = tid; idx < P.np * Q.np; idx += PT_THREADS) {
                 const int p = idx / Q.np, q = idx % Q.np;
                 if (diag_tile && q > p) continue;
                 const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
