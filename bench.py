@@ -6,7 +6,8 @@
 One step = one pass of the hot path: guess_energy (one vsvb_energy evaluation: one-electron
 part, spin-block inverses, Schwarz pass, fused ERI + contraction pass) of a synthetic
 (H2O)_M cluster, 6-31G, five DOCC orbitals per monomer (SURVEY.md section 8d, config 5;
-tolerances `10 20 10`, see DESIGN.md "Tolerances").  The unit counted is the reference's:
+tolerances `10 20 10`, see DESIGN.md "Tolerances").  Default M = 256, the cluster BASELINE.json's
+north_star names (768 atoms, 3328 AOs, 1280 doubly occupied orbitals); it fits one GPU.  The unit counted is the reference's:
 one contracted AO shell quartet evaluated and digested = one simint_compute_eri call of the
 reference algorithm (/root/reference/src/valence.F90:3398); the count comes from the engine's
 bit-exact screening counters, so recomputation the GPU formulation avoids still counts once per
@@ -73,6 +74,22 @@ class ClockSampler(threading.Thread):
         reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(self.samples)}
+
+
+def traffic_from_profiles(waters: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the energy-pass launch of k_ptile for this cluster size, from the
+    committed ncu capture (profiles/r1_k_ptile_dram_H2O<M>.csv); None when no capture of this size exists."""
+    path = os.path.join(ROOT, "profiles", f"r1_k_ptile_dram_H2O{waters}.csv")
+    try:
+        tot = 0.0
+        with open(path) as fh:
+            for line in fh:
+                f = [x.strip().strip('"') for x in line.split(",")]
+                if len(f) >= 3 and f[0].startswith("dram__bytes_") and f[0].endswith(".sum"):
+                    tot += float(f[1])
+        return tot or None
+    except OSError:
+        return None
 
 
 def run_reference(args) -> None:
@@ -191,7 +208,7 @@ def run_ours(args) -> None:
                             "pair tables are rebuilt on the host and copied to the device inside the timed region"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "kernel": "k_tile<false> (fused ERI + transform + contraction)",
+                         "traffic": traffic_from_profiles(args.waters), "kernel": "k_ptile<0> (fused primitive ERI + DMMA density transforms + cofactor contraction)",
                          "peak_source": "measured here: DFMA micro-benchmark vb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                          "flops": "algorithmic: executed primitive quartets per class x per-class operation count (DESIGN.md)"},
             "clocks": sampler.summary() if sampler else None,
@@ -214,7 +231,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--waters", type=int, default=int(os.environ.get("VB_BENCH_WATERS", "16")))
+    ap.add_argument("--waters", type=int, default=int(os.environ.get("VB_BENCH_WATERS", "256")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     args = ap.parse_args()

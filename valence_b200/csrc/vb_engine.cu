@@ -397,6 +397,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     const bool gen = bas_lmax >= 2;   // d shells: shell-pair kernel with the loop-based recurrence (k_tile<true>)
     TileSetup ts;
     build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts);
+    const double t_bt = now_ms();
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
     const int dq_cap = std::max(1, ts.max_ne * ts.max_np);
@@ -454,6 +455,8 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         launches++;
     };
     double t3 = now_ms();
+    const bool dbg_time = std::getenv("VB_DEBUG_TIME") != nullptr;
+    if (dbg_time) { CK(cudaStreamSynchronize(st)); std::printf("[time] density %.1f build_tiles %.1f upload+setup %.1f ms\n", t2 - t1, t_bt - t2, now_ms() - t_bt); }
     // ---- diagonal pass: (st|st) for every pair -> Schwarz table (schwarz_ints, :1489-1523) ------------
     std::vector<double> sch;
     if (sch_in) {
@@ -493,35 +496,49 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         pg.smax = m;
     }
     // ---- tile list: pair-group pairs that can hold a significant integral ----------------------------
+    // Tile (a, b), b <= a, exists when smax_a * smax_b > itol.  Order: blocks of PB consecutive bra pair groups
+    // against chunks of QC consecutive ket pair groups, so that the tables of one (block, chunk) -- a few tens of
+    // MB -- stay in L2 while the CTAs work through it; inside a chunk the partners of a come by decreasing
+    // Schwarz bound (early exit).  A run = the tiles of one (a, chunk).
+    const int PB = 128, QC = 1024;
+    const int nchunks = (npg + QC - 1) / QC;
     std::vector<int> order(npg);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ts.pgs[a].smax > ts.pgs[b].smax; });
-    // grouped by the bra pair group (the larger index), partners in order of decreasing Schwarz bound
+    for (int c = 0; c < nchunks; ++c)
+        std::stable_sort(order.begin() + (size_t)c * QC, order.begin() + std::min<size_t>(npg, (size_t)(c + 1) * QC),
+                         [&](int x, int y) { return ts.pgs[x].smax > ts.pgs[y].smax; });
     std::vector<int2> tl;
-    std::vector<long long> run_beg;            // first tile of every bra pair group's run
-    for (int a = 0; a < npg; ++a) {
-        const double sa = ts.pgs[a].smax;
-        run_beg.push_back((long long)tl.size());
-        for (int j = 0; j < npg; ++j) {
-            const int b = order[j];
-            if (!(sa * ts.pgs[b].smax > itol)) break;
-            if (b <= a) tl.push_back(make_int2(a, b));
+    std::vector<std::pair<long long, int>> runs;      // (first tile, # tiles) of every non-empty (a, chunk)
+    for (int B0 = 0; B0 < npg; B0 += PB) {
+        const int B1 = std::min(npg, B0 + PB);
+        for (int c = 0; c < nchunks && c * QC < B1; ++c) {
+            const int c0 = c * QC, c1 = std::min(npg, c0 + QC);
+            for (int a = std::max(B0, c0); a < B1; ++a) {
+                const double sa = ts.pgs[a].smax;
+                const long long start = (long long)tl.size();
+                for (int j = c0; j < c1; ++j) {
+                    const int b = order[j];
+                    if (!(sa * ts.pgs[b].smax > itol)) break;
+                    if (b <= a) tl.push_back(make_int2(a, b));
+                }
+                if ((long long)tl.size() > start) runs.emplace_back(start, (int)((long long)tl.size() - start));
+            }
         }
     }
-    run_beg.push_back((long long)tl.size());
     const long long ntiles = (long long)tl.size();
     if (ntiles > 2000000000LL) throw std::runtime_error("valence_b200: tile list too long");
-    // work items of the s/p kernel: runs of <= m tiles sharing the bra pair group; the d-shell kernel takes single tiles
-    // (only this rank's items: block-cyclic over the ranks; z = slot of the item's first tile in the G hand-over buffer)
+    // work items of the s/p kernel: pieces of <= m tiles of a run (they share the bra pair group); the d-shell
+    // kernel takes single tiles.  Only this rank's items are kept (block-cyclic over the ranks; z = slot of the
+    // item's first tile in the G hand-over buffer).
     std::vector<int4> itl;
     long long my_tiles = 0;
     if (!gen) {
         const long long m = std::max<long long>(1, std::min<long long>(PT_MAXQ, ntiles / ((long long)nsm * nranks * 16)));
         long long idx = 0;
-        for (int a = 0; a < npg; ++a)
-            for (long long k = run_beg[a]; k < run_beg[a + 1]; k += m, ++idx) {
+        for (const auto& run : runs)
+            for (long long k = run.first; k < run.first + run.second; k += m, ++idx) {
                 if (idx % nranks != rank) continue;
-                const int cnt = (int)std::min<long long>(m, run_beg[a + 1] - k);
+                const int cnt = (int)std::min<long long>(m, run.first + run.second - k);
                 itl.push_back(make_int4((int)k, cnt, (int)my_tiles, 0));
                 my_tiles += cnt;
             }
@@ -529,6 +546,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     long long mine = (long long)itl.size();
     if (gen) { mine = 0; for (long long k = rank; k < ntiles; k += nranks) mine++; }
     double t4 = now_ms();
+    if (dbg_time) std::printf("[time] diag pass + tile list %.1f ms (tiles %lld items %zu)\n", t4 - t3, ntiles, itl.size());
     // ---- energy pass ---------------------------------------------------------------------------------
     this->sch.upload(sch, st);
     tiles.upload(tl, st); items.upload(itl, st);
