@@ -57,6 +57,17 @@ __device__ __forceinline__ void quartet_values(const double* __restrict__ boys_t
 {
     constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
     constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    if constexpr (M == 0) {
+        // (ss|ss): the far field needs one reciprocal square root.  With s = p q |PQ|^2 and T = s / (p + q):
+        // T >= Tmax  <=>  s >= Tmax (p + q), and  pref F_0(T) = Ka Kb (p+q)^-1/2 * (sqrt(pi)/2) T^-1/2 = Ka Kb (sqrt(pi)/2) s^-1/2
+        const double u = a.p + b.p;
+        const double dx = a.Px - b.Px, dy = a.Py - b.Py, dz = a.Pz - b.Pz;
+        const double s = a.p * b.p * (dx * dx + dy * dy + dz * dz);
+        if (s >= BOYS_S_TMAX * u) {
+            acc[0] += a.Kp * b.Kp * 0.88622692545275801365 * rsqrt(s);
+            return;
+        }
+    }
     QuartetGeom geo;
     double T, pref;
     quartet_geom(a, b, geo, T, pref);
