@@ -1,0 +1,74 @@
+// Host-side check of the pair-group table build (vb_setup.cpp): the layout must not depend on the
+// number of host threads (every rank of a multi-GPU run derives its tile list from it), the flat
+// (magnitude-sorted) primitive lists must be permutations of the shell-pair-grouped ones, and the
+// compact Boys table must reproduce the exact series.  Built and run by tests/test_host_math.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../valence_b200/csrc/vb_setup.h"
+using namespace vb;
+
+static TileSetup build(const Input& in, const char* threads)
+{
+    setenv("VB_HOST_THREADS", threads, 1);
+    std::vector<double> xyz(3 * in.natom);
+    for (int i = 0; i < 3 * in.natom; ++i) xyz[i] = in.coords[i] * ANGS2BOHR;
+    Basis bas = build_basis(in, xyz);
+    std::vector<std::vector<double>> coeff;
+    for (const OrbitalDef& o : in.orbitals) coeff.push_back(o.coeff);
+    std::vector<ExpOrb> orbs;
+    for (int o = 0; o < in.norbs(); ++o) orbs.push_back(expand_orbital(in, bas, coeff, o));
+    Wavefunction wf;
+    wf.nnd = in.nnd(); wf.nso = wf.nnd + in.ndocc;
+    for (int i = 0; i < wf.nnd; ++i) { wf.bra.push_back(i); wf.ket.push_back(i); }
+    for (int d = 0; d < in.ndocc; ++d) for (int k = 0; k < 2; ++k) { wf.bra.push_back(wf.nnd + d); wf.ket.push_back(wf.nnd + d); }
+    TileSetup ts;
+    build_tiles(in, bas, wf, orbs, 1e-22, true, &ts);
+    return ts;
+}
+
+template <class T>
+static bool same(const std::vector<T>& a, const std::vector<T>& b)
+{
+    return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(T)) == 0);
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) return 2;
+    Input in = parse_input_file(argv[1]);
+    TileSetup a = build(in, "1"), b = build(in, "5");
+    int bad = 0;
+    if (!same(a.pg_pairs, b.pg_pairs) || !same(a.sps, b.sps) || !same(a.pps, b.pps) || !same(a.pps_flat, b.pps_flat) ||
+        !same(a.dmat, b.dmat) || !same(a.pgs, b.pgs)) { std::printf("layout depends on the thread count\n"); ++bad; }
+    if (a.pps.size() != a.pps_flat.size()) { std::printf("flat list size\n"); ++bad; }
+    for (const PGDesc& pg : a.pgs)
+        for (int t = 0; t < NPTYPE; ++t) {
+            std::vector<double> g, f;
+            for (int k = pg.pp_beg[t]; k < pg.pp_beg[t + 1]; ++k) { g.push_back(a.pps[k].w); f.push_back(a.pps_flat[k].w); }
+            if (!std::is_sorted(f.begin(), f.end(), [](double x, double y) { return x > y; })) { std::printf("flat list not sorted\n"); ++bad; }
+            std::sort(g.begin(), g.end()); std::sort(f.begin(), f.end());
+            if (g != f) { std::printf("flat list is not a permutation\n"); ++bad; }
+        }
+    // shell pairs of a type come by non-increasing contraction length (quads of similar trip count)
+    for (const PGDesc& pg : a.pgs)
+        for (int t = 0; t < NPTYPE; ++t)
+            for (int k = pg.sp_beg[t] + 1; k < pg.sp_beg[t + 1]; ++k)
+                if (a.sps[k].pp_cnt > a.sps[k - 1].pp_cnt) { std::printf("shell pairs not sorted by length\n"); ++bad; }
+    // compact Boys table against the exact series
+    std::vector<double> tab(BOYS_S_SIZE);
+    boys_make_table_small(tab.data());
+    double worst = 0.0;
+    for (double T = 0.0; T < 60.0; T += 0.0173) {
+        double F[5], R[5], G[3];
+        boys_s<4>(tab.data(), T, F); boys_s<2>(tab.data(), T, G); boys_reference(4, T, R);
+        for (int m = 0; m <= 4; ++m) worst = std::fmax(worst, std::fabs(F[m] - R[m]));
+        for (int m = 0; m <= 2; ++m) worst = std::fmax(worst, std::fabs(G[m] - R[m]));
+    }
+    if (worst > 2e-15) { std::printf("compact Boys table off by %.3e\n", worst); ++bad; }
+    std::printf("pair groups %zu, primitive pairs %zu, Boys max abs dev %.2e, %s\n", a.pgs.size(), a.pps.size(), worst, bad ? "FAIL" : "OK");
+    return bad ? 1 : 0;
+}

@@ -15,3 +15,20 @@ def test_vrr_and_boys_against_oracle(tmp_path):
                            str(obj), "-lm"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_pair_table_build_is_thread_count_independent(tmp_path):
+    """vb_setup.cpp on the CPU: identical tables for 1 and 5 host threads (multi-GPU ranks must derive
+    the same tile list), flat primitive lists = sorted permutations, compact Boys table vs exact series."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from valence_b200 import inputs
+    inp = tmp_path / "w6.inp"
+    inp.write_text(inputs.write(inputs.water_cluster(6, tol=(10, 20, 10), rotate=True)))
+    exe = tmp_path / "test_setup"
+    csrc = os.path.join(ROOT, "valence_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I", csrc, "-o", str(exe),
+                           os.path.join(ROOT, "tests", "host", "test_setup_host.cpp"),
+                           os.path.join(csrc, "vb_setup.cpp"), os.path.join(csrc, "vb_input.cpp")])
+    out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

@@ -102,7 +102,7 @@ struct Engine::Impl {
     std::vector<std::vector<double>> coeff;          // current orbital weights (normalised in energy())
     std::vector<double> xyz_angs;
     // device data
-    DBuf<double> boys, boys_small, gbuf, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
+    DBuf<double> boys, boys_small, gbuf, gred, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket, gj_n;
     DBuf<long long> gj_off, gj_poff;
@@ -407,6 +407,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     int pp_cap = std::max(1, ts.max_npp);
     size_t smem;
     int boys_cap = 0;
+    double* A_gred = nullptr;
     if (gen) {
         smem = ((size_t)dq_cap2 + hs_cap) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
         if (smem + 2 * (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += 2 * (size_t)pp_cap * sizeof(PrimPair);
@@ -427,6 +428,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
     pps.upload(ts.pps, st); pps_flat.upload(ts.pps_flat, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
+    if (!gen) { gred.alloc((size_t)nsm * PT_MAXQ * g_cap); A_gred = gred.p; }
     int grid_cap = nsm;
     if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
     if (gen) CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -438,6 +440,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
 
     TileArgs A;
     std::memset(&A, 0, sizeof A);
+    A.gred = A_gred;
     A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pps_flat = pps_flat.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;

@@ -41,6 +41,7 @@ struct TileArgs {
     int ntiles;
     const int4* items;               // k_ptile work items: (first tile, # tiles, G slot, -) runs of tiles sharing the bra pair group
     int nitems;
+    double* gred;                    // k_ptile energy pass: per-CTA G accumulation slices, grid x 8 x g_cap doubles
     double* gbuf;                    // hand-over of the heavy classes' share of G, g_cap doubles per tile slot
     long long gslot_base;            // slot of the first tile of the current chunk
     int tile_first, tile_stride;     // static block-cyclic shard of this rank; work stealing inside

@@ -101,7 +101,7 @@ template <int PART, int TK>
 __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const PGDesc& Q, int oct, const PrimPair* __restrict__ bpps,
                                       const SPRec* __restrict__ spss,
                                       const double* __restrict__ Dp_s, const double* __restrict__ Dq_g, const double* __restrict__ boys_tab,
-                                      double* __restrict__ scratch, double* __restrict__ Gw, bool priv, int lane,
+                                      double* __restrict__ scratch, double* __restrict__ Gw, double* __restrict__ Gglob, bool priv, int lane,
                                       unsigned long long* __restrict__ s_pq)
 {
     constexpr int NF = pt_ne(TK);
@@ -189,7 +189,7 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
         }
     }
     // Schwarz pass: warp-private partials (fixed order inside a warp; the warps are summed in fixed order
-    // later); energy pass: the tile's shared G through shared-memory atomics
+    // later); energy pass: FP64 reductions into the tile's G in the CTA's global slice (RED.ADD.F64 at L2)
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int q = 8 * m + g;
@@ -201,7 +201,7 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
                 const int p = 8 * j + 2 * t + i;
                 if (p < P.np) {
                     if (priv) Gw[q * P.np + p] += C[m][j][i];
-                    else atomicAdd(&Gw[q * P.np + p], C[m][j][i]);
+                    else atomicAdd(&Gglob[q * P.np + p], C[m][j][i]);
                 }
             }
     }
@@ -296,10 +296,14 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
             s_unit = 0;
         }
         const PrimPair* bpps = A.pp_cap ? bpp_s : A.pps + P.pp_beg[0];
-        if (PART == PART_LIGHT) {
-            for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) Gs[i] = gbuf[i];        // the heavy classes' share
+        // energy pass: the tiles' G live in this CTA's slice of a global (L2-resident) buffer and are accumulated with
+        // fire-and-forget FP64 reductions (native at L2; shared memory has no FP64 atomic add, only a CAS loop)
+        double* Gg = A.gred + (size_t)blockIdx.x * PT_MAXQ * A.g_cap;
+        if (priv) {
+            for (int i = tid; i < nwp * A.g_cap; i += PT_THREADS) Gs[i] = 0.0;
         } else {
-            for (int i = tid; i < (priv ? nwp : ntl) * A.g_cap; i += PT_THREADS) Gs[i] = 0.0;
+            for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) __stcg(&Gg[i], PART == PART_LIGHT ? gbuf[i] : 0.0);
+            __threadfence();
         }
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
@@ -329,19 +333,24 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
             while (s_cum[c + 1] <= u) ++c;
             const int tk = 2 - c / PT_MAXQ, qi = c % PT_MAXQ, oct = u - s_cum[c];
             const PGDesc& Q = s_Q[qi];
-            double* Gw = Gs + (priv ? warp : qi) * A.g_cap;
+            double* Gw = Gs + warp * A.g_cap;                 // Schwarz pass: warp-private partial
+            double* Gglob = A.gred + ((size_t)blockIdx.x * PT_MAXQ + qi) * A.g_cap;   // energy pass: the tile's G in the CTA's global slice
             const double* Dq_g = A.dmat + Q.d_off;
             switch (tk) {
-                case 0: ptask<PART, 0>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
-                case 1: ptask<PART, 1>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
-                default: ptask<PART, 2>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, priv, lane, s_pq); break;
+                case 0: ptask<PART, 0>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, Gglob, priv, lane, s_pq); break;
+                case 1: ptask<PART, 1>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, Gglob, priv, lane, s_pq); break;
+                default: ptask<PART, 2>(A, P, Q, oct, bpps, sps_s, Dp_s, Dq_g, boys_tab, scratch, Gw, Gglob, priv, lane, s_pq); break;
             }
         }
+        if (!priv) __threadfence();
         __syncthreads();
+        if (!priv)
+            for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) Gs[i] = __ldcg(&Gg[i]);
         if (PART == PART_HEAVY) {
             for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) gbuf[i] = Gs[i];
             continue;
         }
+        if (!priv) __syncthreads();
         if (priv) {
             // fixed-order sum of the warp partials -> Gs[0 .. gsz)
             const int gsz = P.np * s_Q[0].np;

@@ -491,41 +491,75 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         work();
         for (std::thread& t : pool) t.join();
     }
+    // merge: offsets by a serial scan, the copies (and the magnitude sort of the flat lists) on the host cores
+    struct Off { size_t pairs, sps, pps, d; int pg; };
+    std::vector<Off> offs(outs.size());
     {
-        size_t n_pairs = 0, n_sps = 0, n_pps = 0, n_d = 0, n_pg = 0;
-        for (const PGOut& o : outs)
-            if (o.used) { n_pairs += o.pairs.size(); n_sps += o.sps.size(); n_pps += o.pps.size(); n_d += o.dmat.size(); ++n_pg; }
-        ts.pg_pairs.reserve(n_pairs); ts.sps.reserve(n_sps); ts.pps.reserve(n_pps); if (flat) ts.pps_flat.reserve(n_pps); ts.dmat.reserve(n_d); ts.pgs.reserve(n_pg);
-    }
-    for (PGOut& o : outs) {
-        if (!o.used) continue;
-        PGDesc pg = o.pg;
-        const int pp0 = (int)ts.pps.size(), sp0 = (int)ts.sps.size();
-        pg.pair_beg = (int)ts.pg_pairs.size() / 2;
-        pg.d_off = (long long)ts.dmat.size();
-        for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += pp0; pg.sp_beg[t] += sp0; }
-        for (SPRec& r : o.sps) r.pp_beg += pp0;
-        ts.pg_pairs.insert(ts.pg_pairs.end(), o.pairs.begin(), o.pairs.end());
-        ts.sps.insert(ts.sps.end(), o.sps.begin(), o.sps.end());
-        ts.pps.insert(ts.pps.end(), o.pps.begin(), o.pps.end());
-        if (flat) {   // one magnitude-sorted list per pair type (each primitive carries its shell pair's e-offset)
-            ts.pps_flat.insert(ts.pps_flat.end(), o.pps.begin(), o.pps.end());
-            for (int t = 0; t < NPTYPE; ++t)
-                std::stable_sort(ts.pps_flat.begin() + pg.pp_beg[t], ts.pps_flat.begin() + pg.pp_beg[t + 1],
-                                 [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
+        Off run = {0, 0, 0, 0, 0};
+        for (size_t i = 0; i < outs.size(); ++i) {
+            offs[i] = run;
+            const PGOut& o = outs[i];
+            if (!o.used) continue;
+            run.pairs += o.pairs.size(); run.sps += o.sps.size(); run.pps += o.pps.size(); run.d += o.dmat.size(); run.pg += 1;
         }
-        ts.dmat.insert(ts.dmat.end(), o.dmat.begin(), o.dmat.end());
+        ts.pg_pairs.resize(run.pairs); ts.sps.resize(run.sps); ts.pps.resize(run.pps); ts.dmat.resize(run.d); ts.pgs.resize(run.pg);
+        if (flat) ts.pps_flat.resize(run.pps);
+    }
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t i0 = next.fetch_add(64);
+                if (i0 >= outs.size()) break;
+                for (size_t i = i0; i < std::min(outs.size(), i0 + 64); ++i) {
+                    PGOut& o = outs[i];
+                    if (!o.used) continue;
+                    const Off& f = offs[i];
+                    PGDesc pg = o.pg;
+                    const int pp0 = (int)f.pps, sp0 = (int)f.sps;
+                    pg.pair_beg = (int)(f.pairs / 2);
+                    pg.d_off = (long long)f.d;
+                    for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += pp0; pg.sp_beg[t] += sp0; }
+                    for (SPRec& r : o.sps) r.pp_beg += pp0;
+                    std::copy(o.pairs.begin(), o.pairs.end(), ts.pg_pairs.begin() + f.pairs);
+                    std::copy(o.sps.begin(), o.sps.end(), ts.sps.begin() + f.sps);
+                    std::copy(o.pps.begin(), o.pps.end(), ts.pps.begin() + f.pps);
+                    std::copy(o.dmat.begin(), o.dmat.end(), ts.dmat.begin() + f.d);
+                    if (flat) {   // one magnitude-sorted list per pair type (each primitive carries its shell pair's e-offset)
+                        std::vector<int> idx;
+                        for (int t = 0; t < NPTYPE; ++t) {
+                            const int b0 = pg.pp_beg[t] - pp0, b1 = pg.pp_beg[t + 1] - pp0;
+                            idx.resize(b1 - b0);
+                            for (int k = 0; k < b1 - b0; ++k) idx[k] = b0 + k;
+                            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return o.pps[x].w > o.pps[y].w; });
+                            for (int k = 0; k < b1 - b0; ++k) ts.pps_flat[f.pps + b0 + k] = o.pps[idx[k]];
+                        }
+                    }
+                    ts.pgs[f.pg] = pg;
+                    std::vector<int>().swap(o.pairs); std::vector<double>().swap(o.dmat); std::vector<PrimPair>().swap(o.pps);
+                }
+            }
+        };
+        int nthr = (int)std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("VB_HOST_THREADS")) nthr = std::atoi(e);
+        nthr = std::max(1, std::min(nthr, 32));
+        if (outs.size() < 256) nthr = 1;
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread& t : pool) t.join();
+    }
+    for (size_t i = 0; i < outs.size(); ++i) {
+        const PGOut& o = outs[i];
+        if (!o.used) continue;
+        const PGDesc& pg = ts.pgs[offs[i].pg];
         ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
         ts.max_nsp = std::max(ts.max_nsp, (int)o.sps.size());
-        {
-            int ks[NPTYPE] = {0, 0, 0, 0, 0, 0};
-            for (const SPRec& r : o.sps) ks[r.type] += pt_ne(r.type);
-            for (int t = 0; t < NPTYPE; ++t) ts.max_ks = std::max(ts.max_ks, ks[t]);
-        }
+        int ks[NPTYPE] = {0, 0, 0, 0, 0, 0};
+        for (const SPRec& r : o.sps) ks[r.type] += pt_ne(r.type);
+        for (int t = 0; t < NPTYPE; ++t) ts.max_ks = std::max(ts.max_ks, ks[t]);
         ts.max_ne = std::max(ts.max_ne, pg.ne);
         ts.max_np = std::max(ts.max_np, pg.np);
-        ts.pgs.push_back(pg);
-        PGOut().pairs.swap(o.pairs); std::vector<double>().swap(o.dmat); std::vector<PrimPair>().swap(o.pps);
     }
     for (const GShell& s : bas.shells) ts.lmax = std::max(ts.lmax, s.l);
 }
