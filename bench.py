@@ -213,6 +213,19 @@ def run_ours(args) -> None:
                          "flops": "algorithmic: executed primitive quartets per class x per-class operation count (DESIGN.md)"},
             "clocks": sampler.summary() if sampler else None,
         }
+        if args.grad_waters > 0 and world == 1:
+            # Metric 2: guess energy + one first_order_opt accumulator build (ham, ovl of orbital 1) on a
+            # smaller cluster -- the (ib,jb) loop re-runs the tile pass per matrix element, like the reference
+            gp = make_input(args.grad_waters)
+            ge = api.Engine(gp, device=local)
+            ge.energy(); ge.first_order(1)
+            torch.cuda.synchronize(local)
+            t0g = time.perf_counter()
+            ge.energy(); _, _, st = ge.first_order(1)
+            torch.cuda.synchronize(local)
+            line["energy_plus_first_order"] = {"waters": args.grad_waters, "ms": 1e3 * (time.perf_counter() - t0g), "orbital": 1,
+                                               "tile_passes": int(st["tile_launches"])}
+            ge.close(); os.unlink(gp)
         if args.cpu_baseline_seconds > 0 and world == 1:
             from oracle import oracle
             cb = oracle.cpu_baseline(path, seconds=args.cpu_baseline_seconds)
@@ -234,6 +247,7 @@ def main():
     ap.add_argument("--waters", type=int, default=int(os.environ.get("VB_BENCH_WATERS", "256")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--grad-waters", type=int, default=16, help="cluster size of the energy + first_order_opt timing (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

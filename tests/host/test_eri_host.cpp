@@ -39,6 +39,14 @@ static void run_unrolled(const std::vector<PrimPair>& P, const std::vector<PrimP
         vrr_unrolled<LA,EA,LC,EC>(g, F, acc);
     }
 }
+template <int LA, int EA, int LC, int EC>
+static void run_unrolled_small(const std::vector<PrimPair>& P, const std::vector<PrimPair>& Q, const double* tabs, double* acc) {
+    for (auto& a : P) for (auto& b : Q) {   // what k_ptile executes: compact Boys table (boys_s) + unrolled VRR
+        QuartetGeom g; double T, pref; quartet_geom(a, b, g, T, pref);
+        double F[EA+EC+1]; boys_s<EA+EC>(tabs, T, F); for (int m = 0; m <= EA+EC; ++m) F[m] *= pref;
+        vrr_unrolled<LA,EA,LC,EC>(g, F, acc);
+    }
+}
 static void run_generic(int LA, int EA, int LC, int EC, const std::vector<PrimPair>& P, const std::vector<PrimPair>& Q, const double* tab, double* acc) {
     std::vector<double> scratch(GEN_SCRATCH);
     for (auto& a : P) for (auto& b : Q) {
@@ -50,6 +58,7 @@ static void run_generic(int LA, int EA, int LC, int EC, const std::vector<PrimPa
 
 int main() {
     std::vector<double> tab((size_t)BOYS_ROWS*BOYS_COLS); boys_make_table(tab.data());
+    std::vector<double> tabs(BOYS_S_SIZE); boys_make_table_small(tabs.data());
     // Boys check
     double worst_b = 0;
     for (double T = 0; T < 90; T += 0.0173) { double F[MTOP+1], R[MTOP+1]; boys_rt(MTOP, tab.data(), T, F); boys_reference(MTOP, T, R);
@@ -70,13 +79,11 @@ int main() {
         std::vector<double> acc(NE*NF, 0.0), acc2(NE*NF, 0.0);
         auto P = pairs(A,B), Q = pairs(C,D);
         run_generic(l[0],EA,l[2],EC,P,Q,tab.data(),acc.data());
-        if (l[0] <= 1 && l[2] <= 1) {   // compact table-driven path vs loop-based generic
-            std::vector<double> acc3(NE*NF, 0.0), sc(CMP_SCRATCH);
-            for (auto& a : P) for (auto& b : Q) {
-                QuartetGeom g; double T, pref; quartet_geom(a, b, g, T, pref);
-                double F[MTOP+1]; boys_rt(EA+EC, tab.data(), T, F); for (int m = 0; m <= EA+EC; ++m) F[m] *= pref;
-                vrr_compact(l[0],EA,l[2],EC,g,F,sc.data(),acc3.data());
-            }
+        if (l[0] <= 1 && l[2] <= 1) {   // the s/p kernel's path (compact Boys table) vs loop-based generic
+            std::vector<double> acc3(NE*NF, 0.0);
+            int tb = ptype(l[0],l[1]), tk = ptype(l[2],l[3]);
+#define CASES(TB,TK) if (tb==TB && tk==TK) run_unrolled_small<pt_la(TB),pt_E(TB),pt_la(TK),pt_E(TK)>(P,Q,tabs.data(),acc3.data());
+            CASES(0,0) CASES(0,1) CASES(0,2) CASES(1,0) CASES(1,1) CASES(1,2) CASES(2,0) CASES(2,1) CASES(2,2)
             double mx = 0; for (int i = 0; i < NE*NF; ++i) mx = std::fmax(mx, std::fabs(acc[i]));
             for (int i = 0; i < NE*NF; ++i) worst_ug = std::fmax(worst_ug, std::fabs(acc[i]-acc3[i])/mx);
         }

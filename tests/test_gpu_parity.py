@@ -144,6 +144,22 @@ def test_sharded_partials_sum_to_single_gpu_energy(write_input):
     assert r["counters"] == full["counters"]
 
 
+def test_split_launch_variant_matches_single_launch(write_input, monkeypatch):
+    """VB_SPLIT=1: pp-containing classes and light classes in separate launches with G handed over through
+    HBM in chunks (VB_GBUF_MB bounds the buffer; 1 MB forces several chunks): same energy and counters."""
+    from valence_b200 import api, inputs
+    path, _ = write_input(inputs.water_cluster(8, tol=(10, 20, 10), rotate=True))
+    eng = api.Engine(path)
+    a = eng.energy()
+    monkeypatch.setenv("VB_SPLIT", "1")
+    monkeypatch.setenv("VB_GBUF_MB", "1")
+    b = eng.energy()
+    eng.close()
+    assert abs(a["energy"] - b["energy"]) < 1e-11
+    assert a["counters"] == b["counters"]
+    assert b["tile_launches"] > 1
+
+
 def test_medium_cluster_properties(write_input):
     """(H2O)_16: beyond the literal oracle's reach.  Size-independent checks: extensivity against
     the monomer (weakly interacting at 3.1 A: binding energy per molecule is small and negative-ish

@@ -104,8 +104,7 @@ struct Engine::Impl {
     // device data
     DBuf<double> boys, boys_small, gbuf, gred, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
-    DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket, gj_n;
-    DBuf<long long> gj_off, gj_poff;
+    DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket;
     DBuf<double> oc;
     DBuf<int2> opairs, tiles;
     DBuf<int4> items;
@@ -444,7 +443,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pps_flat = pps_flat.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
-    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.strip_ld = 0; A.g_cap = g_cap; A.boys_small = boys_small.p; A.boys_cap = boys_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.g_cap = g_cap; A.boys_small = boys_small.p; A.boys_cap = boys_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;

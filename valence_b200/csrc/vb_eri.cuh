@@ -333,75 +333,6 @@ VB_HD void vrr_generic(int LA, int EA, int LC, int EC, const QuartetGeom& g, con
 #undef TT
 }
 
-// ---------------------------------------------------------------------------
-// Compact VRR for the rare heavy s/p classes (EA, EC <= 2): same recurrence, runtime loops over
-// small lookup tables, so the code stays a few hundred instructions (the unrolled pp|pp body alone
-// is ~10k instructions and evicts the hot classes from the instruction cache).
-// ---------------------------------------------------------------------------
-struct CompTab {
-    signed char dir[ncum(2)], dec[ncum(2)], dec2[ncum(2)], n1[ncum(2)], L[ncum(2)], lx[ncum(2)], ly[ncum(2)], lz[ncum(2)];
-};
-constexpr CompTab make_comp_tab()
-{
-    CompTab t{};
-    for (int c = 0; c < ncum(2); ++c) {
-        t.L[c] = (signed char)c_L(c);
-        t.lx[c] = (signed char)c_lx(c); t.ly[c] = (signed char)c_ly(c); t.lz[c] = (signed char)c_lz(c);
-        if (c == 0) { t.dir[c] = 0; t.dec[c] = 0; t.dec2[c] = 0; t.n1[c] = 0; continue; }
-        int d = c_dir(c), e1 = c_dec(c, d), n = c_l(e1, d);
-        t.dir[c] = (signed char)d; t.dec[c] = (signed char)e1; t.n1[c] = (signed char)n;
-        t.dec2[c] = (signed char)(n > 0 ? c_dec(e1, d) : 0);
-    }
-    return t;
-}
-#ifdef __CUDACC__
-__device__ __constant__ CompTab d_comp_tab = make_comp_tab();
-#define VB_COMP_TAB d_comp_tab
-#else
-static const CompTab h_comp_tab = make_comp_tab();
-#define VB_COMP_TAB h_comp_tab
-#endif
-constexpr int CMP_NE = ncum(2);                 // 10
-constexpr int CMP_SCRATCH = 5 * CMP_NE * CMP_NE;
-
-#ifdef __CUDACC__
-__device__
-#endif
-inline void vrr_compact(int LA, int EA, int LC, int EC, const QuartetGeom& g, const double* __restrict__ Fm,
-                        double* __restrict__ T /* CMP_SCRATCH */, double* __restrict__ acc)
-{
-    const CompTab& tab = VB_COMP_TAB;
-    const int NE = ncum(EA), NFc = ncum(EC), MT = EA + EC, NF = ncum(EC) - coff(LC);
-#define TT(m, e, f) T[((m) * CMP_NE + (e)) * CMP_NE + (f)]
-    for (int m = 0; m <= MT; ++m) TT(m, 0, 0) = Fm[m];
-    for (int e = 1; e < NE; ++e) {
-        const int d = tab.dir[e], e1 = tab.dec[e], n1 = tab.n1[e], e2 = tab.dec2[e], Le = tab.L[e];
-        for (int m = 0; m <= MT - Le; ++m) {
-            double v = g.PA[d] * TT(m, e1, 0) + g.WP[d] * TT(m + 1, e1, 0);
-            if (n1 > 0) v += (n1 * g.h2p) * (TT(m, e2, 0) - g.rp * TT(m + 1, e2, 0));
-            TT(m, e, 0) = v;
-        }
-    }
-    for (int f = 1; f < NFc; ++f) {
-        const int d = tab.dir[f], f1 = tab.dec[f], n1 = tab.n1[f], f2 = tab.dec2[f], Lf = tab.L[f];
-        for (int e = 0; e < NE; ++e) {
-            const int Le = tab.L[e];
-            const int ne = d == 0 ? tab.lx[e] : (d == 1 ? tab.ly[e] : tab.lz[e]);
-            int em = 0;
-            if (ne > 0) em = (tab.dir[e] == d) ? tab.dec[e] : cidx(tab.lx[e] - (d == 0), tab.ly[e] - (d == 1), tab.lz[e] - (d == 2));
-            for (int m = 0; m <= MT - Le - Lf; ++m) {
-                double v = g.QC[d] * TT(m, e, f1) + g.WQ[d] * TT(m + 1, e, f1);
-                if (n1 > 0) v += (n1 * g.h2q) * (TT(m, e, f2) - g.rq * TT(m + 1, e, f2));
-                if (ne > 0) v += (ne * g.h2pq) * TT(m + 1, em, f1);
-                TT(m, e, f) = v;
-            }
-        }
-    }
-    for (int e = coff(LA); e < NE; ++e)
-        for (int f = coff(LC); f < NFc; ++f) acc[(e - coff(LA)) * NF + (f - coff(LC))] += TT(0, e, f);
-#undef TT
-}
-
 // geometry of one primitive quartet; returns T = rho |PQ|^2 and the prefactor K_a K_b / (p q sqrt(p+q)).
 // Division-free: one rsqrt.
 VB_HD void quartet_geom(const PrimPair& a, const PrimPair& b, QuartetGeom& g, double& T, double& pref)

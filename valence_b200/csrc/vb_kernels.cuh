@@ -3,7 +3,7 @@
 //   k_ao_1e        AO overlap and core-Hamiltonian matrices (replaces the SIMINT
 //                  overlap/ke/potential calls of ovint/int1e, valence.F90:2988,3132,3151)
 //   k_orb_1e       orbital-level <bra_s|ket_t>, <bra_s|h|ket_t> (ovint/int1e, :2891-3176)
-//   k_gather_block / k_gj_inverse / k_entry_density
+//   k_gather_block / k_gj_inverse_grid / k_entry_density
 //                  spin-block overlap matrices, their inverses and determinants
 //                  (replaces density/det/givdr, :1535-2144, by the inverse form,
 //                  SURVEY.md appendix B)
@@ -50,7 +50,7 @@ struct TileArgs {
     int nso, nnd, sym, subject;
     int dq_cap;                      // doubles reserved for the staged ket density
     int hs_cap, pp_cap, sp_cap;      // shared-memory capacities: H tile (doubles), primitive pairs per side, shell pairs
-    int hs_ld, strip_ld;             // row strides of the H tile and of the per-warp integral strips
+    int hs_ld;                       // row stride of the H tile (k_tile)
     int g_cap;                       // k_ptile: doubles per warp-private G[q][p] partial
     const double* boys_small;        // compact Boys table (vb_eri.cuh, boys_s)
     int boys_cap;                    // BOYS_S_SIZE when the table is staged in shared memory, else 0
@@ -262,71 +262,6 @@ __global__ void k_gather_block(const double* __restrict__ Se, int nso, const int
     if (idx >= n * n) return;
     int r = idx / n, c = idx % n;
     M[idx] = Se[(size_t)bra_entry[r] * nso + ket_entry[c]];
-}
-
-// In-place Gauss-Jordan inverse with partial pivoting, one CTA per matrix (row-major, n x n).
-// out[0] = determinant, out[1] = smallest |pivot| / largest |pivot| seen.
-__global__ void k_gj_inverse(double* __restrict__ Ms, const int* __restrict__ ns, const long long* __restrict__ offs,
-                             int* __restrict__ piv_ws, const long long* __restrict__ piv_offs, double* __restrict__ outs)
-{
-    const int b = blockIdx.x, n = ns[b];
-    double* A = Ms + offs[b];
-    int* piv = piv_ws + piv_offs[b];
-    double* out = outs + 2 * b;
-    __shared__ double s_val[32];
-    __shared__ int s_idx[32];
-    __shared__ double s_piv, s_det, s_min, s_max;
-    __shared__ int s_row;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) { s_det = 1.0; s_min = 1e300; s_max = 0.0; }
-    if (n == 0) { if (tid == 0) { out[0] = 1.0; out[1] = 1.0; } return; }
-    __syncthreads();
-    for (int k = 0; k < n; ++k) {
-        // pivot search in column k, rows k..n-1
-        double best = -1.0; int bi = k;
-        for (int r = k + tid; r < n; r += nt) { double v = fabs(A[(size_t)r * n + k]); if (v > best) { best = v; bi = r; } }
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_down_sync(0xffffffffu, best, o); int oi = __shfl_down_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            double bv = -1.0; int br = k;
-            for (int w = 0; w < (nt + 31) / 32; ++w) if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < br)) { bv = s_val[w]; br = s_idx[w]; }
-            s_row = br; piv[k] = br;
-            double pv = A[(size_t)br * n + k];
-            s_piv = pv;
-            s_det *= (br != k) ? -pv : pv;
-            s_min = fmin(s_min, fabs(pv)); s_max = fmax(s_max, fabs(pv));
-        }
-        __syncthreads();
-        const int pr = s_row; const double pv = s_piv;
-        if (pv == 0.0) { if (tid == 0) { out[0] = 0.0; out[1] = 0.0; } return; }
-        if (pr != k) for (int c = tid; c < n; c += nt) { double t = A[(size_t)k * n + c]; A[(size_t)k * n + c] = A[(size_t)pr * n + c]; A[(size_t)pr * n + c] = t; }
-        __syncthreads();
-        const double ipv = 1.0 / pv;
-        for (int c = tid; c < n; c += nt) A[(size_t)k * n + c] = (c == k) ? ipv : A[(size_t)k * n + c] * ipv;
-        __syncthreads();
-        // eliminate column k from every other row: one warp per row strip
-        for (int r = (tid >> 5); r < n; r += (nt >> 5)) {
-            if (r == k) continue;
-            double f = A[(size_t)r * n + k];
-            if (f == 0.0) continue;
-            for (int c = (tid & 31); c < n; c += 32) {
-                double v = A[(size_t)r * n + c];
-                A[(size_t)r * n + c] = (c == k) ? -f * A[(size_t)k * n + k] : v - f * A[(size_t)k * n + c];
-            }
-        }
-        __syncthreads();
-    }
-    // undo the row interchanges as column interchanges, last first
-    for (int k = n - 1; k >= 0; --k) {
-        int pr = piv[k];
-        if (pr != k) for (int r = tid; r < n; r += nt) { double t = A[(size_t)r * n + k]; A[(size_t)r * n + k] = A[(size_t)r * n + pr]; A[(size_t)r * n + pr] = t; }
-        __syncthreads();
-    }
-    if (tid == 0) { out[0] = s_det; out[1] = s_max > 0.0 ? s_min / s_max : 0.0; }
 }
 
 // Multi-CTA in-place Gauss-Jordan inverse for large blocks (cooperative launch, grid-wide barriers).

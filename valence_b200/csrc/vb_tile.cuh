@@ -1,4 +1,5 @@
-// The fused hot kernel: for one tile (bra pair group P, ket pair group Q)
+// Shell-pair formulation of the fused kernel, kept for basis sets with d shells (k_tile<true>; the s/p
+// kernel is vb_ptile.cuh): for one tile (bra pair group P, ket pair group Q)
 //   1. every contracted shell quartet of the AO block (P-support | Q-support) is generated once
 //      (Obara-Saika VRR per angular-momentum class; warp = one bra shell pair, lanes = ket
 //      primitive-pair chunks of one class),
@@ -191,108 +192,6 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int STRIP_ROWS = 9;    // bra e-rows one warp collects before the tensor-core transform: 8 ss / 2 ps / 1 pp shell pairs
-__host__ __device__ constexpr int strip_spb(int tb) { return tb == 0 ? 8 : (tb == 1 ? 2 : 1); }
-
-// Same work as batch_unrolled up to the contracted partial blocks; the segment heads then add their
-// block into the warp's strip (row = bra e-component of the unit, column = ket f-component inside
-// the ket pair type).  The transformation with the ket densities happens once per unit on the
-// tensor cores (strip_transform) instead of once per segment head with shuffles.
-template <int TB, int TK>
-__device__ __forceinline__ void batch_strip(const TileArgs& A, const SPRec& sp, const PrimPair* __restrict__ bpp,
-                                            const PrimPair* __restrict__ kpp, int base, int nket, int lane, int eoff_tk,
-                                            double* __restrict__ strip, int ld, unsigned long long& npq)
-{
-    constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK), M = EA + EC;
-    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
-    double acc[NE * NF];
-#pragma unroll
-    for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
-    const bool active = base + lane < nket;
-    PrimPair b = kpp[base + (active ? lane : 0)];
-    int seg = active ? b.eoff : -1 - lane;
-    if (!active) { b.Kp = 0.0; b.w = 0.0; }
-    const double wq = kpp[base].wseg;
-    int nbra = 0;
-    for (int ip = 0; ip < sp.pp_cnt; ++ip) {
-        const PrimPair a = bpp[ip];
-        if (!(a.w * wq >= A.tau)) break;           // bra primitives are sorted by weight
-        ++nbra;
-        QuartetGeom g;
-        double T, pref;
-        quartet_geom(a, b, g, T, pref);
-        double F[M + 1];
-        boys<M>(A.boys, T, F);
-#pragma unroll
-        for (int m = 0; m <= M; ++m) F[m] *= pref;
-        if constexpr (M == 0) acc[0] += F[0];
-        else vrr_unrolled<LA, EA, LC, EC>(g, F, acc);
-    }
-    if (nbra == 0) return;
-    if (lane == 0) npq += (unsigned long long)nbra * min(32, nket - base);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int so = __shfl_down_sync(0xffffffffu, seg, o);
-        const bool take = (lane + o < 32) && (so == seg);
-        if (!__any_sync(0xffffffffu, take)) break;     // no run is longer than the stride: done
-#pragma unroll
-        for (int i = 0; i < NE * NF; ++i) {
-            const double v = __shfl_down_sync(0xffffffffu, acc[i], o);
-            if (take) acc[i] += v;
-        }
-    }
-    const int sprev = __shfl_up_sync(0xffffffffu, seg, 1);
-    if (active && (lane == 0 || sprev != seg)) {
-        double* dst = strip + (seg - eoff_tk);       // a ket shell pair may continue from the previous batch: accumulate
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-#pragma unroll
-            for (int f = 0; f < NF; ++f) dst[e * ld + f] += acc[e * NF + f];
-    }
-}
-
-// H[hrow[r]][q] += sum_k strip[r][k] * Dq[k][q] on the FP64 tensor cores (m8n8k4), one warp.
-// MT m-tiles of 8 strip rows; 4 n-tiles cover the (<= 32) ket orbital pairs.
-template <int MT>
-__device__ __forceinline__ void strip_transform(const double* __restrict__ strip, int ld, int nrows, const double* __restrict__ Dq_tk,
-                                                int np, int ks, const int* __restrict__ hrow, double* __restrict__ Hs, int hs_ld, int lane)
-{
-    const int g = lane >> 2, t = lane & 3;
-    double c[MT][4][2];
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { c[m][j][0] = 0.0; c[m][j][1] = 0.0; }
-    const double* arow[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) arow[m] = strip + min(m * 8 + g, STRIP_ROWS - 1) * ld + t;
-    for (int k0 = 0; k0 < ks; k0 += 4) {
-        double a[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) a[m] = arow[m][k0];
-        const double* brow = Dq_tk + min(k0 + t, ks - 1) * np + g;   // padded strip columns are zero: any finite B will do
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double b = brow[8 * j];
-#pragma unroll
-            for (int m = 0; m < MT; ++m) dmma_884(c[m][j][0], c[m][j][1], a[m], b);
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        const int r = m * 8 + g;
-        if (r >= nrows) continue;
-        double* hr = Hs + hrow[r] * hs_ld;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int q = 8 * j + 2 * t + i;
-                if (q < np) atomicAdd(&hr[q], c[m][j][i]);
-            }
-    }
-}
-
 // generic path (any class with a d shell): runtime loops, scratch in global memory
 __device__ __noinline__ void batch_generic(const TileArgs& A, int tb, int tk, const SPRec& sp, const PrimPair* __restrict__ bpp,
                                            const PrimPair* __restrict__ kpp, int npQ, int base, int nket,
@@ -356,9 +255,6 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
     SPRec* spss = reinterpret_cast<SPRec*>(Hs + A.hs_cap);      // bra shell pairs of P
     PrimPair* kpp_s = reinterpret_cast<PrimPair*>(spss + A.sp_cap);   // ket primitive pairs of Q (when they fit)
     PrimPair* bpp_s = kpp_s + A.pp_cap;                         // bra primitive pairs of P
-    double* strips = reinterpret_cast<double*>(bpp_s + A.pp_cap);   // per-warp strips of contracted integrals [STRIP_ROWS][strip_ld]
-    __shared__ int s_hrow[TILE_THREADS / 32][16];
-    __shared__ int s_eoffq[NPTYPE], s_ksq[NPTYPE], s_cumb[NPTYPE];
     __shared__ unsigned long long s_bar;
     unsigned phase = 0;
     if (threadIdx.x == 0) {
@@ -422,158 +318,71 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
         //   energy pass : handed out through a shared counter (dynamic), which keeps all warps busy
         //                 until the tile is done; rows of Hs are accumulated with shared atomics.
         constexpr int NT = GEN ? NPTYPE : 3;
-        if constexpr (!GEN) {
-            // Units = (class (tb|tk), block of bra shell pairs of type tb filling the warp's strip), in class order.
-            if (tid == 0) {
-                int n = 0, nb = 0;
-                for (int tb = 0; tb < NT; ++tb) {
-                    const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb];
-                    const int nblk = (nspb + strip_spb(tb) - 1) / strip_spb(tb);
-                    s_cumb[tb] = nb;
-                    nb += nblk;
-                    for (int tk = 0; tk < NT; ++tk) {
-                        const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-                        s_cum[tb * NT + tk] = n;
-                        if (nspb > 0 && nket > 0 && P.kwmax[tb] * Q.kwmax[tk] >= A.tau) n += nblk;
-                    }
+        if (tid == 0) {
+            int n = 0;
+            for (int tb = 0; tb < NT; ++tb)
+                for (int tk = 0; tk < NT; ++tk) {
+                    const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb], nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+                    s_cum[tb * NT + tk] = n;
+                    if (nspb > 0 && nket > 0 && P.kwmax[tb] * Q.kwmax[tk] >= A.tau) n += nspb;
                 }
-                s_cum[NT * NT] = n;
-                s_unit = 0;
-                // e-offset and width of each ket pair type inside Q's e-space (types are laid out in order)
-                int next = Q.ne;
-                for (int t = NT - 1; t >= 0; --t) {
-                    if (Q.pp_beg[t + 1] > Q.pp_beg[t]) {
-                        const int e = kpps[Q.pp_beg[t] - Q.pp_beg[0]].eoff;
-                        s_eoffq[t] = e; s_ksq[t] = next - e; next = e;
-                    } else { s_eoffq[t] = next; s_ksq[t] = 0; }
-                }
+            s_cum[NT * NT] = n;
+            s_unit = 0;
+        }
+        __syncthreads();
+        const int nunits = s_cum[NT * NT];
+        const bool dynamic = A.mode != 0;
+        int ustat = warp;
+        for (;;) {
+            int u;
+            if (dynamic) {
+                u = 0;
+                if (lane == 0) u = atomicAdd(&s_unit, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+            } else {
+                u = ustat;
+                ustat += nw;
             }
-            __syncthreads();
-            const int nunits = s_cum[NT * NT];
-            const bool dynamic = A.mode != 0;
-            const int ld = A.strip_ld;
-            double* strip = strips + warp * (STRIP_ROWS * ld);
-            int* hrow = s_hrow[warp];
-            int ustat = -1;
-            for (;;) {
-                int u;
-                if (dynamic) {
-                    u = 0;
-                    if (lane == 0) u = atomicAdd(&s_unit, 1);
-                    u = __shfl_sync(0xffffffffu, u, 0);
-                } else {
-                    u = ++ustat;      // static: a warp owns all classes of "its" bra blocks, in class order
-                }
-                if (u >= nunits) break;
-                int c = 0;
-                while (s_cum[c + 1] <= u) ++c;
-                const int tb = c / NT, tk = c - tb * NT, blk = u - s_cum[c];
-                if (!dynamic && (s_cumb[tb] + blk) % nw != warp) continue;
-                const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-                const int cls = tb * NPTYPE + tk;
-                const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb];
-                const int j0 = blk * strip_spb(tb), j1 = min(nspb, j0 + strip_spb(tb));
-                const int neb = pt_ne(tb), ks = s_ksq[tk], eoff_tk = s_eoffq[tk];
-                const PrimPair* kpp = kpps + (Q.pp_beg[tk] - Q.pp_beg[0]);
-                __syncwarp();
-                for (int i = lane; i < STRIP_ROWS * ld; i += 32) strip[i] = 0.0;
-                __syncwarp();
-                unsigned long long npq = 0ull;
-                for (int j = j0; j < j1; ++j) {
-                    const SPRec sp = spss[P.sp_beg[tb] - P.sp_beg[0] + j];
-                    if (lane < neb) hrow[(j - j0) * neb + lane] = sp.eoff + lane;
-                    if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
-                    const PrimPair* bpp = bpps + (sp.pp_beg - P.pp_beg[0]);
-                    double* srow = strip + (j - j0) * neb * ld;
-                    for (int base = 0; base < nket; base += 32) {
-                        // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
-                        if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
-                        switch (cls) {
-#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_strip<TB, TK>(A, sp, bpp, kpp, base, nket, lane, eoff_tk, srow, ld, npq); break;
-                            VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
-                            VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
-                            VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
+            if (u >= nunits) break;
+            int c = 0;
+            while (s_cum[c + 1] <= u) ++c;
+            const int tb = c / NT, tk = c - tb * NT;
+            const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
+            const int cls = tb * NPTYPE + tk;
+            const SPRec sp = spss[P.sp_beg[tb] - P.sp_beg[0] + (u - s_cum[c])];
+            if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
+            const PrimPair* bpp = bpps + (sp.pp_beg - P.pp_beg[0]);
+            const PrimPair* kpp = kpps + (Q.pp_beg[tk] - Q.pp_beg[0]);
+            double H[HM];
+#pragma unroll
+            for (int e = 0; e < HM; ++e) H[e] = 0.0;
+            unsigned long long npq = 0ull;
+            for (int base = 0; base < nket; base += 32) {
+                // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
+                if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
+                switch (cls) {
+#define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, npq); break;
+                    VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
+                    VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
+                    VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
 #undef VB_CASE
-                            default: break;
-                        }
-                        __syncwarp();
-                    }
+                    default:
+                        if constexpr (GEN) batch_generic(A, tb, tk, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, scratch, npq);
+                        break;
                 }
-                npq = __shfl_sync(0xffffffffu, npq, 0);
-                if (npq == 0ull) continue;
-                if (lane == 0) atomicAdd(&s_pq[cls], npq);
-                __syncwarp();
-                const int nrows = (j1 - j0) * neb;
-                if (nrows <= 8) strip_transform<1>(strip, ld, nrows, Dq + eoff_tk * Q.np, Q.np, ks, hrow, Hs, A.hs_ld, lane);
-                else strip_transform<2>(strip, ld, nrows, Dq + eoff_tk * Q.np, Q.np, ks, hrow, Hs, A.hs_ld, lane);
             }
-        } else {
-            if (tid == 0) {
-                int n = 0;
-                for (int tb = 0; tb < NT; ++tb)
-                    for (int tk = 0; tk < NT; ++tk) {
-                        const int nspb = P.sp_beg[tb + 1] - P.sp_beg[tb], nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-                        s_cum[tb * NT + tk] = n;
-                        if (nspb > 0 && nket > 0 && P.kwmax[tb] * Q.kwmax[tk] >= A.tau) n += nspb;
-                    }
-                s_cum[NT * NT] = n;
-                s_unit = 0;
-            }
-            __syncthreads();
-            const int nunits = s_cum[NT * NT];
-            const bool dynamic = A.mode != 0;
-            int ustat = warp;
-            for (;;) {
-                int u;
-                if (dynamic) {
-                    u = 0;
-                    if (lane == 0) u = atomicAdd(&s_unit, 1);
-                    u = __shfl_sync(0xffffffffu, u, 0);
-                } else {
-                    u = ustat;
-                    ustat += nw;
-                }
-                if (u >= nunits) break;
-                int c = 0;
-                while (s_cum[c + 1] <= u) ++c;
-                const int tb = c / NT, tk = c - tb * NT;
-                const int nket = Q.pp_beg[tk + 1] - Q.pp_beg[tk];
-                const int cls = tb * NPTYPE + tk;
-                const SPRec sp = spss[P.sp_beg[tb] - P.sp_beg[0] + (u - s_cum[c])];
-                if (!(sp.wmax * Q.kwmax[tk] >= A.tau)) continue;
-                const PrimPair* bpp = bpps + (sp.pp_beg - P.pp_beg[0]);
-                const PrimPair* kpp = kpps + (Q.pp_beg[tk] - Q.pp_beg[0]);
-                double H[HM];
-    #pragma unroll
-                for (int e = 0; e < HM; ++e) H[e] = 0.0;
-                unsigned long long npq = 0ull;
-                for (int base = 0; base < nket; base += 32) {
-                    // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
-                    if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
-                    switch (cls) {
-    #define VB_CASE(TB, TK) case TB * NPTYPE + TK: batch_unrolled<TB, TK>(A, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, npq); break;
-                        VB_CASE(0, 0) VB_CASE(0, 1) VB_CASE(0, 2)
-                        VB_CASE(1, 0) VB_CASE(1, 1) VB_CASE(1, 2)
-                        VB_CASE(2, 0) VB_CASE(2, 1) VB_CASE(2, 2)
-    #undef VB_CASE
-                        default:
-                            if constexpr (GEN) batch_generic(A, tb, tk, sp, bpp, kpp, Q.np, base, nket, lane, Dq, H, scratch, npq);
-                            break;
-                    }
-                }
-                npq = __shfl_sync(0xffffffffu, npq, 0);
-                if (npq == 0ull) continue;
-                if (lane == 0) atomicAdd(&s_pq[cls], npq);
-                if (lane < Q.np) {
-                    switch (pt_ne(tb)) {
-                        case 1: add_rows<1>(Hs, A.hs_ld, sp.eoff, H, lane); break;
-                        case 3: add_rows<3>(Hs, A.hs_ld, sp.eoff, H, lane); break;
-                        case 9: add_rows<9>(Hs, A.hs_ld, sp.eoff, H, lane); break;
-                        default:
-                            if constexpr (GEN)
-                                for (int e = 0; e < pt_ne(tb); ++e) atomicAdd(&Hs[(sp.eoff + e) * A.hs_ld + lane], H[e]);
-                            break;
-                    }
+            npq = __shfl_sync(0xffffffffu, npq, 0);
+            if (npq == 0ull) continue;
+            if (lane == 0) atomicAdd(&s_pq[cls], npq);
+            if (lane < Q.np) {
+                switch (pt_ne(tb)) {
+                    case 1: add_rows<1>(Hs, A.hs_ld, sp.eoff, H, lane); break;
+                    case 3: add_rows<3>(Hs, A.hs_ld, sp.eoff, H, lane); break;
+                    case 9: add_rows<9>(Hs, A.hs_ld, sp.eoff, H, lane); break;
+                    default:
+                        if constexpr (GEN)
+                            for (int e = 0; e < pt_ne(tb); ++e) atomicAdd(&Hs[(sp.eoff + e) * A.hs_ld + lane], H[e]);
+                        break;
                 }
             }
         }
