@@ -1315,7 +1315,6 @@ long long vo_baseline_timed(vo_ctx *c, int irank, int nrank, double seconds, dou
     memset(&c->cnt, 0, sizeof c->cnt);
     int nnd = 2 * c->npair + c->nunpd, nso = nnd + c->ndocc;
     default_lists(c, nnd);
-    wfndet(c);
     double t0 = mono_now();
     c->deadline = t0 + seconds; c->expired = 0;
     long long before = c->cnt.shell_quartets;
@@ -1337,6 +1336,8 @@ long long vo_baseline_timed(vo_ctx *c, int irank, int nrank, double seconds, dou
         /* the 2e loop needs the whole table: the other ranks' entries are filled here untimed */
         double pause = mono_now();
         c->deadline = 0.0;
+        wfndet(c);   /* only the densities of the 2e loop need it (nelec^2 overlaps: untimed, and skipped when the
+                        sample ends inside schwarz_ints, as it does for the large clusters) */
         int task = 0;
         for (int i = 1; i <= nso; ++i)
             for (int j = 1; j <= i; ++j) {
