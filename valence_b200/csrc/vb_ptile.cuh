@@ -47,9 +47,6 @@ __host__ __device__ constexpr bool pt_class_in_part(int part, int tb, int tk)
 {
     return part == PART_ALL || ((tb < 2 && tk < 2) == (part == PART_LIGHT));
 }
-#ifndef VB_PAIR_MAXM
-#define VB_PAIR_MAXM -1
-#endif
 constexpr int PT_SLD = 33;                      // row stride of the per-warp X scratch (8 x 32 doubles)
 constexpr int PT_SCRATCH = 8 * PT_SLD + 1;      // doubles per warp (odd row stride, even total keeps the next region aligned)
 
@@ -139,28 +136,17 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
 #pragma unroll
             for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
             int ip = 0;
-            constexpr bool PAIRED = pt_E(TB) + pt_E(TK) <= VB_PAIR_MAXM;   // light classes: two primitives per trip (ILP)
-            for (;;) {
+            // (processing two primitives per trip for more instruction-level parallelism was measured 20-35 % slower:
+            //  the kernel is bound by instruction supply -- 9 unrolled class bodies, 12 warps in different ones -- not
+            //  by dependency latency)
+            for (;; ++ip) {
                 // primitives of a shell pair are sorted by magnitude: a lane that stops stays stopped
                 PrimPair a = bl[ip < cnt ? ip : 0];
                 const bool act = ip < cnt && a.w * wk >= A.tau;
                 if (!__any_sync(0xffffffffu, act)) break;
                 if (!act) a.Kp = 0.0;
-                if constexpr (PAIRED) {
-                    PrimPair a2 = bl[ip + 1 < cnt ? ip + 1 : 0];
-                    const bool act2 = ip + 1 < cnt && a2.w * wk >= A.tau;
-                    if (__any_sync(0xffffffffu, act2)) {
-                        if (!act2) a2.Kp = 0.0;
-                        quartet_values<TB, TK>(boys_tab, a, b, acc);
-                        quartet_values<TB, TK>(boys_tab, a2, b, acc);
-                        nq += ((act && kact) ? 1u : 0u) + ((act2 && kact) ? 1u : 0u);
-                        ip += 2;
-                        continue;
-                    }
-                }
                 quartet_values<TB, TK>(boys_tab, a, b, acc);
                 nq += (act && kact) ? 1u : 0u;
-                ++ip;
             }
             if (ip > 0) feed_dmma<TB, TK>(acc, sp.eoff, Dp_s, P.np, g, X);
         }
