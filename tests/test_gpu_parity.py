@@ -334,3 +334,29 @@ def test_c3h8_orbital_optimisation_sweep_is_variational(write_input):
     # the shipped orbitals are already optimised: the sweep lowers the energy by ~2e-8 Eh (never raises it)
     assert r["total_energy"] <= r["guess_energy"] + 1e-10
     assert r["total_energy"] > r["guess_energy"] - 1e-4
+
+
+def test_lif_cluster_matches_oracle_and_full_lif128_runs(write_input):
+    """BASELINE config 4 (reconstructed examples/lif128, inputs.lif_cluster): a 2x2x2 piece of the lattice against
+    the oracle (exact determinants: dtol 1e-20), the same piece with the file's own loose tolerances (9 9 8: the
+    reference's Givens skip moves its energy by 2e-6), and the full 128-atom / 384-orbital
+    cluster through the engine: reproducible, extensive within the lattice's interaction energy."""
+    from valence_b200 import api, inputs
+    path, _ = write_input(inputs.lif_cluster(2, 2, 2, tol=(9, 20, 8)), "lif8.inp")
+    r, ro = gpu_and_oracle(path)
+    assert abs(r["energy"] - ro["energy"]) < 1e-10
+    for k in EXACT + VALUE:
+        assert r["counters"][k] == ro["counters"][k], k
+    path, _ = write_input(inputs.lif_cluster(2, 2, 2), "lif8_loose.inp")
+    rl, rol = gpu_and_oracle(path)
+    assert abs(rl["energy"] - rol["energy"]) < 1e-5
+    assert rl["counters"]["shell_quartets_2e"] == rol["counters"]["shell_quartets_2e"]
+    path, _ = write_input(inputs.lif_cluster(), "lif128.inp")
+    eng = api.Engine(path)
+    a = eng.energy()
+    b = eng.energy()
+    eng.close()
+    assert a["counters"] == b["counters"] and abs(a["energy"] - b["energy"]) < 1e-9
+    assert 0.0 < a["wfnorm"] <= 1.0
+    per_pair = a["energy"] / 64.0            # 64 LiF units
+    assert -108.0 < per_pair < -105.0        # 8 units: -427.96 Eh = -107.0 per unit

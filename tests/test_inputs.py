@@ -54,3 +54,25 @@ def test_water_cluster_generator(n):
     assert again.to_json() == inp.to_json()
     sc = inputs.water_cluster(n, sc_molecules=1)
     assert sc.npair == 2 and sc.ndocc == 5 * n - 2 and sc.nelec == 10 * n
+
+
+def test_lif128_reconstruction_matches_the_surviving_part_of_the_reference_file():
+    """BASELINE config 4: examples/lif128 is truncated in the reference; lif_cluster() rebuilds it.  Header counts
+    (lif128:1, except the primitive count: 30 for 6-31+G / 6-31G vs the 44 the header claims),
+    tolerances, and a few of the 114 surviving geometry lines / orbital records (lif128:5-118, 128-137)."""
+    from valence_b200 import inputs
+    inp = inputs.lif_cluster()
+    assert (inp.natom, inp.natom_t, inp.npair, inp.nunpd, inp.ndocc, inp.totlen, inp.xpmax, inp.num_sh, inp.nang, inp.mxctr) == \
+           (128, 2, 0, 0, 384, 896, 3, 12, 1, 1)
+    assert (inp.ntol_c, inp.ntol_d, inp.ntol_i) == (9, 9, 8)
+    # lif128:5-8 and :116-118 (type, x, y, z)
+    for k, (t, xyz) in {0: (1, (0.0, 0.0, 0.0)), 1: (2, (0.0, 0.0, 2.015)), 2: (1, (0.0, 0.0, 4.03)), 3: (2, (0.0, 0.0, 6.045)),
+                        111: (2, (6.045, 2.015, 14.105)), 112: (2, (6.045, 4.03, 0.0)), 113: (1, (6.045, 4.03, 2.015))}.items():
+        assert inp.atom_t[k] == t and all(abs(a - b) < 1e-9 for a, b in zip(inp.coords[k], xyz))
+    # atom 16 is F: five one-centre orbitals with the surviving weights; atom 15 is Li: one core orbital
+    o16 = [o for o in inp.orbitals if o.atoms == [16]]
+    assert len(o16) == 5 and o16[1].terms == [(2, 0.49077911), (3, 0.55470885), (10, 0.05607011)]
+    assert [o.terms for o in inp.orbitals if o.atoms == [15]] == [[(1, 1.0)]]
+    # round trip through the writer / parser
+    again = inputs.parse(inputs.write(inp))
+    assert again.ndocc == 384 and again.coords[113] == inp.coords[113]

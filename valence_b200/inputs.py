@@ -370,6 +370,62 @@ def water_cluster(n: int, spacing: float = 3.10, tol: Tuple[int, int, int] = (10
     return inp.fix_counts()
 
 
+# LiF rock-salt cluster: the reference's examples/lif128 is truncated
+# (114 of 128 geometry lines survive), so it is reconstructed: 4x4x8 lattice, spacing 2.015 Angstrom, x outer /
+# z inner, F where ix+iy+iz is even else Li (matches every surviving line, /root/reference/examples/lif128:5-118);
+# F basis 6-31+G (numeric content of examples/f-:8-31), Li basis 6-31G (examples/lih.VSHF:8-27); per F five DOCC
+# orbitals with the surviving weights (examples/lif128:128-137), per Li one 1s core; tolerances 9 9 8 (lif128:2).
+_F_631PG = AtomType(9.0, [
+    Shell(0, [7001.71309, 1051.36609, 239.28569, 67.3974453, 21.5199573, 7.4031013],
+          [0.0018196169, 0.0139160796, 0.0684053245, 0.23318576, 0.471267439, 0.356618546]),
+    Shell(0, [20.8479528, 4.80830834, 1.34406986], [-0.108506975, -0.146451658, 1.12868858]),
+    Shell(0, [0.358151393], [1.0]),
+    Shell(1, [20.8479528, 4.80830834, 1.34406986], [0.0716287243, 0.345912103, 0.722469957]),
+    Shell(1, [0.358151393], [1.0]),
+    Shell(0, [0.1076], [1.0]),
+    Shell(1, [0.1076], [1.0]),
+])
+_LI_631G = AtomType(3.0, [
+    Shell(0, [642.41892, 96.798515, 22.091121, 6.2010703, 1.9351177, 0.6367358],
+          [0.0021426, 0.0162089, 0.0773156, 0.245786, 0.470189, 0.3454708]),
+    Shell(0, [2.3249184, 0.6324306, 0.0790534], [-0.0350917, -0.1912328, 1.0839878]),
+    Shell(0, [0.035962], [1.0]),
+    Shell(1, [2.3249184, 0.6324306, 0.0790534], [0.0089415, 0.1410095, 0.9453637]),
+    Shell(1, [0.035962], [1.0]),
+])
+_F_ORBS = [
+    [(1, 1.0)],
+    [(2, 0.49077911), (3, 0.55470885), (10, 0.05607011)],
+    [(4, 0.62842494), (7, 0.44739668), (11, 0.15779489)],
+    [(5, 0.62855015), (8, 0.44737824), (12, 0.15760430)],
+    [(6, 0.62862278), (9, 0.44736537), (13, 0.15749744)],
+]
+
+
+def lif_cluster(nx: int = 4, ny: int = 4, nz: int = 8, spacing: float = 2.015,
+                tol: Tuple[int, int, int] = (9, 9, 8)) -> ValenceInput:
+    """Rock-salt LiF cluster; lif_cluster() is the reconstructed examples/lif128 (128 atoms, 384 DOCC orbitals,
+    one-atom orbital basis sets).  Atom order and orbital order follow the surviving part of the file: atoms x
+    outer / z inner, orbitals atom by atom."""
+    atom_t, coords, docc = [], [], []
+    for ix in range(nx):
+        for iy in range(ny):
+            for iz in range(nz):
+                is_f = (ix + iy + iz) % 2 == 0
+                atom_t.append(1 if is_f else 2)
+                coords.append([ix * spacing, iy * spacing, iz * spacing])
+                a = len(atom_t)
+                if is_f:
+                    for terms in _F_ORBS:
+                        docc.append(Orbital([a], list(terms)))
+                else:
+                    docc.append(Orbital([a], [(1, 1.0)]))
+    inp = ValenceInput(0, 0, 0, 0, len(docc), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                       tol[0], tol[1], tol[2], 0, 0, 0, 0.0, 0.0, [], atom_t, coords,
+                       [copy.deepcopy(_F_631PG), copy.deepcopy(_LI_631G)], [1.0], [], [], docc)
+    return inp.fix_counts()
+
+
 def dump_json(inp: ValenceInput, path: str, **extra) -> None:
     with open(path, "w") as fh:
         json.dump({"input": inp.to_json(), **extra}, fh, indent=0, separators=(",", ":"))
