@@ -86,6 +86,12 @@ int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out);
  * norbas x norbas column-major matrices <Psi[chi_ib]|H_el|Psi[chi_jb]>, <Psi[chi_ib]|Psi[chi_jb]>
  * (numerators: not divided by the norm, no nuclear repulsion); cap = doubles available in each. */
 int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int cap, int* norbas, vb_energy_result* stats);
+/* sharded form (one process per GPU): the two-electron part of ham is this rank's share of the tiles (the
+ * one-electron part is added on rank 0 only); the caller sums ham over the ranks -- one all-reduce of
+ * norbas^2 doubles, the counterpart of xm_equalize(ham) in first_order_opt (valence.F90:755-764); ovl is
+ * complete on every rank. */
+int vb_engine_first_order_sharded(vb_engine* e, int iorb, int rank, int nranks, double* ham, double* ovl, int cap, int* norbas,
+                                  vb_energy_result* stats);
 /* calculate_vsvb_energy (valence.F90:28-302): guess energy and, if the input asks for it, the
  * first-order orbital optimisation + spin-coupling optimisation of minimize_energy (:2744-2885) */
 int vb_engine_run(vb_engine* e, int print, double* enucrep, double* guess_energy, double* total_energy, int* converged, int* iterations);

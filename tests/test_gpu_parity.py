@@ -273,6 +273,93 @@ def test_first_order_matrices_match_oracle(name, iorb, write_input):
     assert np.allclose(Hg, Hg.T, atol=0) and np.allclose(Sg, Sg.T, atol=0)
 
 
+def _first_order(path, iorb, env=None, sharded=None):
+    """first_order through the C-ABI with temporary environment switches (read per call by the library)."""
+    import os
+    from valence_b200 import api
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        eng = api.Engine(path)
+        if sharded is None:
+            out = eng.first_order(iorb)
+        else:
+            # one process plays every rank in turn: the partial ham matrices must add up to the whole
+            import ctypes as C
+            hs, ss, st = [], [], []
+            for r in range(sharded):
+                cap = 64 * 64
+                ham = np.zeros(cap); ovl = np.zeros(cap); n = C.c_int(0); res = api.CEnergyResult()
+                eng._check(eng.L.vb_engine_first_order_sharded(eng.h, iorb, r, sharded, ham.ctypes.data, ovl.ctypes.data, cap,
+                                                               C.byref(n), C.byref(res)))
+                k = n.value
+                hs.append(ham[:k * k].reshape(k, k).T.copy()); ss.append(ovl[:k * k].reshape(k, k).T.copy()); st.append(res.asdict())
+            out = (sum(hs), ss[0], st)
+        eng.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return out
+
+
+FO_CACHE_CASES = [("examples__h2o", 4), ("examples__ch4", 2), ("examples__h2o.SC", 3), ("examples__be.DBF", 2), ("water3rot", 6),
+                  ("water4", 1), ("water2sc", 3)]
+
+
+def _fo_case(name, write_input):
+    from valence_b200 import inputs
+    if name == "water3rot":
+        return write_input(inputs.water_cluster(3, tol=(10, 20, 10), rotate=True))[0]
+    if name == "water4":
+        return write_input(inputs.water_cluster(4, tol=(10, 20, 10)))[0]
+    if name == "water2sc":
+        return write_input(inputs.water_cluster(2, tol=(10, 20, 10), sc_molecules=1))[0]
+    return write_input(name)[0]
+
+
+@pytest.mark.parametrize("name,iorb", FO_CACHE_CASES)
+def test_first_order_integral_cache_matches_plain_loop(name, iorb, write_input):
+    """first_order_opt with the HBM integral cache (subject-free tiles generated once, contraction-only pass per
+    (ib,jb): the counterpart of the reference's eribuf, valence.F90:1227-1273) against the plain loop that
+    regenerates every integral: same matrices, and bit-identical task counters."""
+    path = _fo_case(name, write_input)
+    Hc, Sc, stc = _first_order(path, iorb)
+    Hp, Sp, stp = _first_order(path, iorb, env={"VB_FO_CACHE": "0"})
+    scale = max(1.0, np.abs(Hp).max())
+    assert np.abs(Hc - Hp).max() < 1e-11 * scale
+    assert np.abs(Sc - Sp).max() < 1e-13 * max(1.0, np.abs(Sp).max())
+    for k in EXACT:
+        assert stc["counters"][k] == stp["counters"][k], k
+    assert stc["n_prim_quartets"] < stp["n_prim_quartets"]     # the cache did save integral work
+
+
+@pytest.mark.parametrize("name,iorb", [("water3rot", 2), ("water4", 7), ("examples__c3h8", 5)])
+def test_first_order_large_determinant_path_matches_oracle(name, iorb, write_input):
+    """Substituted (non-symmetric) lists through the GPU inverse form (the path large clusters take; forced here
+    with VB_FAST_MIN_N) against the oracle's first_order_opt."""
+    from oracle.oracle import Oracle
+    path = _fo_case(name, write_input)
+    o = Oracle(path)
+    Ho, So, _ = o.first_order(iorb)
+    o.close()
+    Hg, Sg, _ = _first_order(path, iorb, env={"VB_FAST_MIN_N": "2"})
+    assert np.abs(Hg - Ho).max() < 1e-8
+    assert np.abs(Sg - So).max() < 1e-8
+
+
+def test_first_order_sharded_partials_add_up(write_input):
+    """Two ranks' shares of ham (tiles block-cyclic over the ranks, one-electron part on rank 0) sum to the
+    single-rank matrices; ovl is complete on every rank."""
+    path = _fo_case("water4", write_input)
+    H1, S1, _ = _first_order(path, 3)
+    H2, S2, _ = _first_order(path, 3, sharded=2)
+    assert np.abs(H1 - H2).max() < 1e-11 * max(1.0, np.abs(H1).max())
+    assert np.abs(S1 - S2).max() < 1e-13
+
+
 OPT_CASES = ["examples__li_opt", "testing__be", "testing__he", "testing__h2-dz", "testing__h2-sz", "testing__be+ndf",
              "testing__he1s2s", "testing__he3s-1s3s", "testing__be3s2", "testing__h2o-vdz", "testing__lih-sv",
              "testing__be-sc", "testing__be-scv3s+2sc", "testing__h2o-vdz-sc1"]

@@ -75,6 +75,8 @@ def load(build_if_needed: bool = True):
     L.vb_engine_stream.restype = C.c_void_p
     L.vb_engine_stream.argtypes = [C.c_void_p]
     L.vb_engine_first_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(CEnergyResult)]
+    L.vb_engine_first_order_sharded.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                                C.POINTER(CEnergyResult)]
     L.vb_engine_run.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int)] * 2
     L.vb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
@@ -142,6 +144,25 @@ class Engine:
         r = CEnergyResult()
         self._check(self.L.vb_engine_first_order(self.h, iorb, ham.ctypes.data, ovl.ctypes.data, cap, C.byref(n), C.byref(r)))
         k = n.value
+        return ham[:k * k].reshape(k, k).T.copy(), ovl[:k * k].reshape(k, k).T.copy(), r.asdict()
+
+    def first_order_distributed(self, iorb: int, rank: int, nranks: int):
+        """first_order_opt matrices with the tiles sharded over the ranks and ONE all-reduce of ham
+        (the reference equalizes ham the same way, valence.F90:755-764)."""
+        cap = 64 * 64
+        ham = np.zeros(cap)
+        ovl = np.zeros(cap)
+        n = C.c_int(0)
+        r = CEnergyResult()
+        self._check(self.L.vb_engine_first_order_sharded(self.h, iorb, rank, nranks, ham.ctypes.data, ovl.ctypes.data, cap, C.byref(n),
+                                                         C.byref(r)))
+        k = n.value
+        if nranks > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(ham[:k * k].copy()).to(f"cuda:{self.device}")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ham[:k * k] = t.cpu().numpy()
         return ham[:k * k].reshape(k, k).T.copy(), ovl[:k * k].reshape(k, k).T.copy(), r.asdict()
 
     def run(self, print_output: bool = False) -> dict:

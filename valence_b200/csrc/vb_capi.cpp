@@ -165,6 +165,22 @@ int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int 
     });
 }
 
+int vb_engine_first_order_sharded(vb_engine* e, int iorb, int rank, int nranks, double* ham, double* ovl, int cap, int* norbas,
+                                  vb_energy_result* stats)
+{
+    return guarded([&] {
+        if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("first_order: bad rank / nranks");
+        std::vector<double> h, s;
+        vb::EnergyResult r;
+        int n = e->eng->first_order(iorb - 1, &h, &s, &r, rank, nranks);
+        *norbas = n;
+        if (n * n > cap) throw std::runtime_error("first_order: output buffers too small");
+        std::copy(h.begin(), h.end(), ham);
+        std::copy(s.begin(), s.end(), ovl);
+        if (stats) to_c(r, stats);
+    });
+}
+
 int vb_engine_run(vb_engine* e, int print, double* enucrep, double* guess_energy, double* total_energy, int* converged, int* iterations)
 {
     return guarded([&] {

@@ -52,6 +52,12 @@ struct DBuf {
         if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
         g_h2d_bytes += (long long)(v.size() * sizeof(T));
     }
+    void upload_at(size_t off, const std::vector<T>& v, cudaStream_t st)   // into an allocation made with alloc()
+    {
+        if (off + v.size() > cap) throw std::runtime_error("valence_b200: device table overflow");
+        if (!v.empty()) CK(cudaMemcpyAsync(p + off, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        g_h2d_bytes += (long long)(v.size() * sizeof(T));
+    }
     void zero(cudaStream_t st) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
     void download(std::vector<T>& v, cudaStream_t st)
     {
@@ -122,6 +128,12 @@ struct Engine::Impl {
     void prepare(const Input& in, int subject);
     void evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only, int rank, int nranks,
                   EnergyResult* out, std::vector<double>* sch_out);
+    bool first_order_cached(const Input& in, const Wavefunction& wf, int es, int iorb, const std::vector<double>& sch, int rank, int nranks,
+                            std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* acc);
+    DBuf<double> gcache;                             // first_order_opt: orbital-level integrals of the subject-free tiles
+    DBuf<int4> vtiles;
+    DBuf<int> fo_perm;
+    void cofactor_stage(const Input& in, const Wavefunction& wf, bool diag_only, EnergyResult* out, bool* fast_out, double* c0_out, int* ndp_out);
     int only_isc = -1, only_jsc = -1;                 // spin_opt: restrict the cofactors to one coupling pair
     std::vector<double> coeff_sc;                    // current spin-coupling weights
     double enuc = 0, e1 = 0, wfnorm = 0;
@@ -305,11 +317,12 @@ void Engine::Impl::prepare(const Input& in, int subject)
 //   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
 //             valence.F90:667 vs 674-704); null -> run the diagonal pass (schwarz_ints)
 //   diag_only: stop after the Schwarz table (returned in sch_out)
-void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only,
-                            int rank, int nranks, EnergyResult* out, std::vector<double>* sch_out)
+// Entry-level overlap / core-Hamiltonian matrices and the cofactor densities of one bra/ket list pair
+// (wfndet, the 1e loop and the density set-up of vsvb_energy): leaves Se, He, Pa/Pb or cof on the device,
+// e1 and wfnorm in the object.
+void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool diag_only, EnergyResult* out, bool* fast_out, double* c0_out, int* ndp_out)
 {
     const int nso = wf.nso, nelec = in.nelec(), nao = bas.nao;
-    double t1 = now_ms();
     // ---- entry-level overlap and core-Hamiltonian matrices (wfndet :1440-1480, 1e loop :1072) ----
     {
         std::vector<int2> prs((size_t)nso * nso);
@@ -323,22 +336,34 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     }
     // ---- cofactor densities ------------------------------------------------------------------------
     const int na = in.nalpha(), nb = in.nbeta();
-    const bool fast = in.npair == 0 && wf.sym && std::max(na, nb) > 64;   // large closed/open-shell single determinant
+    // large single determinant (closed/open shell, also the substituted lists of first_order_opt): inverse form on the GPU
+    int fast_min = 64;
+    if (const char* e = std::getenv("VB_FAST_MIN_N")) fast_min = std::atoi(e);
+    bool fast = in.npair == 0 && std::max(na, nb) > fast_min;
     double c0 = 1.0;
     int ndp = 0;
     if (!diag_only) {
+        bool singular = false, same = false;
         if (fast) {
-            // alpha block: unpaired entries then DOCC entries; beta block: DOCC entries (valence.F90:2461-2480)
+            // spin of an electron slot is its position in the list (set_up_unpaired_docc, valence.F90:2461-2480):
+            // unpaired slots and the first slot of every DOCC pair are alpha, the second slots beta
+            std::vector<int> entry_of_slot(wf.bra.size());
+            for (int s = 0; s < nso; ++s)
+                for (int k = 0; k < wf.nslots(s); ++k) entry_of_slot[wf.slot(s, k)] = s;
             std::vector<int> ea, eb, posa(nso, -1), posb(nso, -1);
-            for (int s = 0; s < nso; ++s) { posa[s] = (int)ea.size(); ea.push_back(s); }
-            for (int s = wf.nnd; s < nso; ++s) { posb[s] = (int)eb.size(); eb.push_back(s); }
+            for (int i = 0; i < in.nunpd; ++i) { const int s = entry_of_slot[i]; posa[s] = (int)ea.size(); ea.push_back(s); }
+            for (int d = 0; d < in.ndocc; ++d) {
+                const int sa = entry_of_slot[in.nunpd + 2 * d], sb = entry_of_slot[in.nunpd + 2 * d + 1];
+                posa[sa] = (int)ea.size(); ea.push_back(sa);
+                posb[sb] = (int)eb.size(); eb.push_back(sb);
+            }
             ea_bra.upload(ea, st); eb_bra.upload(eb, st); posa_bra.upload(posa, st); posb_bra.upload(posb, st);
             Ma.alloc((size_t)na * na + 1); Mb.alloc((size_t)nb * nb + 1);
-            if (na) { k_gather_block<<<(na * na + 255) / 256, 256, 0, st>>>(Se.p, nso, ea_bra.p, ea_bra.p, na, Ma.p); launches++; }
-            if (nb && !(wf.nnd == 0 && na == nb)) { k_gather_block<<<(nb * nb + 255) / 256, 256, 0, st>>>(Se.p, nso, eb_bra.p, eb_bra.p, nb, Mb.p); launches++; }
-            CK(cudaGetLastError());
             // one inverse when both spin blocks hold the same entries (closed shell)
-            const bool same = wf.nnd == 0 && na == nb;
+            same = ea == eb;
+            if (na) { k_gather_block<<<(na * na + 255) / 256, 256, 0, st>>>(Se.p, nso, ea_bra.p, ea_bra.p, na, Ma.p); launches++; }
+            if (nb && !same) { k_gather_block<<<(nb * nb + 255) / 256, 256, 0, st>>>(Se.p, nso, eb_bra.p, eb_bra.p, nb, Mb.p); launches++; }
+            CK(cudaGetLastError());
             gjout.alloc(4);
             auto invert = [&](DBuf<double>& M, DBuf<double>& Minv, int n, double* res) {
                 Minv.alloc((size_t)n * n + 1);
@@ -356,9 +381,17 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             std::vector<double> g;
             gjout.download(g, st);
             out->min_pivot_ratio = std::min(g[1], g[3]);
-            if (!(g[0] != 0.0) || !(g[2] != 0.0) || out->min_pivot_ratio < 1e-13)
-                throw std::runtime_error("valence_b200: singular spin-block overlap matrix (linearly dependent orbitals)");
+            if (!(g[0] != 0.0) || !(g[2] != 0.0) || out->min_pivot_ratio < 1e-13) {
+                // symmetric lists: linearly dependent orbitals.  Substituted lists (first_order_opt) can be singular
+                // legitimately (a basis function orthogonal to the space it replaces): exact null-space treatment on
+                // the host while that is affordable
+                if (wf.sym || std::max(na, nb) > 320)
+                    throw std::runtime_error("valence_b200: singular spin-block overlap matrix (linearly dependent orbitals)");
+                singular = true;
+            }
             c0 = g[0] * g[2];
+        }
+        if (fast && !singular) {
             Pa.alloc((size_t)nso * nso); Pb.alloc((size_t)nso * nso);
             k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mai.p, na, posa_bra.p, posa_bra.p, nso, Pa.p);
             k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(same ? Mai.p : Mbi.p, nb, posb_bra.p, posb_bra.p, nso, Pb.p);
@@ -371,6 +404,8 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             e1 = c0 * oe[0];
             wfnorm = c0 * oe[1] / (double)nelec;    // valence.F90:1106
         } else {
+            fast = false;
+            c0 = 1.0;
             // small blocks / several determinant pairs / possibly singular blocks: factorise on the host
             // (O(n^3) once per determinant pair, n <= 64), contract on the GPU
             std::vector<double> hSe, hHe;
@@ -385,6 +420,19 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             ndp = cs.ndp;
         }
     }
+    *fast_out = fast; *c0_out = c0; *ndp_out = ndp;
+}
+
+void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only,
+                            int rank, int nranks, EnergyResult* out, std::vector<double>* sch_out)
+{
+    const int nso = wf.nso, nao = bas.nao;
+    (void)nao;
+    double t1 = now_ms();
+    bool fast = false;
+    double c0 = 1.0;
+    int ndp = 0;
+    cofactor_stage(in, wf, diag_only, out, &fast, &c0, &ndp);
     double t2 = now_ms();
 
     // ---- pair groups, shell-pair tables, folded densities ---------------------------------------------
@@ -655,10 +703,405 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
     I.evaluate(in_, wf, nullptr, false, rank, nranks, out, nullptr);
 }
 
+namespace {
+
+struct PtCfg { int dq_cap2, g_cap, pp_cap, sp_cap, boys_cap, hs_cap, hs_ld; size_t smem; };
+
+// shared-memory layout of k_ptile for the given table maxima (same rules as the energy pass)
+PtCfg pt_cfg(int max_ne, int max_np, int max_nsp, int max_npp)
+{
+    PtCfg c;
+    const int dq_cap = std::max(1, max_ne * max_np);
+    c.hs_ld = std::max(1, max_np) | 1;
+    c.dq_cap2 = (dq_cap + 1) & ~1;
+    c.hs_cap = (max_ne * c.hs_ld + 1) & ~1;
+    c.sp_cap = std::max(1, max_nsp);
+    c.g_cap = (max_np * max_np + 1) & ~1;
+    c.pp_cap = std::max(1, max_npp);
+    c.boys_cap = 0;
+    constexpr int nw = PT_MAX_WARPS;
+    c.smem = ((size_t)c.dq_cap2 + (size_t)PT_MAXQ * c.g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double) + (size_t)c.sp_cap * sizeof(SPRec);
+    if (c.smem + (size_t)c.pp_cap * sizeof(PrimPair) <= 225 * 1024) c.smem += (size_t)c.pp_cap * sizeof(PrimPair);
+    else c.pp_cap = 0;
+    if (c.smem + BOYS_S_SIZE * sizeof(double) <= 225 * 1024) { c.boys_cap = BOYS_S_SIZE; c.smem += BOYS_S_SIZE * sizeof(double); }
+    return c;
+}
+
+// Tiles (a, b), a in avec, b in bvec (both ascending pair-group indices), b <= a, smax_a * smax_b > itol; ordered in
+// blocks of bra pair groups against chunks of ket pair groups (L2 residency), partners by decreasing Schwarz bound.
+// runs: (first tile, # tiles) of every non-empty (a, chunk).
+void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec, const std::vector<int>& bvec, double itol,
+                    std::vector<int2>* tl, std::vector<std::pair<long long, int>>* runs)
+{
+    tl->clear(); runs->clear();
+    const int PB = 128, QC = 1024;
+    const int na = (int)avec.size(), nb = (int)bvec.size();
+    const int nchunks = (nb + QC - 1) / QC;
+    std::vector<int> order(bvec);
+    std::vector<int> cmin(nchunks);
+    for (int c = 0; c < nchunks; ++c) {
+        cmin[c] = bvec[(size_t)c * QC];
+        std::stable_sort(order.begin() + (size_t)c * QC, order.begin() + std::min<size_t>(nb, (size_t)(c + 1) * QC),
+                         [&](int x, int y) { return pgs[x].smax > pgs[y].smax; });
+    }
+    for (int B0 = 0; B0 < na; B0 += PB) {
+        const int B1 = std::min(na, B0 + PB);
+        for (int c = 0; c < nchunks; ++c) {
+            if (cmin[c] > avec[B1 - 1]) break;
+            const int c0 = c * QC, c1 = std::min(nb, c0 + QC);
+            for (int ai = B0; ai < B1; ++ai) {
+                const int a = avec[ai];
+                if (a < cmin[c]) continue;
+                const double sa = pgs[a].smax;
+                const long long start = (long long)tl->size();
+                for (int j = c0; j < c1; ++j) {
+                    const int b = order[j];
+                    if (!(sa * pgs[b].smax > itol)) break;
+                    if (b <= a) tl->push_back(make_int2(a, b));
+                }
+                if ((long long)tl->size() > start) runs->emplace_back(start, (int)((long long)tl->size() - start));
+            }
+        }
+    }
+    if ((long long)tl->size() > 2000000000LL) throw std::runtime_error("valence_b200: tile list too long");
+}
+
+// work items of k_ptile: pieces of <= m tiles of a run, block-cyclic over the ranks; z = slot of the item's first tile
+void make_items(const std::vector<std::pair<long long, int>>& runs, long long ntiles, int nsm, int rank, int nranks,
+                std::vector<int4>* itl, long long* my_tiles)
+{
+    itl->clear();
+    *my_tiles = 0;
+    const long long m = std::max<long long>(1, std::min<long long>(PT_MAXQ, ntiles / ((long long)nsm * nranks * 16)));
+    long long idx = 0;
+    for (const auto& run : runs)
+        for (long long k = run.first; k < run.first + run.second; k += m, ++idx) {
+            if (idx % nranks != rank) continue;
+            const int cnt = (int)std::min<long long>(m, run.first + run.second - k);
+            itl->push_back(make_int4((int)k, cnt, (int)*my_tiles, 0));
+            *my_tiles += cnt;
+        }
+}
+
+}  // namespace
+
+// first_order_opt with an integral cache.  The (ib,jb) loop of first_order_opt (valence.F90:674-764) replaces ONE
+// orbital of the bra and of the ket list; every orbital-level integral that does not involve that entry is the same in
+// all norbas(norbas+1)/2 evaluations -- the reference keeps those in eribuf when store_eri is set
+// (valence.F90:1227-1273).  Here:
+//   * the subject entry forms a pair-group family of its own ("subject" pair groups, rebuilt per (ib,jb)); all other
+//     ("free") pair groups and their tables are built and uploaded once;
+//   * one integral pass (k_ptile, mode 2) leaves G of every canonical free tile in HBM (g_cap doubles per tile; sized
+//     for the 180 GB of a B200: 38 GB for (H2O)_256);
+//   * every (ib,jb) evaluation = cofactors of the substituted lists + integrals of the subject tiles (k_ptile) +
+//     a contraction-only pass over the cached tiles (k_contract), in the reference's non-symmetric task order.
+// Returns false when the cache does not apply (d shells, not enough memory); the caller then runs the plain loop.
+bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, int es, int iorb, const std::vector<double>& sch_tab,
+                                      int rank, int nranks, std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* acc)
+{
+    int bas_lmax = 0;
+    for (const GShell& gs : bas.shells) bas_lmax = std::max(bas_lmax, gs.l);
+    if (bas_lmax >= 2) return false;
+    if (const char* e = std::getenv("VB_FO_CACHE")) if (std::atoi(e) == 0) return false;
+    const int nso = wf.nso, norbs = in.norbs();
+    const int norbas = (int)in.orbitals[iorb].xp.size();
+    const double tau_diag = std::min(tau, 0.01 * itol * itol), tau_energy = std::min(tau, 0.01 * itol);
+    const bool dbg_time = std::getenv("VB_DEBUG_TIME") != nullptr;
+    double tm0 = now_ms();
+    Wavefunction wb = wf;              // unsubstituted lists in the non-symmetric task order
+    wb.sym = false;
+    wb.subject = -1;
+    Wavefunction w2 = wb;
+    w2.subject = es;
+    auto substitute = [&](int ib, int jb) {
+        const int idf = in.orbitals[iorb].xp[ib], jdf = in.orbitals[iorb].xp[jb];
+        w2.bra[es] = idf < 1 ? norbs + idf - 1 : norbs + ib;
+        w2.ket[es] = jdf < 1 ? norbs + jdf - 1 : norbs + jb;
+    };
+    // ---- bound of the primitive weights over every list of the loop (consistent pruning of all tables) ----
+    double wall = 0.0;
+    {
+        TileOpts mo;
+        mo.isolate = es; mo.measure_only = true;
+        TileSetup tmp;
+        build_tiles(in, bas, wb, orbs2e, tau_diag, true, &tmp, mo);
+        wall = tmp.wmax;
+        mo.only_subject = true;
+        for (int ib = 0; ib < norbas; ++ib) {
+            substitute(ib, ib);
+            build_tiles(in, bas, w2, orbs2e, tau_diag, true, &tmp, mo);
+            wall = std::max(wall, tmp.wmax);
+        }
+    }
+    // ---- all tables of the unsubstituted lists; the free part stays resident ---------------------------------
+    TileOpts fo;
+    fo.isolate = es; fo.wcut = wall;
+    TileSetup tsF;
+    build_tiles(in, bas, wb, orbs2e, tau_diag, true, &tsF, fo);
+    const int nfree = tsF.n_free_pg, npgF = (int)tsF.pgs.size();
+    if (nfree == 0) return false;
+    const size_t fPairs = tsF.n_free_pairs, fSps = tsF.n_free_sps, fPps = tsF.n_free_pps, fD = tsF.n_free_d;
+    const size_t sPairs = tsF.pg_pairs.size() / 2 - fPairs, sSps = tsF.sps.size() - fSps, sPps = tsF.pps.size() - fPps, sD = tsF.dmat.size() - fD;
+    if (tsF.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
+    auto set_smax = [&](std::vector<PGDesc>& v, const std::vector<int>& pairs, size_t pair_shift, size_t from) {
+        for (size_t i = from; i < v.size(); ++i) {
+            PGDesc& pg = v[i];
+            double m = 0.0;
+            for (int p = 0; p < pg.np; ++p) {
+                const size_t k = (size_t)pg.pair_beg - pair_shift + p;
+                const double x = sch_tab[(size_t)pairs[2 * k] * nso + pairs[2 * k + 1]];
+                if (x > m) m = x;
+            }
+            pg.smax = m;
+        }
+    };
+    std::vector<PGDesc> hp(tsF.pgs.begin(), tsF.pgs.begin() + nfree);
+    set_smax(hp, tsF.pg_pairs, 0, 0);
+    // device tables with room for the per-evaluation subject part (3x the size of the unsubstituted one)
+    const size_t room = 3;
+    pgs.alloc((size_t)nfree + room * (npgF - nfree) + 64);
+    pg_pairs.alloc(2 * (fPairs + room * sPairs + 64));
+    sps.alloc(fSps + room * sSps + 256);
+    pps.alloc(fPps + room * sPps + 1024);
+    pps_flat.alloc(fPps + room * sPps + 1024);
+    dmat.alloc(fD + room * sD + 4096);
+    {
+        std::vector<int> v(tsF.pg_pairs.begin(), tsF.pg_pairs.begin() + 2 * fPairs);
+        pg_pairs.upload_at(0, v, st);
+        std::vector<SPRec> v2(tsF.sps.begin(), tsF.sps.begin() + fSps);
+        sps.upload_at(0, v2, st);
+        std::vector<PrimPair> v3(tsF.pps.begin(), tsF.pps.begin() + fPps);
+        pps.upload_at(0, v3, st);
+        std::vector<PrimPair> v4(tsF.pps_flat.begin(), tsF.pps_flat.begin() + fPps);
+        pps_flat.upload_at(0, v4, st);
+        std::vector<double> v5(tsF.dmat.begin(), tsF.dmat.begin() + fD);
+        dmat.upload_at(0, v5, st);
+        pgs.upload_at(0, hp, st);
+        CK(cudaStreamSynchronize(st));
+    }
+    // ---- canonical pair groups (g >= h) and the pair permutation of the flipped ones ----------------------------
+    const long long ng = (long long)tsF.groups.size();
+    std::vector<int> idx_of((size_t)(ng * ng), -1);
+    for (int x = 0; x < nfree; ++x) idx_of[(size_t)(hp[x].g * ng + hp[x].h)] = x;
+    std::vector<int> flip(nfree), canon(nfree), perm(fPairs);
+    for (int x = 0; x < nfree; ++x) {
+        const PGDesc& pg = hp[x];
+        flip[x] = idx_of[(size_t)(pg.h * ng + pg.g)];
+        canon[x] = (pg.g < pg.h && flip[x] >= 0) ? flip[x] : x;
+        const PGDesc& cg = hp[canon[x]];
+        for (int p = 0; p < pg.np; ++p) {
+            int found = p;
+            if (canon[x] != x) {
+                const int s_ = tsF.pg_pairs[2 * (pg.pair_beg + p)], t_ = tsF.pg_pairs[2 * (pg.pair_beg + p) + 1];
+                found = -1;
+                for (int q = 0; q < cg.np && found < 0; ++q)
+                    if (tsF.pg_pairs[2 * (cg.pair_beg + q)] == t_ && tsF.pg_pairs[2 * (cg.pair_beg + q) + 1] == s_) found = q;
+                if (found < 0 || cg.np != pg.np) throw std::runtime_error("valence_b200: first_order cache: pair groups do not mirror");
+            }
+            perm[pg.pair_beg + p] = found;
+        }
+    }
+    fo_perm.upload(perm, st);
+    // ---- integral pass over the canonical free tiles -> cache ----------------------------------------------
+    std::vector<int> cand;
+    for (int x = 0; x < nfree; ++x) if (canon[x] == x) cand.push_back(x);
+    std::vector<int2> tlc;
+    std::vector<std::pair<long long, int>> runs;
+    make_tile_list(hp, cand, cand, itol, &tlc, &runs);
+    std::vector<int4> itc;
+    long long my_tiles = 0;
+    make_items(runs, (long long)tlc.size(), nsm, rank, nranks, &itc, &my_tiles);
+    PtCfg cfg = pt_cfg(tsF.max_ne, tsF.max_np, tsF.max_nsp, tsF.max_npp);
+    {
+        size_t fr = 0, tot = 0;
+        CK(cudaMemGetInfo(&fr, &tot));
+        const double need = (double)my_tiles * cfg.g_cap * 8.0;
+        double cap = 0.8 * ((double)fr + (double)gcache.cap * 8.0);
+        if (const char* e = std::getenv("VB_FO_CACHE_MB")) cap = std::min(cap, std::atof(e) * 1048576.0);
+        if (need > cap) return false;
+    }
+    if (cfg.smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+    gcache.alloc((size_t)std::max<long long>(1, my_tiles) * cfg.g_cap);
+    counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
+    gred.alloc((size_t)nsm * PT_MAXQ * cfg.g_cap);
+    CK(cudaFuncSetAttribute(k_ptile<PART_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    TileArgs A;
+    std::memset(&A, 0, sizeof A);
+    auto fill_cfg = [&](const PtCfg& c) {
+        A.dq_cap = c.dq_cap2; A.hs_cap = c.hs_cap; A.hs_ld = c.hs_ld; A.g_cap = c.g_cap; A.boys_cap = c.boys_cap; A.pp_cap = c.pp_cap; A.sp_cap = c.sp_cap;
+    };
+    A.gred = gred.p;
+    A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pps_flat = pps_flat.p; A.dmat = dmat.p;
+    A.pq_counters = pq_counters.p; A.boys = boys.p; A.boys_small = boys_small.p; A.counter = counter.p; A.counters = counters.p;
+    A.nso = nso; A.nnd = wf.nnd; A.sym = 0; A.subject = es; A.itol = itol;
+    A.tile_first = 0; A.tile_stride = 1;
+    fill_cfg(cfg);
+    auto add_pq = [&]() {
+        std::vector<unsigned long long> pq;
+        pq_counters.download(pq, st);
+        for (int a = 0; a < NPTYPE; ++a)
+            for (int b = 0; b < NPTYPE; ++b) {
+                acc->flops_model += (double)pq[a * NPTYPE + b] * flops_prim_quartet(a, b);
+                acc->n_prim_quartets += (long long)pq[a * NPTYPE + b];
+            }
+    };
+    double tm1 = now_ms();
+    if (my_tiles > 0) {
+        tiles.upload(tlc, st); items.upload(itc, st);
+        counter.zero(st); counters.zero(st); pq_counters.zero(st);
+        A.tiles = tiles.p; A.ntiles = (int)tlc.size(); A.items = items.p; A.nitems = (int)itc.size();
+        A.gbuf = gcache.p; A.gslot_base = 0; A.mode = 2; A.tau = tau_energy;
+        CK(cudaEventRecord(ev2, st));
+        k_ptile<PART_ALL><<<std::max(1, std::min(nsm, (int)itc.size())), pt_threads(PART_ALL), cfg.smem, st>>>(A);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev3, st));
+        launches++;
+        acc->tile_launches++;
+        add_pq();
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev2, ev3));
+        acc->t_tiles += ms;
+    }
+    acc->n_tiles += (long long)tlc.size();
+    // ---- variant tiles: every free tile of the non-symmetric task order, mapped onto its canonical tile ---------
+    std::vector<int4> vts;
+    vts.reserve((size_t)my_tiles * 4);
+    for (const int4& it : itc)
+        for (int j = 0; j < it.y; ++j) {
+            const int2 t = tlc[(size_t)it.x + j];
+            const int slot = it.z + j;
+            const int A0 = t.x, B0 = t.y;
+            const int Af = (flip[A0] >= 0 && flip[A0] != A0 && canon[flip[A0]] == A0) ? flip[A0] : -1;
+            const int Bf = (flip[B0] >= 0 && flip[B0] != B0 && canon[flip[B0]] == B0) ? flip[B0] : -1;
+            if (A0 != B0) {
+                const int xs[2] = {A0, Af}, ys[2] = {B0, Bf};
+                for (int i = 0; i < 2; ++i)
+                    for (int k = 0; k < 2; ++k) {
+                        const int x = xs[i], y = ys[k];
+                        if (x < 0 || y < 0) continue;
+                        if (x >= y) vts.push_back(make_int4(x, y, slot, 0));
+                        else vts.push_back(make_int4(y, x, slot, 1));
+                    }
+            } else {
+                vts.push_back(make_int4(A0, A0, slot, 0));
+                if (Af >= 0) {
+                    vts.push_back(make_int4(Af, Af, slot, 0));
+                    vts.push_back(make_int4(std::max(A0, Af), std::min(A0, Af), slot, 0));
+                }
+            }
+        }
+    const long long nvt = (long long)vts.size();
+    vtiles.upload(vts, st);
+    { std::vector<int4>().swap(vts); }
+    this->sch.upload(sch_tab, st);
+    A.sch = this->sch.p;
+    CK(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.g_cap * sizeof(double))));
+    double tm2 = now_ms();
+    if (dbg_time) { CK(cudaStreamSynchronize(st)); std::printf("[fo] tables %.1f ms, cache pass %.1f ms (%lld canonical tiles, %lld mine, %.2f GB), %lld variant tiles\n", tm1 - tm0, tm2 - tm1, (long long)tlc.size(), my_tiles, (double)my_tiles * cfg.g_cap * 8e-9, nvt); }
+    // ---- the (ib,jb) loop -------------------------------------------------------------------------------
+    std::vector<int> avec, bvec;
+    for (int ib = 0; ib < norbas; ++ib)
+        for (int jb = 0; jb <= ib; ++jb) {
+            double tp0 = now_ms();
+            substitute(ib, jb);
+            EnergyResult r;
+            bool fast = false;
+            double c0 = 1.0;
+            int ndp = 0;
+            cofactor_stage(in, w2, false, &r, &fast, &c0, &ndp);
+            double tp1 = now_ms();
+            TileOpts so;
+            so.isolate = es; so.only_subject = true; so.wcut = wall;
+            TileSetup tsS;
+            build_tiles(in, bas, w2, orbs2e, tau_diag, true, &tsS, so);
+            const int nS = (int)tsS.pgs.size();
+            if (tsS.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
+            hp.resize(nfree);
+            for (PGDesc pg : tsS.pgs) {
+                pg.pair_beg += (int)fPairs;
+                pg.d_off += (long long)fD;
+                for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += (int)fPps; pg.sp_beg[t] += (int)fSps; }
+                hp.push_back(pg);
+            }
+            for (SPRec& sr : tsS.sps) sr.pp_beg += (int)fPps;
+            set_smax(hp, tsS.pg_pairs, fPairs, nfree);
+            {
+                std::vector<PGDesc> tail(hp.begin() + nfree, hp.end());
+                pgs.upload_at(nfree, tail, st);
+                pg_pairs.upload_at(2 * fPairs, tsS.pg_pairs, st);
+                sps.upload_at(fSps, tsS.sps, st);
+                pps.upload_at(fPps, tsS.pps, st);
+                pps_flat.upload_at(fPps, tsS.pps_flat, st);
+                dmat.upload_at(fD, tsS.dmat, st);
+            }
+            std::vector<int> nshb(nso), nshk(nso);
+            for (int s = 0; s < nso; ++s) {
+                nshb[s] = (int)orbs2e[w2.bra[w2.slot(s, 0)]].sh.size();
+                nshk[s] = (int)orbs2e[w2.ket[w2.slot(s, 0)]].sh.size();
+            }
+            nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
+            // subject tiles: a subject pair group against everything
+            avec.clear(); bvec.clear();
+            for (int x = nfree; x < nfree + nS; ++x) avec.push_back(x);
+            for (int x = 0; x < nfree + nS; ++x) bvec.push_back(x);
+            std::vector<int2> tls;
+            make_tile_list(hp, avec, bvec, itol, &tls, &runs);
+            std::vector<int4> its;
+            long long mine = 0;
+            make_items(runs, (long long)tls.size(), nsm, rank, nranks, &its, &mine);
+            const PtCfg c2 = pt_cfg(std::max(tsF.max_ne, tsS.max_ne), std::max(tsF.max_np, tsS.max_np), std::max(tsF.max_nsp, tsS.max_nsp),
+                                    std::max(tsF.max_npp, tsS.max_npp));
+            if (c2.smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+            if (c2.g_cap != cfg.g_cap) throw std::runtime_error("valence_b200: first_order cache: tile size changed");
+            CK(cudaFuncSetAttribute(k_ptile<PART_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2.smem));
+            fill_cfg(c2);
+            const long long nts = (long long)tls.size();
+            tiles.upload(tls, st); items.upload(its, st);
+            tileE.alloc((size_t)std::max<long long>(1, nts + nvt));
+            tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
+            A.tiles = tiles.p; A.ntiles = (int)nts; A.items = items.p; A.nitems = (int)its.size();
+            A.gbuf = nullptr; A.gslot_base = 0; A.mode = 1; A.tau = tau_energy;
+            A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
+            A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p; A.tileE = tileE.p;
+            CK(cudaEventRecord(ev2, st));
+            if (mine > 0) {
+                k_ptile<PART_ALL><<<std::max(1, std::min(nsm, (int)its.size())), pt_threads(PART_ALL), c2.smem, st>>>(A);
+                CK(cudaGetLastError());
+                launches++;
+                acc->tile_launches++;
+            }
+            if (nvt > 0) {
+                const int grid = (int)std::min<long long>(nvt, (long long)nsm * 16);
+                k_contract<<<grid, CT_THREADS, cfg.g_cap * sizeof(double), st>>>(A, vtiles.p, nvt, fo_perm.p, gcache.p, nts);
+                CK(cudaGetLastError());
+                launches++;
+            }
+            CK(cudaEventRecord(ev3, st));
+            k_sum<<<1, 1024, 0, st>>>(tileE.p, nts + nvt, accum.p);
+            CK(cudaGetLastError());
+            launches++;
+            double e2 = 0.0;
+            CK(cudaMemcpyAsync(&e2, accum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            std::vector<unsigned long long> c;
+            counters.download(c, st);
+            add_pq();
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev2, ev3));
+            acc->t_tiles += ms;
+            acc->n_tiles += nts + nvt;
+            for (int i = 0; i < CNT_N; ++i) acc->counters[i] += (long long)c[i];
+            (*ham)[(size_t)jb * norbas + ib] += (rank == 0 ? e1 : 0.0) + e2;
+            (*ovl)[(size_t)jb * norbas + ib] += wfnorm;
+            if (dbg_time) std::printf("[fo] ib %d jb %d: cofactors %.1f ms, subject tables+tiles %.1f ms (%lld tiles), kernels %.1f ms\n", ib + 1, jb + 1, tp1 - tp0,
+                                      now_ms() - tp1 - ms, nts, ms);
+        }
+    return true;
+}
+
 // first_order_opt matrices (valence.F90:527-764) for 0-based orbital `iorb`:
 //   ham(ib,jb) = <Psi[slot e <- chi_ib] | H_el | Psi[slot e <- chi_jb]>, ovl likewise (not divided,
 //   no nuclear repulsion); column-major n x n in ham/ovl (n = # expansion terms of the orbital).
-int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* stats)
+int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* stats, int rank, int nranks)
 {
     Impl& I = *impl_;
     CK(cudaSetDevice(I.device));
@@ -699,6 +1142,8 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
         const int es = eslot + pass;              // beta-spin position in the second pass
         w2.sym = false;
         w2.subject = es;                          // slot index == entry index for the non-DOCC part of the list
+        // integrals that do not involve the substituted entry are generated once and kept in HBM
+        if (I.first_order_cached(in, wf, es, iorb, sch, rank, nranks, ham, ovl, &acc)) continue;
         for (int ib = 0; ib < norbas; ++ib) {
             int idf = in.orbitals[iorb].xp[ib];
             w2.bra[es] = idf < 1 ? norbs + idf - 1 : norbs + ib;
@@ -706,11 +1151,11 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
                 int jdf = in.orbitals[iorb].xp[jb];
                 w2.ket[es] = jdf < 1 ? norbs + jdf - 1 : norbs + jb;
                 EnergyResult r;
-                I.evaluate(in, w2, &sch, false, 0, 1, &r, nullptr);
+                I.evaluate(in, w2, &sch, false, rank, nranks, &r, nullptr);
                 std::vector<double> a(1 + CNT_N);
                 CK(cudaMemcpyAsync(a.data(), I.accum.p, a.size() * sizeof(double), cudaMemcpyDeviceToHost, I.st));
                 CK(cudaStreamSynchronize(I.st));
-                const double num = r.e1 + a[0];
+                const double num = (rank == 0 ? r.e1 : 0.0) + a[0];
                 if (std::getenv("VB_DEBUG_FO")) {
                     std::printf("---- end of evaluation ib %d jb %d\n", ib + 1, jb + 1);
                     Wavefunction w3 = w2;

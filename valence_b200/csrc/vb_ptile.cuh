@@ -210,6 +210,83 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
     }
 }
 
+// Contraction of one tile's orbital-level integrals G[q][p] with the cofactor densities, with the reference's
+// screening and task bookkeeping line by line (valence.F90:1153-1433).  Threads of the CTA stride over the
+// tile's entries; returns this thread's share of the tile energy and adds to its counters.
+template <int THREADS>
+__device__ __forceinline__ double contract_tile(const TileArgs& A, const PGDesc& P, const PGDesc& Q, const double* __restrict__ G_s,
+                                                int tid, unsigned long long (&cnt)[CNT_N])
+{
+    const int nso = A.nso;
+    const bool diag_tile = P.pair_beg == Q.pair_beg;
+    double epart = 0.0;
+    for (int idx = tid; idx < P.np * Q.np; idx += THREADS) {
+        const int p = idx / Q.np, q = idx % Q.np;
+        if (diag_tile && q > p) continue;
+        const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
+        const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
+        if (A.mode == 0) {
+            if (diag_tile && p == q) {
+                const double G = G_s[q * P.np + p];
+                A.diag[(size_t)s * nso + t] = G;
+                if (A.sym) A.diag[(size_t)t * nso + s] = G;
+            }
+            continue;
+        }
+        // reference screen on the Schwarz product (valence.F90:1189-1190); screened entries
+        // contribute nothing and are counted nowhere
+        const bool ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
+        if (!ssig) continue;
+        const double G = G_s[q * P.np + p];
+        // images of (s,t,u,v) under the integral's permutational symmetry
+        int im[8][4];
+        int nim = 0;
+        {
+            const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
+            for (int k = 0; k < 2; ++k) {
+                const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
+                im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
+                if (A.sym) {
+                    im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
+                    im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
+                    im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
+                }
+            }
+        }
+        double wsum = 0.0;
+        cnt[CNT_ENTRIES]++;
+        for (int k = 0; k < nim; ++k) {
+            const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
+            bool dup = false;
+            for (int k2 = 0; k2 < k; ++k2)
+                dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
+            if (dup) continue;
+            // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
+            const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
+            const double val = shortcut ? A.sch[a * nso + b] * A.sch[a * nso + b] : G;
+            const bool vsig = fabs(val) > A.itol;
+            // as the direct integral of task io=a, ko=b, jo=c, lo=d
+            bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+            if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
+            // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
+            bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
+            if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
+            if (vd) { cnt[CNT_SCHWARZ_EREP]++; cnt[CNT_VALUE_EREP] += vsig; }
+            if (vx) { cnt[CNT_SCHWARZ_EXCH]++; cnt[CNT_VALUE_EXCH] += vsig; }
+            if (!shortcut) {
+                const int calls = (vd ? 1 : 0) + ((vx && b != d) ? 1 : 0);
+                cnt[CNT_INT2E] += calls;
+                cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
+            }
+            if (shortcut && vd) cnt[CNT_SHORTCUT]++;
+            if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
+            if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
+        }
+        epart += 0.5 * wsum;
+    }
+    return epart;
+}
+
 constexpr int PT_MAXQ = 8;     // ket pair groups processed together against one staged bra pair group
 
 // Persistent kernel.  One work item = a bra pair group P with up to PT_MAXQ ket pair groups (tiles
@@ -349,7 +426,8 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
         __syncthreads();
         if (!priv)
             for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) Gs[i] = __ldcg(&Gg[i]);
-        if (PART == PART_HEAVY) {
+        if (PART == PART_HEAVY || A.mode == 2) {
+            // hand-over of the heavy classes' share / mode 2: the tiles' G go to the integral cache of first_order_opt
             for (int i = tid; i < ntl * A.g_cap; i += PT_THREADS) gbuf[i] = Gs[i];
             continue;
         }
@@ -370,76 +448,8 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
         unsigned long long cnt[CNT_N];
 #pragma unroll
         for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
-        const int nso = A.nso;
         for (int qi = 0; qi < ntl; ++qi) {
-            const PGDesc& Q = s_Q[qi];
-            const double* G_s = Gs + qi * A.g_cap;
-            const bool diag_tile = P.pair_beg == Q.pair_beg;
-            double epart = 0.0;
-            for (int idx = tid; idx < P.np * Q.np; idx += PT_THREADS) {
-                const int p = idx / Q.np, q = idx % Q.np;
-                if (diag_tile && q > p) continue;
-                const int s = A.pg_pairs[2 * (P.pair_beg + p)], t = A.pg_pairs[2 * (P.pair_beg + p) + 1];
-                const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
-                if (A.mode == 0) {
-                    if (diag_tile && p == q) {
-                        const double G = G_s[q * P.np + p];
-                        A.diag[(size_t)s * nso + t] = G;
-                        if (A.sym) A.diag[(size_t)t * nso + s] = G;
-                    }
-                    continue;
-                }
-                // reference screen on the Schwarz product (valence.F90:1189-1190); screened entries
-                // contribute nothing and are counted nowhere
-                const bool ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
-                if (!ssig) continue;
-                const double G = G_s[q * P.np + p];
-                // images of (s,t,u,v) under the integral's permutational symmetry
-                int im[8][4];
-                int nim = 0;
-                {
-                    const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
-                    for (int k = 0; k < 2; ++k) {
-                        const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
-                        im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
-                        if (A.sym) {
-                            im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
-                            im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
-                            im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
-                        }
-                    }
-                }
-                double wsum = 0.0;
-                cnt[CNT_ENTRIES]++;
-                for (int k = 0; k < nim; ++k) {
-                    const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
-                    bool dup = false;
-                    for (int k2 = 0; k2 < k; ++k2)
-                        dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
-                    if (dup) continue;
-                    // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
-                    const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
-                    const double val = shortcut ? A.sch[a * nso + b] * A.sch[a * nso + b] : G;
-                    const bool vsig = fabs(val) > A.itol;
-                    // as the direct integral of task io=a, ko=b, jo=c, lo=d
-                    bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
-                    if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
-                    // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
-                    bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
-                    if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
-                    if (vd) { cnt[CNT_SCHWARZ_EREP]++; cnt[CNT_VALUE_EREP] += vsig; }
-                    if (vx) { cnt[CNT_SCHWARZ_EXCH]++; cnt[CNT_VALUE_EXCH] += vsig; }
-                    if (!shortcut) {
-                        const int calls = (vd ? 1 : 0) + ((vx && b != d) ? 1 : 0);
-                        cnt[CNT_INT2E] += calls;
-                        cnt[CNT_SHELLQ] += (unsigned long long)calls * A.nsh_bra[a] * A.nsh_ket[b] * A.nsh_bra[c] * A.nsh_ket[d];
-                    }
-                    if (shortcut && vd) cnt[CNT_SHORTCUT]++;
-                    if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
-                    if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
-                }
-                epart += 0.5 * wsum;
-            }
+            double epart = contract_tile<PT_THREADS>(A, P, s_Q[qi], Gs + qi * A.g_cap, tid, cnt);
             if (A.mode == 1) {
                 for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
                 if (lane == 0) s_red[warp][qi] = epart;
@@ -465,6 +475,66 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
     __syncthreads();
     if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
     if (tid < NPTYPE * NPTYPE && s_pq[tid]) atomicAdd(&A.pq_counters[tid], s_pq[tid]);
+}
+
+// Contraction-only pass over cached integrals (first_order_opt, valence.F90:527-764: the (ib,jb) loop changes one
+// orbital of the bra and of the ket, so every tile that does not touch that entry keeps its integrals -- the GPU
+// counterpart of the reference's eribuf cache, valence.F90:1227-1273).  One variant tile per CTA iteration:
+//   vts[i] = (pair group a, pair group b, cache slot of the canonical tile, flags);  flags bit 0: the canonical tile
+//   is stored as (canon(b), canon(a));  perm[pair] = index, inside the canonical pair group, of the pair (t,s)
+//   [identity for canonical pair groups].  A.tiles is unused; tile energies go to A.tileE[tile_base + i].
+constexpr int CT_THREADS = 128;
+__global__ void __launch_bounds__(CT_THREADS, 4) k_contract(const TileArgs A, const int4* __restrict__ vts, long long nvt,
+                                                         const int* __restrict__ perm, const double* __restrict__ gcache,
+                                                         long long tile_base)
+{
+    extern __shared__ __align__(16) double G_s[];
+    __shared__ PGDesc s_P, s_Q;
+    __shared__ double s_red[CT_THREADS / 32];
+    __shared__ unsigned long long s_cnt[CNT_N];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < CNT_N) s_cnt[tid] = 0ull;
+    unsigned long long cnt[CNT_N];
+#pragma unroll
+    for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
+    for (long long it = blockIdx.x; it < nvt; it += gridDim.x) {
+        __syncthreads();
+        const int4 vt = vts[it];
+        {
+            constexpr int W = sizeof(PGDesc) / 4;
+            if (warp == 0)
+                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_P)[i] = reinterpret_cast<const int*>(A.pgs + vt.x)[i];
+            if (warp == 1)
+                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_Q)[i] = reinterpret_cast<const int*>(A.pgs + vt.y)[i];
+        }
+        __syncthreads();
+        const int npP = s_P.np, npQ = s_Q.np;
+        const double* __restrict__ src = gcache + (size_t)vt.z * A.g_cap;
+        const bool swp = vt.w & 1;
+        for (int idx = tid; idx < npP * npQ; idx += CT_THREADS) {
+            const int p = idx % npP, q = idx / npP;
+            const int pc = perm[s_P.pair_beg + p], qc = perm[s_Q.pair_beg + q];
+            G_s[q * npP + p] = swp ? src[pc * npQ + qc] : src[qc * npP + pc];
+        }
+        __syncthreads();
+        double epart = contract_tile<CT_THREADS>(A, s_P, s_Q, G_s, tid, cnt);
+        for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
+        if (lane == 0) s_red[warp] = epart;
+        __syncthreads();
+        if (tid == 0) {
+            double e = 0.0;
+            for (int w = 0; w < CT_THREADS / 32; ++w) e += s_red[w];
+            A.tileE[tile_base + it] = e * A.c0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CNT_N; ++i) {
+        unsigned long long c = cnt[i];
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(&s_cnt[i], c);
+    }
+    __syncthreads();
+    if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
 }
 
 }  // namespace vb

@@ -202,7 +202,7 @@ static const OrbShell* find_shell(const ExpOrb& o, int gshell)
 }
 
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs,
-                 double tau, bool flat, TileSetup* out)
+                 double tau, bool flat, TileSetup* out, const TileOpts& opts)
 {
     (void)in;
     TileSetup& ts = *out;
@@ -232,6 +232,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
     };
     std::vector<std::vector<int>> group_atoms;
     for (int s = 0; s < nso; ++s) {
+        if (s == opts.isolate) continue;
         std::vector<int> sh = entry_shells(s);
         std::vector<int> at = atoms_of(sh);
         int placed = -1;
@@ -259,6 +260,16 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             ts.groups.push_back(G);
             group_atoms.push_back(at);
         }
+    }
+    int g_iso = -1;
+    if (opts.isolate >= 0 && opts.isolate < nso) {
+        EntryGroup G;
+        G.entries.push_back(opts.isolate);
+        G.shells = entry_shells(opts.isolate);
+        G.nao = nao_of(G.shells);
+        g_iso = (int)ts.groups.size();
+        ts.groups.push_back(G);
+        group_atoms.push_back(atoms_of(G.shells));
     }
     // --- pair groups --------------------------------------------------------
     const double SQ2PI54 = std::sqrt(2.0) * std::pow(PI, 1.25);
@@ -465,13 +476,27 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         out.used = true;
     };
     // pass 0: the largest weights live in the one-group pair groups
-    for (int g = 0; g < ng; ++g) { PGOut o; do_pair_group(g, g, 0, 0.0, o); ts.wmax = std::max(ts.wmax, o.wmax); }
+    if (opts.wcut > 0.0) ts.wmax = opts.wcut;
+    else
+        for (int g = 0; g < ng; ++g) {
+            if (opts.measure_only && opts.only_subject && g != g_iso) continue;
+            PGOut o;
+            do_pair_group(g, g, 0, 0.0, o);
+            ts.wmax = std::max(ts.wmax, o.wmax);
+        }
+    if (opts.measure_only) return;
     const double wcut = ts.wmax;
     // pass 1 over all group pairs, on the host cores; merged in (g,h) order so the layout (and with it
     // every reduction order on the device) does not depend on the thread count
     std::vector<std::pair<int, int>> gh;
     for (int g = 0; g < ng; ++g)
-        for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h) gh.emplace_back(g, h);
+        for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h)
+            if (g != g_iso && h != g_iso && !opts.only_subject) gh.emplace_back(g, h);
+    const size_t n_free_gh = gh.size();
+    if (g_iso >= 0)
+        for (int g = 0; g < ng; ++g)
+            for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h)
+                if (g == g_iso || h == g_iso) gh.emplace_back(g, h);
     std::vector<PGOut> outs(gh.size());
     {
         int nthr = (int)std::thread::hardware_concurrency();
@@ -501,6 +526,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             const PGOut& o = outs[i];
             if (!o.used) continue;
             run.pairs += o.pairs.size(); run.sps += o.sps.size(); run.pps += o.pps.size(); run.d += o.dmat.size(); run.pg += 1;
+            if (i < n_free_gh) { ts.n_free_pg = run.pg; ts.n_free_pairs = run.pairs / 2; ts.n_free_sps = run.sps; ts.n_free_pps = run.pps; ts.n_free_d = run.d; }
         }
         ts.pg_pairs.resize(run.pairs); ts.sps.resize(run.sps); ts.pps.resize(run.pps); ts.dmat.resize(run.d); ts.pgs.resize(run.pg);
         if (flat) ts.pps_flat.resize(run.pps);

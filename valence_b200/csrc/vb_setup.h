@@ -82,6 +82,23 @@ struct TileSetup {
     int max_ne = 0, max_np = 0, max_npp = 0, max_nsp = 0;
     int max_ks = 0;                 // widest e-range of one pair type inside a pair group
     int lmax = 0;
+    int n_free_pg = 0;              // TileOpts::isolate: pair groups that do not touch the isolated entry (they come first)
+    size_t n_free_pairs = 0, n_free_sps = 0, n_free_pps = 0, n_free_d = 0;   // sizes of their tables
+};
+
+// Options of build_tiles for first_order_opt's integral cache (vb_engine.cu: first_order).
+//   isolate      : this entry forms a group of its own, created last; the pair groups touching it ("subject"
+//                  pair groups) are emitted after all the others ("free" pair groups, independent of the
+//                  orbitals of that entry)
+//   only_subject : emit the subject pair groups only (offsets start at 0; the caller shifts them behind its
+//                  resident free tables)
+//   wcut         : > 0 -> upper bound of the primitive weights to prune against (instead of this call's own
+//                  maximum), so that tables built in separate calls are pruned consistently
+struct TileOpts {
+    int isolate = -1;
+    bool only_subject = false;
+    double wcut = 0.0;
+    bool measure_only = false;      // only compute TileSetup::wmax (of the isolated group alone with only_subject)
 };
 
 double dblfac(int n);
@@ -99,6 +116,6 @@ bool obs_position(const Input& in, const Basis& bas, int orb, int pos, int* gshe
 // flat: also emit pps_flat, the primitive pairs of a pair group sorted by magnitude inside each pair
 // type across shell pairs (ket side of k_ptile)
 void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, const std::vector<ExpOrb>& orbs2e,
-                 double tau, bool flat, TileSetup* out);
+                 double tau, bool flat, TileSetup* out, const TileOpts& opts = TileOpts());
 
 }  // namespace vb
