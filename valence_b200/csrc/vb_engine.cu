@@ -28,6 +28,9 @@ namespace vb {
 
 namespace {
 
+// dynamic shared memory k_ptile may ask for: 227 KB per CTA minus its static part
+constexpr size_t PT_SMEM_MAX = 225 * 1024;
+
 long long g_h2d_bytes = 0, g_d2h_bytes = 0;   // host<->device traffic of the current call
 
 template <class T>
@@ -462,11 +465,11 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     } else {
         constexpr int nw = PT_MAX_WARPS;
         smem = ((size_t)dq_cap2 + (size_t)PT_MAXQ * g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double) + (size_t)sp_cap * sizeof(SPRec);
-        if (smem + (size_t)pp_cap * sizeof(PrimPair) <= 225 * 1024) smem += (size_t)pp_cap * sizeof(PrimPair);
+        if (smem + (size_t)pp_cap * sizeof(PrimPair) <= PT_SMEM_MAX) smem += (size_t)pp_cap * sizeof(PrimPair);
         else pp_cap = 0;
-        if (smem + BOYS_S_SIZE * sizeof(double) <= 225 * 1024) { boys_cap = BOYS_S_SIZE; smem += BOYS_S_SIZE * sizeof(double); }
+        if (smem + BOYS_S_SIZE * sizeof(double) <= PT_SMEM_MAX) { boys_cap = BOYS_S_SIZE; smem += BOYS_S_SIZE * sizeof(double); }
     }
-    if (smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+    if (smem > PT_SMEM_MAX) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     std::vector<int> nshb(nso), nshk(nso);
     for (int s = 0; s < nso; ++s) {
         nshb[s] = (int)orbs2e[wf.bra[wf.slot(s, 0)]].sh.size();
@@ -721,9 +724,9 @@ PtCfg pt_cfg(int max_ne, int max_np, int max_nsp, int max_npp)
     c.boys_cap = 0;
     constexpr int nw = PT_MAX_WARPS;
     c.smem = ((size_t)c.dq_cap2 + (size_t)PT_MAXQ * c.g_cap + (size_t)nw * PT_SCRATCH) * sizeof(double) + (size_t)c.sp_cap * sizeof(SPRec);
-    if (c.smem + (size_t)c.pp_cap * sizeof(PrimPair) <= 225 * 1024) c.smem += (size_t)c.pp_cap * sizeof(PrimPair);
+    if (c.smem + (size_t)c.pp_cap * sizeof(PrimPair) <= PT_SMEM_MAX) c.smem += (size_t)c.pp_cap * sizeof(PrimPair);
     else c.pp_cap = 0;
-    if (c.smem + BOYS_S_SIZE * sizeof(double) <= 225 * 1024) { c.boys_cap = BOYS_S_SIZE; c.smem += BOYS_S_SIZE * sizeof(double); }
+    if (c.smem + BOYS_S_SIZE * sizeof(double) <= PT_SMEM_MAX) { c.boys_cap = BOYS_S_SIZE; c.smem += BOYS_S_SIZE * sizeof(double); }
     return c;
 }
 
@@ -920,7 +923,7 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
         if (const char* e = std::getenv("VB_FO_CACHE_MB")) cap = std::min(cap, std::atof(e) * 1048576.0);
         if (need > cap) return false;
     }
-    if (cfg.smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+    if (cfg.smem > PT_SMEM_MAX) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     gcache.alloc((size_t)std::max<long long>(1, my_tiles) * cfg.g_cap);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
     gred.alloc((size_t)nsm * PT_MAXQ * cfg.g_cap);
@@ -965,7 +968,11 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     acc->n_tiles += (long long)tlc.size();
     // ---- variant tiles: every free tile of the non-symmetric task order, mapped onto its canonical tile ---------
     std::vector<int4> vts;
-    vts.reserve((size_t)my_tiles * 4);
+    vts.reserve((size_t)my_tiles * 8);
+    auto add_variant = [&](int x, int y, int slot, int swp) {       // two int4 per variant tile (k_contract)
+        vts.push_back(make_int4(hp[x].pair_beg, hp[y].pair_beg, hp[x].np | (hp[y].np << 8) | (swp << 16), 0));
+        vts.push_back(make_int4(slot, 0, 0, 0));
+    };
     for (const int4& it : itc)
         for (int j = 0; j < it.y; ++j) {
             const int2 t = tlc[(size_t)it.x + j];
@@ -979,23 +986,22 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
                     for (int k = 0; k < 2; ++k) {
                         const int x = xs[i], y = ys[k];
                         if (x < 0 || y < 0) continue;
-                        if (x >= y) vts.push_back(make_int4(x, y, slot, 0));
-                        else vts.push_back(make_int4(y, x, slot, 1));
+                        if (x >= y) add_variant(x, y, slot, 0);
+                        else add_variant(y, x, slot, 1);
                     }
             } else {
-                vts.push_back(make_int4(A0, A0, slot, 0));
+                add_variant(A0, A0, slot, 0);
                 if (Af >= 0) {
-                    vts.push_back(make_int4(Af, Af, slot, 0));
-                    vts.push_back(make_int4(std::max(A0, Af), std::min(A0, Af), slot, 0));
+                    add_variant(Af, Af, slot, 0);
+                    add_variant(std::max(A0, Af), std::min(A0, Af), slot, 0);
                 }
             }
         }
-    const long long nvt = (long long)vts.size();
+    const long long nvt = (long long)vts.size() / 2;
     vtiles.upload(vts, st);
     { std::vector<int4>().swap(vts); }
     this->sch.upload(sch_tab, st);
     A.sch = this->sch.p;
-    CK(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cfg.g_cap * sizeof(double))));
     double tm2 = now_ms();
     if (dbg_time) { CK(cudaStreamSynchronize(st)); std::printf("[fo] tables %.1f ms, cache pass %.1f ms (%lld canonical tiles, %lld mine, %.2f GB), %lld variant tiles\n", tm1 - tm0, tm2 - tm1, (long long)tlc.size(), my_tiles, (double)my_tiles * cfg.g_cap * 8e-9, nvt); }
     // ---- the (ib,jb) loop -------------------------------------------------------------------------------
@@ -1051,7 +1057,7 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
             make_items(runs, (long long)tls.size(), nsm, rank, nranks, &its, &mine);
             const PtCfg c2 = pt_cfg(std::max(tsF.max_ne, tsS.max_ne), std::max(tsF.max_np, tsS.max_np), std::max(tsF.max_nsp, tsS.max_nsp),
                                     std::max(tsF.max_npp, tsS.max_npp));
-            if (c2.smem > 225 * 1024) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+            if (c2.smem > PT_SMEM_MAX) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
             if (c2.g_cap != cfg.g_cap) throw std::runtime_error("valence_b200: first_order cache: tile size changed");
             CK(cudaFuncSetAttribute(k_ptile<PART_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2.smem));
             fill_cfg(c2);
@@ -1070,9 +1076,10 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
                 launches++;
                 acc->tile_launches++;
             }
+            if (dbg_time) CK(cudaEventRecord(ev1, st));
             if (nvt > 0) {
-                const int grid = (int)std::min<long long>(nvt, (long long)nsm * 16);
-                k_contract<<<grid, CT_THREADS, cfg.g_cap * sizeof(double), st>>>(A, vtiles.p, nvt, fo_perm.p, gcache.p, nts);
+                const int grid = (int)std::min<long long>((nvt + CT_THREADS / 32 - 1) / (CT_THREADS / 32), (long long)nsm * 16);
+                k_contract<<<grid, CT_THREADS, 0, st>>>(A, vtiles.p, nvt, fo_perm.p, gcache.p, nts);
                 CK(cudaGetLastError());
                 launches++;
             }
@@ -1092,8 +1099,12 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
             for (int i = 0; i < CNT_N; ++i) acc->counters[i] += (long long)c[i];
             (*ham)[(size_t)jb * norbas + ib] += (rank == 0 ? e1 : 0.0) + e2;
             (*ovl)[(size_t)jb * norbas + ib] += wfnorm;
-            if (dbg_time) std::printf("[fo] ib %d jb %d: cofactors %.1f ms, subject tables+tiles %.1f ms (%lld tiles), kernels %.1f ms\n", ib + 1, jb + 1, tp1 - tp0,
-                                      now_ms() - tp1 - ms, nts, ms);
+            if (dbg_time) {
+                float ms1 = 0.f;
+                CK(cudaEventElapsedTime(&ms1, ev2, ev1));
+                std::printf("[fo] ib %d jb %d: cofactors %.1f ms, subject tables+tiles %.1f ms (%lld tiles), subject kernel %.1f ms, contraction %.1f ms, entries %llu\n",
+                            ib + 1, jb + 1, tp1 - tp0, now_ms() - tp1 - ms, nts, ms1, ms - ms1, c[CNT_ENTRIES]);
+            }
         }
     return true;
 }

@@ -213,10 +213,13 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
 // Contraction of one tile's orbital-level integrals G[q][p] with the cofactor densities, with the reference's
 // screening and task bookkeeping line by line (valence.F90:1153-1433).  Threads of the CTA stride over the
 // tile's entries; returns this thread's share of the tile energy and adds to its counters.
-template <int THREADS>
-__device__ __forceinline__ double contract_tile(const TileArgs& A, const PGDesc& P, const PGDesc& Q, const double* __restrict__ G_s,
+struct TileIdx { int np, pair_beg; };     // what the contraction needs of a pair group
+// SYM = A.sym as a compile-time constant: the image loops unroll and the image table stays in registers.
+template <int THREADS, bool SYM, class GFetch>
+__device__ __forceinline__ double contract_tile(const TileArgs& A, const TileIdx P, const TileIdx Q, GFetch&& Gval,
                                                 int tid, unsigned long long (&cnt)[CNT_N])
 {
+    constexpr int NIM = SYM ? 8 : 2;
     const int nso = A.nso;
     const bool diag_tile = P.pair_beg == Q.pair_beg;
     double epart = 0.0;
@@ -227,9 +230,9 @@ __device__ __forceinline__ double contract_tile(const TileArgs& A, const PGDesc&
         const int u = A.pg_pairs[2 * (Q.pair_beg + q)], v = A.pg_pairs[2 * (Q.pair_beg + q) + 1];
         if (A.mode == 0) {
             if (diag_tile && p == q) {
-                const double G = G_s[q * P.np + p];
+                const double G = Gval(p, q);
                 A.diag[(size_t)s * nso + t] = G;
-                if (A.sym) A.diag[(size_t)t * nso + s] = G;
+                if (SYM) A.diag[(size_t)t * nso + s] = G;
             }
             continue;
         }
@@ -237,27 +240,30 @@ __device__ __forceinline__ double contract_tile(const TileArgs& A, const PGDesc&
         // contribute nothing and are counted nowhere
         const bool ssig = A.sch[s * nso + t] * A.sch[u * nso + v] > A.itol;
         if (!ssig) continue;
-        const double G = G_s[q * P.np + p];
+        const double G = Gval(p, q);
         // images of (s,t,u,v) under the integral's permutational symmetry
-        int im[8][4];
-        int nim = 0;
+        int im[NIM][4];
         {
             const int base4[2][4] = {{s, t, u, v}, {u, v, s, t}};
+#pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int a = base4[k][0], b = base4[k][1], c = base4[k][2], d = base4[k][3];
-                im[nim][0] = a; im[nim][1] = b; im[nim][2] = c; im[nim][3] = d; ++nim;
-                if (A.sym) {
-                    im[nim][0] = b; im[nim][1] = a; im[nim][2] = c; im[nim][3] = d; ++nim;
-                    im[nim][0] = a; im[nim][1] = b; im[nim][2] = d; im[nim][3] = c; ++nim;
-                    im[nim][0] = b; im[nim][1] = a; im[nim][2] = d; im[nim][3] = c; ++nim;
+                constexpr int W = SYM ? 4 : 1;
+                im[W * k][0] = a; im[W * k][1] = b; im[W * k][2] = c; im[W * k][3] = d;
+                if constexpr (SYM) {
+                    im[4 * k + 1][0] = b; im[4 * k + 1][1] = a; im[4 * k + 1][2] = c; im[4 * k + 1][3] = d;
+                    im[4 * k + 2][0] = a; im[4 * k + 2][1] = b; im[4 * k + 2][2] = d; im[4 * k + 2][3] = c;
+                    im[4 * k + 3][0] = b; im[4 * k + 3][1] = a; im[4 * k + 3][2] = d; im[4 * k + 3][3] = c;
                 }
             }
         }
         double wsum = 0.0;
         cnt[CNT_ENTRIES]++;
-        for (int k = 0; k < nim; ++k) {
+#pragma unroll
+        for (int k = 0; k < NIM; ++k) {
             const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
             bool dup = false;
+#pragma unroll
             for (int k2 = 0; k2 < k; ++k2)
                 dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
             if (dup) continue;
@@ -267,10 +273,10 @@ __device__ __forceinline__ double contract_tile(const TileArgs& A, const PGDesc&
             const bool vsig = fabs(val) > A.itol;
             // as the direct integral of task io=a, ko=b, jo=c, lo=d
             bool vd = a >= c && b >= d && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
-            if (vd && A.sym) vd = tri_index(a, c) >= tri_index(b, d);
+            if (vd && SYM) vd = tri_index(a, c) >= tri_index(b, d);
             // as the exchanged integral of task io=a, lo=b, jo=c, ko=d
             bool vx = a >= c && d >= b && !((a == c && a < A.nnd) || (b == d && b < A.nnd));
-            if (vx && A.sym) vx = tri_index(a, c) >= tri_index(d, b);
+            if (vx && SYM) vx = tri_index(a, c) >= tri_index(d, b);
             if (vd) { cnt[CNT_SCHWARZ_EREP]++; cnt[CNT_VALUE_EREP] += vsig; }
             if (vx) { cnt[CNT_SCHWARZ_EXCH]++; cnt[CNT_VALUE_EXCH] += vsig; }
             if (!shortcut) {
@@ -449,7 +455,11 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
 #pragma unroll
         for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
         for (int qi = 0; qi < ntl; ++qi) {
-            double epart = contract_tile<PT_THREADS>(A, P, s_Q[qi], Gs + qi * A.g_cap, tid, cnt);
+            const double* G_s = Gs + qi * A.g_cap;
+            const int npP = P.np;
+            const TileIdx Pi{P.np, P.pair_beg}, Qi{s_Q[qi].np, s_Q[qi].pair_beg};
+            auto gv = [&](int p, int q) { return G_s[q * npP + p]; };
+            double epart = A.sym ? contract_tile<PT_THREADS, true>(A, Pi, Qi, gv, tid, cnt) : contract_tile<PT_THREADS, false>(A, Pi, Qi, gv, tid, cnt);
             if (A.mode == 1) {
                 for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
                 if (lane == 0) s_red[warp][qi] = epart;
@@ -479,53 +489,40 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
 
 // Contraction-only pass over cached integrals (first_order_opt, valence.F90:527-764: the (ib,jb) loop changes one
 // orbital of the bra and of the ket, so every tile that does not touch that entry keeps its integrals -- the GPU
-// counterpart of the reference's eribuf cache, valence.F90:1227-1273).  One variant tile per CTA iteration:
-//   vts[i] = (pair group a, pair group b, cache slot of the canonical tile, flags);  flags bit 0: the canonical tile
-//   is stored as (canon(b), canon(a));  perm[pair] = index, inside the canonical pair group, of the pair (t,s)
-//   [identity for canonical pair groups].  A.tiles is unused; tile energies go to A.tileE[tile_base + i].
-constexpr int CT_THREADS = 128;
-__global__ void __launch_bounds__(CT_THREADS, 4) k_contract(const TileArgs A, const int4* __restrict__ vts, long long nvt,
-                                                         const int* __restrict__ perm, const double* __restrict__ gcache,
-                                                         long long tile_base)
+// counterpart of the reference's eribuf cache, valence.F90:1227-1273).  One variant tile per WARP, no barriers and no
+// shared memory: the kernel is a chain of dependent gathers (tile record -> pairs -> Schwarz values -> G, densities),
+// so it lives on the number of independent warps in flight.
+//   vts[2i]   = (first pair of P, first pair of Q, np(P) | np(Q) << 8 | swap << 16, -)
+//   vts[2i+1] = (cache slot of the canonical tile (low, high 32 bits), -, -)
+//   swap: the canonical tile is stored as (canon(Q), canon(P));  perm[pair] = index, inside the canonical pair group,
+//   of the pair (t,s) [identity for canonical pair groups].  Tile energies go to A.tileE[tile_base + i]; only entries
+//   that pass the reference's Schwarz screen fetch their integral from the cache.
+constexpr int CT_THREADS = 256;
+__global__ void __launch_bounds__(CT_THREADS, 2) k_contract(const TileArgs A, const int4* __restrict__ vts, long long nvt,
+                                                            const int* __restrict__ perm, const double* __restrict__ gcache,
+                                                            long long tile_base)
 {
-    extern __shared__ __align__(16) double G_s[];
-    __shared__ PGDesc s_P, s_Q;
-    __shared__ double s_red[CT_THREADS / 32];
     __shared__ unsigned long long s_cnt[CNT_N];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid < CNT_N) s_cnt[tid] = 0ull;
+    __syncthreads();
     unsigned long long cnt[CNT_N];
 #pragma unroll
     for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
-    for (long long it = blockIdx.x; it < nvt; it += gridDim.x) {
-        __syncthreads();
-        const int4 vt = vts[it];
-        {
-            constexpr int W = sizeof(PGDesc) / 4;
-            if (warp == 0)
-                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_P)[i] = reinterpret_cast<const int*>(A.pgs + vt.x)[i];
-            if (warp == 1)
-                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_Q)[i] = reinterpret_cast<const int*>(A.pgs + vt.y)[i];
-        }
-        __syncthreads();
-        const int npP = s_P.np, npQ = s_Q.np;
-        const double* __restrict__ src = gcache + (size_t)vt.z * A.g_cap;
-        const bool swp = vt.w & 1;
-        for (int idx = tid; idx < npP * npQ; idx += CT_THREADS) {
-            const int p = idx % npP, q = idx / npP;
-            const int pc = perm[s_P.pair_beg + p], qc = perm[s_Q.pair_beg + q];
-            G_s[q * npP + p] = swp ? src[pc * npQ + qc] : src[qc * npP + pc];
-        }
-        __syncthreads();
-        double epart = contract_tile<CT_THREADS>(A, s_P, s_Q, G_s, tid, cnt);
+    const long long nwarps = (long long)gridDim.x * (CT_THREADS / 32);
+    for (long long it = (long long)blockIdx.x * (CT_THREADS / 32) + (tid >> 5); it < nvt; it += nwarps) {
+        const int4 v0 = vts[2 * it], v1 = vts[2 * it + 1];
+        const TileIdx P{v0.z & 0xff, v0.x}, Q{(v0.z >> 8) & 0xff, v0.y};
+        const bool swp = (v0.z >> 16) & 1;
+        const long long slot = (long long)(unsigned)v1.x | ((long long)v1.y << 32);
+        const double* __restrict__ src = gcache + (size_t)slot * A.g_cap;
+        auto gv = [&](int p, int q) {
+            const int pc = perm[P.pair_beg + p], qc = perm[Q.pair_beg + q];
+            return swp ? src[pc * Q.np + qc] : src[qc * P.np + pc];
+        };
+        double epart = A.sym ? contract_tile<32, true>(A, P, Q, gv, lane, cnt) : contract_tile<32, false>(A, P, Q, gv, lane, cnt);
         for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
-        if (lane == 0) s_red[warp] = epart;
-        __syncthreads();
-        if (tid == 0) {
-            double e = 0.0;
-            for (int w = 0; w < CT_THREADS / 32; ++w) e += s_red[w];
-            A.tileE[tile_base + it] = e * A.c0;
-        }
+        if (lane == 0) A.tileE[tile_base + it] = epart * A.c0;
     }
 #pragma unroll
     for (int i = 0; i < CNT_N; ++i) {
