@@ -174,6 +174,31 @@ def run_ours(args) -> None:
 
     R = dist.ReduceOp if world > 1 else None
     wall = red(wall, R.MAX if R else None)
+    # Metric 2: guess energy + one first_order_opt accumulator build (ham, ovl of orbital 1) on the same
+    # cluster, tiles sharded over the ranks, one all-reduce of the accumulators and one of ham.  The (ib,jb) loop reuses
+    # the integrals of all tiles that do not touch the substituted orbital from an HBM cache.
+    grad = None
+    if args.grad_waters != 0:
+        gw = args.waters if args.grad_waters < 0 else args.grad_waters
+        ge, gp = eng, None
+        if gw != args.waters:
+            gp = make_input(gw)
+            ge = api.Engine(gp, device=local)
+            ge.energy_distributed(rank, world)
+        barrier()
+        t0g = time.perf_counter()
+        rg = ge.energy_distributed(rank, world)
+        Hg, Sg, st = ge.first_order_distributed(1, rank, world)
+        barrier()
+        tg = red(time.perf_counter() - t0g, R.MAX if R else None)
+        import numpy as np
+        cw = np.array([w for _, w in vin.water_cluster(gw, tol=(10, 20, 10)).orbitals[0].terms])
+        grad = {"waters": gw, "ms": 1e3 * tg, "orbital": 1, "matrix_order": int(Hg.shape[0]),
+                "first_order_kernel_ms": red(st["t_tiles_ms"], R.MAX if R else None),
+                "kernel_launches": int(st["launches"]),
+                "rayleigh_quotient_minus_energy": float(cw @ Hg @ cw / (cw @ Sg @ cw)) + rg["enucrep"] - rg["energy"]}
+        if gp is not None:
+            ge.close(); os.unlink(gp)
     dev_ms = sum(r["t_1e_ms"] + r["t_density_ms"] + r["t_diag_ms"] + r["t_tiles_ms"] for r in results) / args.steps
     dev_ms = red(dev_ms, R.MAX if R else None)
     tile_ms = red(sum(r["t_tiles_ms"] for r in results) / args.steps, R.MAX if R else None)
@@ -213,19 +238,8 @@ def run_ours(args) -> None:
                          "flops": "algorithmic: executed primitive quartets per class x per-class operation count (DESIGN.md)"},
             "clocks": sampler.summary() if sampler else None,
         }
-        if args.grad_waters > 0 and world == 1:
-            # Metric 2: guess energy + one first_order_opt accumulator build (ham, ovl of orbital 1) on a
-            # smaller cluster -- the (ib,jb) loop re-runs the tile pass per matrix element, like the reference
-            gp = make_input(args.grad_waters)
-            ge = api.Engine(gp, device=local)
-            ge.energy(); ge.first_order(1)
-            torch.cuda.synchronize(local)
-            t0g = time.perf_counter()
-            ge.energy(); _, _, st = ge.first_order(1)
-            torch.cuda.synchronize(local)
-            line["energy_plus_first_order"] = {"waters": args.grad_waters, "ms": 1e3 * (time.perf_counter() - t0g), "orbital": 1,
-                                               "tile_passes": int(st["tile_launches"])}
-            ge.close(); os.unlink(gp)
+        if grad is not None:
+            line["energy_plus_first_order"] = grad
         if args.cpu_baseline_seconds > 0 and world == 1:
             from oracle import oracle
             cb = oracle.cpu_baseline(path, seconds=args.cpu_baseline_seconds)
@@ -247,7 +261,8 @@ def main():
     ap.add_argument("--waters", type=int, default=int(os.environ.get("VB_BENCH_WATERS", "256")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
-    ap.add_argument("--grad-waters", type=int, default=16, help="cluster size of the energy + first_order_opt timing (0 = skip)")
+    ap.add_argument("--grad-waters", type=int, default=-1,
+                    help="cluster size of the energy + first_order_opt timing (metric 2); -1 = the bench cluster, 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

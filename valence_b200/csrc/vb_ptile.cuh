@@ -259,13 +259,18 @@ __device__ __forceinline__ double contract_tile(const TileArgs& A, const TileIdx
         }
         double wsum = 0.0;
         cnt[CNT_ENTRIES]++;
+        const bool e_st = s == t, e_uv = u == v, e_pq = s == u && t == v, e_px = s == v && t == u;
 #pragma unroll
         for (int k = 0; k < NIM; ++k) {
             const int a = im[k][0], b = im[k][1], c = im[k][2], d = im[k][3];
-            bool dup = false;
-#pragma unroll
-            for (int k2 = 0; k2 < k; ++k2)
-                dup = dup || (im[k2][0] == a && im[k2][1] == b && im[k2][2] == c && im[k2][3] == d);
+            // an image repeats an earlier one only through s == t, u == v, (s,t) == (u,v) or (s,t) == (v,u)
+            bool dup;
+            if constexpr (SYM) {
+                dup = (k == 1 && e_st) || (k == 2 && e_uv) || (k == 3 && (e_st || e_uv)) || (k == 4 && (e_pq || e_px)) ||
+                      (k == 5 && (e_uv || e_pq || e_px)) || (k == 6 && (e_st || e_pq || e_px)) || (k == 7 && (e_st || e_uv || e_pq || e_px));
+            } else {
+                dup = k == 1 && e_pq;
+            }
             if (dup) continue;
             // task bookkeeping exactly as the reference visits it (valence.F90:1167-1190)
             const bool shortcut = (a == c && b == d) && a != A.subject && b != A.subject;   // :1213 (nonsub)
