@@ -11,7 +11,7 @@
 #include "../../valence_b200/csrc/vb_setup.h"
 using namespace vb;
 
-static TileSetup build(const Input& in, const char* threads)
+static TileSetup build(const Input& in, const char* threads, bool sym = true, const TileOpts& opts = TileOpts())
 {
     setenv("VB_HOST_THREADS", threads, 1);
     std::vector<double> xyz(3 * in.natom);
@@ -25,8 +25,9 @@ static TileSetup build(const Input& in, const char* threads)
     wf.nnd = in.nnd(); wf.nso = wf.nnd + in.ndocc;
     for (int i = 0; i < wf.nnd; ++i) { wf.bra.push_back(i); wf.ket.push_back(i); }
     for (int d = 0; d < in.ndocc; ++d) for (int k = 0; k < 2; ++k) { wf.bra.push_back(wf.nnd + d); wf.ket.push_back(wf.nnd + d); }
+    wf.sym = sym;
     TileSetup ts;
-    build_tiles(in, bas, wf, orbs, 1e-22, true, &ts);
+    build_tiles(in, bas, wf, orbs, 1e-22, true, &ts, opts);
     return ts;
 }
 
@@ -58,6 +59,39 @@ int main(int argc, char** argv)
         for (int t = 0; t < NPTYPE; ++t)
             for (int k = pg.sp_beg[t] + 1; k < pg.sp_beg[t + 1]; ++k)
                 if (a.sps[k].pp_cnt > a.sps[k - 1].pp_cnt) { std::printf("shell pairs not sorted by length\n"); ++bad; }
+    // first_order_opt's integral cache (TileOpts): with one entry isolated the pair groups touching it come last, the
+    // "subject only" build reproduces exactly that tail (offsets relative), and the free part mirrors under (g,h)<->(h,g)
+    {
+        const int iso = in.nnd() + in.ndocc - 1;
+        TileOpts o1;
+        o1.isolate = iso;
+        TileSetup f = build(in, "3", false, o1);
+        TileOpts o2 = o1;
+        o2.only_subject = true; o2.wcut = f.wmax;
+        TileSetup sj = build(in, "2", false, o2);
+        const int nfree = f.n_free_pg, nall = (int)f.pgs.size();
+        if (nfree <= 0 || nfree >= nall) { std::printf("isolate: no free / subject split (%d of %d)\n", nfree, nall); ++bad; }
+        const int giso = (int)f.groups.size() - 1;
+        for (int x = 0; x < nall; ++x) {
+            const bool subj = f.pgs[x].g == giso || f.pgs[x].h == giso;
+            if (subj != (x >= nfree)) { std::printf("isolate: subject pair groups are not last\n"); ++bad; break; }
+        }
+        if (f.groups[giso].entries.size() != 1 || f.groups[giso].entries[0] != iso) { std::printf("isolate: group\n"); ++bad; }
+        if ((int)sj.pgs.size() != nall - nfree) { std::printf("only_subject: %zu pair groups, expected %d\n", sj.pgs.size(), nall - nfree); ++bad; }
+        else {
+            std::vector<PrimPair> tail(f.pps.begin() + f.n_free_pps, f.pps.end());
+            std::vector<double> dtail(f.dmat.begin() + f.n_free_d, f.dmat.end());
+            std::vector<int> ptail(f.pg_pairs.begin() + 2 * f.n_free_pairs, f.pg_pairs.end());
+            if (!same(tail, sj.pps) || !same(dtail, sj.dmat) || !same(ptail, sj.pg_pairs)) { std::printf("only_subject: tables differ from the tail of the full build\n"); ++bad; }
+            for (int x = nfree; x < nall; ++x)
+                if (f.pgs[x].d_off - (long long)f.n_free_d != sj.pgs[x - nfree].d_off || f.pgs[x].np != sj.pgs[x - nfree].np) { std::printf("only_subject: offsets\n"); ++bad; break; }
+        }
+        for (int x = 0; x < nfree; ++x) {
+            bool found = false;
+            for (int y = 0; y < nfree && !found; ++y) found = f.pgs[y].g == f.pgs[x].h && f.pgs[y].h == f.pgs[x].g && f.pgs[y].np == f.pgs[x].np;
+            if (!found) { std::printf("free pair group (%d,%d) has no mirror\n", f.pgs[x].g, f.pgs[x].h); ++bad; break; }
+        }
+    }
     // compact Boys table against the exact series
     std::vector<double> tab(BOYS_S_SIZE);
     boys_make_table_small(tab.data());
