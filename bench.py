@@ -13,6 +13,9 @@ reference algorithm (/root/reference/src/valence.F90:3398); the count comes from
 bit-exact screening counters, so recomputation the GPU formulation avoids still counts once per
 reference call.  `unique_ao_quartets_per_s` reports what the GPU actually generates.
 
+Metric 2 (`energy_plus_first_order`): wall time of one guess energy plus the first_order_opt matrices (ham, ovl) of
+orbital 1 on the same cluster, through the sharded C-ABI calls.
+
 N > 1 (torchrun): the tile list is sharded block-cyclically over ranks with work stealing
 inside each GPU; one NCCL all-reduce of the packed accumulators per step; "scaling": "strong"
 (the same cluster is split over more GPUs).
