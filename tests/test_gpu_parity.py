@@ -315,6 +315,8 @@ def _fo_case(name, write_input):
         return write_input(inputs.water_cluster(3, tol=(10, 20, 10), rotate=True))[0]
     if name == "water4":
         return write_input(inputs.water_cluster(4, tol=(10, 20, 10)))[0]
+    if name == "water2":
+        return write_input(inputs.water_cluster(2, tol=(10, 20, 10)))[0]
     if name == "water2sc":
         return write_input(inputs.water_cluster(2, tol=(10, 20, 10), sc_molecules=1))[0]
     return write_input(name)[0]
@@ -336,7 +338,7 @@ def test_first_order_integral_cache_matches_plain_loop(name, iorb, write_input):
     assert stc["n_prim_quartets"] < stp["n_prim_quartets"]     # the cache did save integral work
 
 
-@pytest.mark.parametrize("name,iorb", [("water3rot", 2), ("water4", 7), ("examples__c3h8", 5)])
+@pytest.mark.parametrize("name,iorb", [("water3rot", 2), ("water2", 7), ("examples__c3h8", 5)])
 def test_first_order_large_determinant_path_matches_oracle(name, iorb, write_input):
     """Substituted (non-symmetric) lists through the GPU inverse form (the path large clusters take; forced here
     with VB_FAST_MIN_N) against the oracle's first_order_opt."""
