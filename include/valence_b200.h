@@ -95,6 +95,10 @@ int vb_engine_first_order_sharded(vb_engine* e, int iorb, int rank, int nranks, 
 /* calculate_vsvb_energy (valence.F90:28-302): guess energy and, if the input asks for it, the
  * first-order orbital optimisation + spin-coupling optimisation of minimize_energy (:2744-2885) */
 int vb_engine_run(vb_engine* e, int print, double* enucrep, double* guess_energy, double* total_energy, int* converged, int* iterations);
+/* xm_output (xm_module.F90:464-577) without a GPU: writes `orbitals` (and `nelecwfn` when the input has several
+ * spin couplings) for the wavefunction of an input file into the current directory, as the reference does after the
+ * guess energy (valence.F90:192) and at convergence (:2882, converged != 0 adds the "converged to" line). */
+int vb_write_wavefunction_files(const char* input_path, double energy, int converged);
 double* vb_engine_accum_device(const vb_engine* e);
 int vb_engine_accum_len(const vb_engine* e);
 void* vb_engine_stream(const vb_engine* e);

@@ -1,5 +1,6 @@
 // C-ABI of libvalence_b200.so (see include/valence_b200.h for the contract and the reference
 // lines each entry point replaces).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -68,9 +69,46 @@ std::string host_argv1()
     return std::string(all.c_str() + z + 1);
 }
 
-// xm_output 'save' (xm_module.F90:464-577): orbitals + energy, formats :571-576
-void write_orbitals_file(const vb::Input& in, const std::vector<std::vector<double>>* coeff, double energy)
+// Fortran edit descriptor 1e10.2 (0.dddE+xx, right-justified in 10 columns)
+std::string fortran_e10_2(double x)
 {
+    char buf[32];
+    if (x == 0.0) return "  0.00E+00";
+    int ex = (int)std::floor(std::log10(std::fabs(x))) + 1;
+    double m = std::fabs(x) / std::pow(10.0, ex);
+    long d = std::lround(m * 100.0);
+    if (d >= 100) { d = 10; ex += 1; }
+    std::snprintf(buf, sizeof buf, "%s0.%02ldE%c%02d", x < 0 ? "-" : "", d, ex < 0 ? '-' : '+', std::abs(ex));
+    std::string out(buf);
+    while (out.size() < 10) out.insert(out.begin(), ' ');
+    return out;
+}
+
+// xm_output (xm_module.F90:464-577): `orbitals` (formats 1, 2, 5, 7 at :571-577) and, for more than one spin
+// coupling, `nelecwfn` (formats 3, 4; :479-505).  mode 'done' adds the convergence line (:561).
+void write_orbitals_file(const vb::Input& in, const std::vector<std::vector<double>>* coeff, const std::vector<double>* coeff_sc,
+                         double energy, bool done = false, double etol = 0.0)
+{
+    if (in.nspinc > 1) {
+        if (FILE* fn = std::fopen("nelecwfn", "w")) {
+            for (int j = 0; j < in.nspinc; ++j) {
+                const double w = (coeff_sc && (int)coeff_sc->size() > j) ? (*coeff_sc)[j] : in.coeff_sc[j];
+                std::fprintf(fn, " %13.8f", w);                                   // format 4: 1x,1f13.8,7(2i3,2x)
+                for (int k = 0; k < in.npair; ++k) {
+                    if (k > 0 && k % 7 == 0) std::fprintf(fn, "\n");              // format reversion: new record from 7(2i3,2x)
+                    std::fprintf(fn, "%3d%3d  ", in.pair(j, k, 0), in.pair(j, k, 1));
+                }
+                std::fprintf(fn, "\n");
+            }
+            std::fprintf(fn, " ");                                                // format 3: 1x,7(2i3,2x)
+            for (int i = 0; i < in.nxorb; ++i) {
+                if (i > 0 && i % 7 == 0) std::fprintf(fn, "\n");
+                std::fprintf(fn, "%3d%3d  ", in.xorb[i], in.root[i]);
+            }
+            std::fprintf(fn, "\n\n");
+            std::fclose(fn);
+        }
+    }
     FILE* fh = std::fopen("orbitals", "w");
     if (!fh) return;
     const int nval = in.norbs() - in.ndf;
@@ -87,7 +125,9 @@ void write_orbitals_file(const vb::Input& in, const std::vector<std::vector<doub
         }
     }
     if (in.ndf == 0) std::fprintf(fh, "\n");
-    std::fprintf(fh, "\n total energy in atomic units %32.16f\n\n", energy);
+    std::fprintf(fh, "\n total energy in atomic units %32.16f\n", energy);
+    if (done) std::fprintf(fh, " converged to %s kCal/mol\n", fortran_e10_2(etol).c_str());
+    std::fprintf(fh, "\n");
     std::fclose(fh);
 }
 
@@ -228,11 +268,24 @@ void valence_api_calculate_energy_(double* x, double* v)
         g_api->set_coords_angstrom(x);                                   // valence_api.F90:57-63
         vb::Engine::RunResult r;
         g_api->run(&r, true);                                            // calculate_vsvb_energy, valence_api.F90:96-97
-        write_orbitals_file(g_api->input(), &g_api->weights(), r.total_energy);   // valence.F90:192,2823,2882
+        // valence.F90:192,2823,2859 ('save') and :2882 ('done' with the last feathering tolerance, :2771-2772)
+        const bool done = r.converged && g_api->input().max_iter > 0;
+        write_orbitals_file(g_api->input(), &g_api->weights(), &g_api->coupling_weights(), r.total_energy, done,
+                            std::pow(10.0, -(double)g_api->input().ntol_e_max));
         *v = r.total_energy;
     } catch (const std::exception& ex) {
         api_abort(ex.what());
     }
+}
+
+// Host-only utility (no GPU): write `orbitals` (and `nelecwfn`) for the wavefunction of an input file as xm_output
+// does, into the current directory.  converged != 0 adds the 'done' line.
+int vb_write_wavefunction_files(const char* input_path, double energy, int converged)
+{
+    return guarded([&] {
+        vb::Input in = vb::parse_input_file(input_path);
+        write_orbitals_file(in, nullptr, nullptr, energy, converged != 0, std::pow(10.0, -(double)in.ntol_e_max));
+    });
 }
 
 const double* vb_api_input_coords(void) { return g_api ? g_api->input().coords.data() : nullptr; }
