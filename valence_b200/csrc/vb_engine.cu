@@ -12,6 +12,8 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
+#include <atomic>
 
 #include "vb_cofactor.h"
 #include "vb_kernels.cuh"
@@ -133,6 +135,7 @@ struct Engine::Impl {
                   EnergyResult* out, std::vector<double>* sch_out);
     bool first_order_cached(const Input& in, const Wavefunction& wf, int es, int iorb, const std::vector<double>& sch, int rank, int nranks,
                             std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* acc);
+    TileSetup ts_keep;                               // host tables of the last evaluation (storage kept)
     DBuf<double> gcache;                             // first_order_opt: orbital-level integrals of the subject-free tiles
     DBuf<int4> vtiles;
     DBuf<int> fo_perm;
@@ -316,6 +319,13 @@ void Engine::Impl::prepare(const Input& in, int subject)
     }
 }
 
+namespace {
+void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec, const std::vector<int>& bvec, double itol,
+                    std::vector<int2>* tl, std::vector<std::pair<long long, int>>* runs);
+void make_items(const std::vector<std::pair<long long, int>>& runs, long long ntiles, int nsm, int rank, int nranks,
+                std::vector<int4>* itl, long long* my_tiles);
+}  // namespace
+
 // One vsvb_energy evaluation (valence.F90:1010-1434) for the bra/ket lists in wf.
 //   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
 //             valence.F90:667 vs 674-704); null -> run the diagonal pass (schwarz_ints)
@@ -445,7 +455,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     int bas_lmax = 0;
     for (const GShell& gs : bas.shells) bas_lmax = std::max(bas_lmax, gs.l);
     const bool gen = bas_lmax >= 2;   // d shells: shell-pair kernel with the loop-based recurrence (k_tile<true>)
-    TileSetup ts;
+    TileSetup& ts = ts_keep;    // storage reused across calls (no zero-fill / page faults of ~0.6 GB per energy)
     build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts);
     const double t_bt = now_ms();
     const int npg = (int)ts.pgs.size();
@@ -553,49 +563,18 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     // against chunks of QC consecutive ket pair groups, so that the tables of one (block, chunk) -- a few tens of
     // MB -- stay in L2 while the CTAs work through it; inside a chunk the partners of a come by decreasing
     // Schwarz bound (early exit).  A run = the tiles of one (a, chunk).
-    const int PB = 128, QC = 1024;
-    const int nchunks = (npg + QC - 1) / QC;
-    std::vector<int> order(npg);
-    std::iota(order.begin(), order.end(), 0);
-    for (int c = 0; c < nchunks; ++c)
-        std::stable_sort(order.begin() + (size_t)c * QC, order.begin() + std::min<size_t>(npg, (size_t)(c + 1) * QC),
-                         [&](int x, int y) { return ts.pgs[x].smax > ts.pgs[y].smax; });
+    std::vector<int> all(npg);
+    std::iota(all.begin(), all.end(), 0);
     std::vector<int2> tl;
     std::vector<std::pair<long long, int>> runs;      // (first tile, # tiles) of every non-empty (a, chunk)
-    for (int B0 = 0; B0 < npg; B0 += PB) {
-        const int B1 = std::min(npg, B0 + PB);
-        for (int c = 0; c < nchunks && c * QC < B1; ++c) {
-            const int c0 = c * QC, c1 = std::min(npg, c0 + QC);
-            for (int a = std::max(B0, c0); a < B1; ++a) {
-                const double sa = ts.pgs[a].smax;
-                const long long start = (long long)tl.size();
-                for (int j = c0; j < c1; ++j) {
-                    const int b = order[j];
-                    if (!(sa * ts.pgs[b].smax > itol)) break;
-                    if (b <= a) tl.push_back(make_int2(a, b));
-                }
-                if ((long long)tl.size() > start) runs.emplace_back(start, (int)((long long)tl.size() - start));
-            }
-        }
-    }
+    make_tile_list(ts.pgs, all, all, itol, &tl, &runs);
     const long long ntiles = (long long)tl.size();
-    if (ntiles > 2000000000LL) throw std::runtime_error("valence_b200: tile list too long");
     // work items of the s/p kernel: pieces of <= m tiles of a run (they share the bra pair group); the d-shell
     // kernel takes single tiles.  Only this rank's items are kept (block-cyclic over the ranks; z = slot of the
     // item's first tile in the G hand-over buffer).
     std::vector<int4> itl;
     long long my_tiles = 0;
-    if (!gen) {
-        const long long m = std::max<long long>(1, std::min<long long>(PT_MAXQ, ntiles / ((long long)nsm * nranks * 16)));
-        long long idx = 0;
-        for (const auto& run : runs)
-            for (long long k = run.first; k < run.first + run.second; k += m, ++idx) {
-                if (idx % nranks != rank) continue;
-                const int cnt = (int)std::min<long long>(m, run.first + run.second - k);
-                itl.push_back(make_int4((int)k, cnt, (int)my_tiles, 0));
-                my_tiles += cnt;
-            }
-    }
+    if (!gen) make_items(runs, ntiles, nsm, rank, nranks, &itl, &my_tiles);
     long long mine = (long long)itl.size();
     if (gen) { mine = 0; for (long long k = rank; k < ntiles; k += nranks) mine++; }
     double t4 = now_ms();
@@ -747,8 +726,15 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
         std::stable_sort(order.begin() + (size_t)c * QC, order.begin() + std::min<size_t>(nb, (size_t)(c + 1) * QC),
                          [&](int x, int y) { return pgs[x].smax > pgs[y].smax; });
     }
-    for (int B0 = 0; B0 < na; B0 += PB) {
-        const int B1 = std::min(na, B0 + PB);
+    // one bra block per task on the host cores; the blocks are concatenated in order, so the list does not depend on
+    // the thread count
+    const int nblocks = (na + PB - 1) / PB;
+    std::vector<std::vector<int2>> btl(nblocks);
+    std::vector<std::vector<std::pair<long long, int>>> bruns(nblocks);
+    auto do_block = [&](int blk) {
+        const int B0 = blk * PB, B1 = std::min(na, B0 + PB);
+        std::vector<int2>& t = btl[blk];
+        std::vector<std::pair<long long, int>>& r = bruns[blk];
         for (int c = 0; c < nchunks; ++c) {
             if (cmin[c] > avec[B1 - 1]) break;
             const int c0 = c * QC, c1 = std::min(nb, c0 + QC);
@@ -756,15 +742,36 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
                 const int a = avec[ai];
                 if (a < cmin[c]) continue;
                 const double sa = pgs[a].smax;
-                const long long start = (long long)tl->size();
+                const long long start = (long long)t.size();
                 for (int j = c0; j < c1; ++j) {
                     const int b = order[j];
                     if (!(sa * pgs[b].smax > itol)) break;
-                    if (b <= a) tl->push_back(make_int2(a, b));
+                    if (b <= a) t.push_back(make_int2(a, b));
                 }
-                if ((long long)tl->size() > start) runs->emplace_back(start, (int)((long long)tl->size() - start));
+                if ((long long)t.size() > start) r.emplace_back(start, (int)((long long)t.size() - start));
             }
         }
+    };
+    {
+        int nthr = (int)std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("VB_HOST_THREADS")) nthr = std::atoi(e);
+        nthr = std::max(1, std::min(nthr, 32));
+        if (nblocks < 8) nthr = 1;
+        std::atomic<int> next{0};
+        auto work = [&]() { for (int blk; (blk = next.fetch_add(1)) < nblocks;) do_block(blk); };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread& t : pool) t.join();
+    }
+    size_t total = 0, nruns = 0;
+    for (int blk = 0; blk < nblocks; ++blk) { total += btl[blk].size(); nruns += bruns[blk].size(); }
+    tl->reserve(total); runs->reserve(nruns);
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const long long off = (long long)tl->size();
+        tl->insert(tl->end(), btl[blk].begin(), btl[blk].end());
+        for (const auto& r : bruns[blk]) runs->emplace_back(r.first + off, r.second);
+        std::vector<int2>().swap(btl[blk]);
     }
     if ((long long)tl->size() > 2000000000LL) throw std::runtime_error("valence_b200: tile list too long");
 }

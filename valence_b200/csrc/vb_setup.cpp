@@ -3,10 +3,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <chrono>
 #include <thread>
 
 namespace vb {
@@ -206,7 +208,13 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
 {
     (void)in;
     TileSetup& ts = *out;
-    ts = TileSetup();
+    // reset, but keep the storage of the big tables: a TileSetup that is reused across calls is resized in place at
+    // the merge (every element is overwritten there), which saves zero-filling and page-faulting ~0.6 GB per call
+    ts.groups.clear(); ts.pgs.clear();
+    ts.wmax = 0.0;
+    ts.max_ne = ts.max_np = ts.max_npp = ts.max_nsp = ts.max_ks = ts.lmax = 0;
+    ts.n_free_pg = 0; ts.n_free_pairs = ts.n_free_sps = ts.n_free_pps = ts.n_free_d = 0;
+    if (opts.measure_only) { ts.pg_pairs.clear(); ts.sps.clear(); ts.pps.clear(); ts.pps_flat.clear(); ts.dmat.clear(); }
     const int nso = wf.nso;
     // --- entry groups -------------------------------------------------------
     const int NG_MAX = 5, AO_BUDGET = 80;
@@ -475,6 +483,9 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         }
         out.used = true;
     };
+    const bool dbg_t = std::getenv("VB_DEBUG_SETUP") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tt0 = tnow();
     // pass 0: the largest weights live in the one-group pair groups
     if (opts.wcut > 0.0) ts.wmax = opts.wcut;
     else
@@ -486,6 +497,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         }
     if (opts.measure_only) return;
     const double wcut = ts.wmax;
+    const double tt1 = tnow();
     // pass 1 over all group pairs, on the host cores; merged in (g,h) order so the layout (and with it
     // every reduction order on the device) does not depend on the thread count
     std::vector<std::pair<int, int>> gh;
@@ -516,6 +528,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         work();
         for (std::thread& t : pool) t.join();
     }
+    const double tt2 = tnow();
     // merge: offsets by a serial scan, the copies (and the magnitude sort of the flat lists) on the host cores
     struct Off { size_t pairs, sps, pps, d; int pg; };
     std::vector<Off> offs(outs.size());
@@ -530,6 +543,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         }
         ts.pg_pairs.resize(run.pairs); ts.sps.resize(run.sps); ts.pps.resize(run.pps); ts.dmat.resize(run.d); ts.pgs.resize(run.pg);
         if (flat) ts.pps_flat.resize(run.pps);
+        else ts.pps_flat.clear();
     }
     {
         std::atomic<size_t> next{0};
@@ -588,6 +602,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         ts.max_np = std::max(ts.max_np, pg.np);
     }
     for (const GShell& s : bas.shells) ts.lmax = std::max(ts.lmax, s.l);
+    if (dbg_t) std::printf("[setup] groups+pass0 %.1f ms, pass1 %.1f ms, merge %.1f ms\n", tt1 - tt0, tt2 - tt1, tnow() - tt2);
 }
 
 }  // namespace vb
