@@ -32,3 +32,15 @@ def test_pair_table_build_is_thread_count_independent(tmp_path):
                            os.path.join(csrc, "vb_setup.cpp"), os.path.join(csrc, "vb_input.cpp")])
     out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_tile_list_and_rank_sharding_on_the_host(tmp_path):
+    """vb_tilelist.cpp on the CPU: the tile list is exactly the Schwarz-screened set of pair-group pairs, independent
+    of the host thread count, and the work items of 1/2/3/8 ranks partition it (the N > 1 data path has no other
+    exchange than the final all-reduce)."""
+    exe = tmp_path / "test_tilelist"
+    csrc = os.path.join(ROOT, "valence_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I", csrc, "-o", str(exe),
+                           os.path.join(ROOT, "tests", "host", "test_tilelist_host.cpp"), os.path.join(csrc, "vb_tilelist.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

@@ -17,6 +17,7 @@
 
 #include "vb_cofactor.h"
 #include "vb_kernels.cuh"
+#include "vb_tilelist.h"
 #include "vb_ptile.cuh"
 #include "vb_tile.cuh"
 
@@ -32,6 +33,8 @@ namespace {
 
 // dynamic shared memory k_ptile may ask for: 227 KB per CTA minus its static part
 constexpr size_t PT_SMEM_MAX = 225 * 1024;
+static_assert(sizeof(TilePair) == sizeof(int2) && sizeof(WorkItem) == sizeof(int4) && alignof(WorkItem) == alignof(int4), "tile list records must match int2 / int4");
+static_assert(PT_MAXQ == TILES_PER_ITEM_MAX, "work items hold at most PT_MAXQ tiles");
 
 long long g_h2d_bytes = 0, g_d2h_bytes = 0;   // host<->device traffic of the current call
 
@@ -117,8 +120,9 @@ struct Engine::Impl {
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket;
     DBuf<double> oc;
-    DBuf<int2> opairs, tiles;
-    DBuf<int4> items;
+    DBuf<int2> opairs;
+    DBuf<TilePair> tiles;       // same layout as int2 / int4 (vb_tilelist.h)
+    DBuf<WorkItem> items;
     DBuf<PGDesc> pgs;
     DBuf<SPRec> sps;
     DBuf<PrimPair> pps, pps_flat;
@@ -318,13 +322,6 @@ void Engine::Impl::prepare(const Input& in, int subject)
         optr.upload(ptr, st); oao.upload(ao, st); oc.upload(c, st);
     }
 }
-
-namespace {
-void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec, const std::vector<int>& bvec, double itol,
-                    std::vector<int2>* tl, std::vector<std::pair<long long, int>>* runs);
-void make_items(const std::vector<std::pair<long long, int>>& runs, long long ntiles, int nsm, int rank, int nranks,
-                std::vector<int4>* itl, long long* my_tiles);
-}  // namespace
 
 // One vsvb_energy evaluation (valence.F90:1010-1434) for the bra/ket lists in wf.
 //   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
@@ -526,13 +523,13 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         sch = *sch_in;
     } else {
         std::vector<double> dg;
-        std::vector<int2> dt(npg);
-        std::vector<int4> di(npg);
-        for (int i = 0; i < npg; ++i) { dt[i] = make_int2(i, i); di[i] = make_int4(i, 1, 0, 0); }
+        std::vector<TilePair> dt(npg);
+        std::vector<WorkItem> di(npg);
+        for (int i = 0; i < npg; ++i) { dt[i] = TilePair{i, i}; di[i] = WorkItem{i, 1, 0, 0}; }
         tiles.upload(dt, st); items.upload(di, st);
         diag.alloc((size_t)nso * nso);
         diag.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-        A.tiles = tiles.p; A.ntiles = npg; A.items = items.p; A.nitems = npg; A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
+        A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = npg; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = npg; A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
         CK(cudaEventRecord(ev0, st));
         launch(npg, PART_ALL);
         CK(cudaEventRecord(ev1, st));
@@ -565,14 +562,14 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     // Schwarz bound (early exit).  A run = the tiles of one (a, chunk).
     std::vector<int> all(npg);
     std::iota(all.begin(), all.end(), 0);
-    std::vector<int2> tl;
+    std::vector<TilePair> tl;
     std::vector<std::pair<long long, int>> runs;      // (first tile, # tiles) of every non-empty (a, chunk)
     make_tile_list(ts.pgs, all, all, itol, &tl, &runs);
     const long long ntiles = (long long)tl.size();
     // work items of the s/p kernel: pieces of <= m tiles of a run (they share the bra pair group); the d-shell
     // kernel takes single tiles.  Only this rank's items are kept (block-cyclic over the ranks; z = slot of the
     // item's first tile in the G hand-over buffer).
-    std::vector<int4> itl;
+    std::vector<WorkItem> itl;
     long long my_tiles = 0;
     if (!gen) make_items(runs, ntiles, nsm, rank, nranks, &itl, &my_tiles);
     long long mine = (long long)itl.size();
@@ -584,7 +581,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     tiles.upload(tl, st); items.upload(itl, st);
     tileE.alloc((size_t)std::max<long long>(ntiles, 1));
     tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-    A.tiles = tiles.p; A.ntiles = (int)ntiles; A.items = items.p; A.nitems = (int)itl.size(); A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
+    A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)ntiles; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itl.size(); A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
     A.sch = this->sch.p; A.tileE = tileE.p;
     bool split = false;   // VB_SPLIT=1: separate heavy / light launches (measured slower: 5.97 s vs 5.46 s on (H2O)_256)
     if (const char* e = std::getenv("VB_SPLIT")) split = std::atoi(e) != 0;
@@ -592,7 +589,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     if (gen) {
         if (mine > 0) launch((int)mine, PART_ALL);
     } else if (mine > 0 && !split) {
-        A.items = items.p; A.nitems = (int)itl.size(); A.tile_first = 0; A.tile_stride = 1;
+        A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itl.size(); A.tile_first = 0; A.tile_stride = 1;
         launch((int)mine, PART_ALL);
         out->tile_launches += 1;
     } else if (mine > 0) {
@@ -607,7 +604,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             size_t i1 = i0;
             long long nt = 0;
             while (i1 < itl.size() && nt + itl[i1].y <= chunk_tiles) { nt += itl[i1].y; ++i1; }
-            A.items = items.p + i0; A.nitems = (int)(i1 - i0); A.gslot_base = itl[i0].z;
+            A.items = reinterpret_cast<const int4*>(items.p + i0); A.nitems = (int)(i1 - i0); A.gslot_base = itl[i0].z;
             counter.zero(st);
             launch((int)(i1 - i0), PART_HEAVY);
             counter.zero(st);
@@ -707,90 +704,6 @@ PtCfg pt_cfg(int max_ne, int max_np, int max_nsp, int max_npp)
     else c.pp_cap = 0;
     if (c.smem + BOYS_S_SIZE * sizeof(double) <= PT_SMEM_MAX) { c.boys_cap = BOYS_S_SIZE; c.smem += BOYS_S_SIZE * sizeof(double); }
     return c;
-}
-
-// Tiles (a, b), a in avec, b in bvec (both ascending pair-group indices), b <= a, smax_a * smax_b > itol; ordered in
-// blocks of bra pair groups against chunks of ket pair groups (L2 residency), partners by decreasing Schwarz bound.
-// runs: (first tile, # tiles) of every non-empty (a, chunk).
-void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec, const std::vector<int>& bvec, double itol,
-                    std::vector<int2>* tl, std::vector<std::pair<long long, int>>* runs)
-{
-    tl->clear(); runs->clear();
-    const int PB = 128, QC = 1024;
-    const int na = (int)avec.size(), nb = (int)bvec.size();
-    const int nchunks = (nb + QC - 1) / QC;
-    std::vector<int> order(bvec);
-    std::vector<int> cmin(nchunks);
-    for (int c = 0; c < nchunks; ++c) {
-        cmin[c] = bvec[(size_t)c * QC];
-        std::stable_sort(order.begin() + (size_t)c * QC, order.begin() + std::min<size_t>(nb, (size_t)(c + 1) * QC),
-                         [&](int x, int y) { return pgs[x].smax > pgs[y].smax; });
-    }
-    // one bra block per task on the host cores; the blocks are concatenated in order, so the list does not depend on
-    // the thread count
-    const int nblocks = (na + PB - 1) / PB;
-    std::vector<std::vector<int2>> btl(nblocks);
-    std::vector<std::vector<std::pair<long long, int>>> bruns(nblocks);
-    auto do_block = [&](int blk) {
-        const int B0 = blk * PB, B1 = std::min(na, B0 + PB);
-        std::vector<int2>& t = btl[blk];
-        std::vector<std::pair<long long, int>>& r = bruns[blk];
-        for (int c = 0; c < nchunks; ++c) {
-            if (cmin[c] > avec[B1 - 1]) break;
-            const int c0 = c * QC, c1 = std::min(nb, c0 + QC);
-            for (int ai = B0; ai < B1; ++ai) {
-                const int a = avec[ai];
-                if (a < cmin[c]) continue;
-                const double sa = pgs[a].smax;
-                const long long start = (long long)t.size();
-                for (int j = c0; j < c1; ++j) {
-                    const int b = order[j];
-                    if (!(sa * pgs[b].smax > itol)) break;
-                    if (b <= a) t.push_back(make_int2(a, b));
-                }
-                if ((long long)t.size() > start) r.emplace_back(start, (int)((long long)t.size() - start));
-            }
-        }
-    };
-    {
-        int nthr = (int)std::thread::hardware_concurrency();
-        if (const char* e = std::getenv("VB_HOST_THREADS")) nthr = std::atoi(e);
-        nthr = std::max(1, std::min(nthr, 32));
-        if (nblocks < 8) nthr = 1;
-        std::atomic<int> next{0};
-        auto work = [&]() { for (int blk; (blk = next.fetch_add(1)) < nblocks;) do_block(blk); };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
-        work();
-        for (std::thread& t : pool) t.join();
-    }
-    size_t total = 0, nruns = 0;
-    for (int blk = 0; blk < nblocks; ++blk) { total += btl[blk].size(); nruns += bruns[blk].size(); }
-    tl->reserve(total); runs->reserve(nruns);
-    for (int blk = 0; blk < nblocks; ++blk) {
-        const long long off = (long long)tl->size();
-        tl->insert(tl->end(), btl[blk].begin(), btl[blk].end());
-        for (const auto& r : bruns[blk]) runs->emplace_back(r.first + off, r.second);
-        std::vector<int2>().swap(btl[blk]);
-    }
-    if ((long long)tl->size() > 2000000000LL) throw std::runtime_error("valence_b200: tile list too long");
-}
-
-// work items of k_ptile: pieces of <= m tiles of a run, block-cyclic over the ranks; z = slot of the item's first tile
-void make_items(const std::vector<std::pair<long long, int>>& runs, long long ntiles, int nsm, int rank, int nranks,
-                std::vector<int4>* itl, long long* my_tiles)
-{
-    itl->clear();
-    *my_tiles = 0;
-    const long long m = std::max<long long>(1, std::min<long long>(PT_MAXQ, ntiles / ((long long)nsm * nranks * 16)));
-    long long idx = 0;
-    for (const auto& run : runs)
-        for (long long k = run.first; k < run.first + run.second; k += m, ++idx) {
-            if (idx % nranks != rank) continue;
-            const int cnt = (int)std::min<long long>(m, run.first + run.second - k);
-            itl->push_back(make_int4((int)k, cnt, (int)*my_tiles, 0));
-            *my_tiles += cnt;
-        }
 }
 
 }  // namespace
@@ -915,10 +828,10 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     // ---- integral pass over the canonical free tiles -> cache ----------------------------------------------
     std::vector<int> cand;
     for (int x = 0; x < nfree; ++x) if (canon[x] == x) cand.push_back(x);
-    std::vector<int2> tlc;
+    std::vector<TilePair> tlc;
     std::vector<std::pair<long long, int>> runs;
     make_tile_list(hp, cand, cand, itol, &tlc, &runs);
-    std::vector<int4> itc;
+    std::vector<WorkItem> itc;
     long long my_tiles = 0;
     make_items(runs, (long long)tlc.size(), nsm, rank, nranks, &itc, &my_tiles);
     PtCfg cfg = pt_cfg(tsF.max_ne, tsF.max_np, tsF.max_nsp, tsF.max_npp);
@@ -959,7 +872,7 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     if (my_tiles > 0) {
         tiles.upload(tlc, st); items.upload(itc, st);
         counter.zero(st); counters.zero(st); pq_counters.zero(st);
-        A.tiles = tiles.p; A.ntiles = (int)tlc.size(); A.items = items.p; A.nitems = (int)itc.size();
+        A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)tlc.size(); A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itc.size();
         A.gbuf = gcache.p; A.gslot_base = 0; A.mode = 2; A.tau = tau_energy;
         CK(cudaEventRecord(ev2, st));
         k_ptile<PART_ALL><<<std::max(1, std::min(nsm, (int)itc.size())), pt_threads(PART_ALL), cfg.smem, st>>>(A);
@@ -980,9 +893,9 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
         vts.push_back(make_int4(hp[x].pair_beg, hp[y].pair_beg, hp[x].np | (hp[y].np << 8) | (swp << 16), 0));
         vts.push_back(make_int4(slot, 0, 0, 0));
     };
-    for (const int4& it : itc)
+    for (const WorkItem& it : itc)
         for (int j = 0; j < it.y; ++j) {
-            const int2 t = tlc[(size_t)it.x + j];
+            const TilePair t = tlc[(size_t)it.x + j];
             const int slot = it.z + j;
             const int A0 = t.x, B0 = t.y;
             const int Af = (flip[A0] >= 0 && flip[A0] != A0 && canon[flip[A0]] == A0) ? flip[A0] : -1;
@@ -1057,9 +970,9 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
             avec.clear(); bvec.clear();
             for (int x = nfree; x < nfree + nS; ++x) avec.push_back(x);
             for (int x = 0; x < nfree + nS; ++x) bvec.push_back(x);
-            std::vector<int2> tls;
+            std::vector<TilePair> tls;
             make_tile_list(hp, avec, bvec, itol, &tls, &runs);
-            std::vector<int4> its;
+            std::vector<WorkItem> its;
             long long mine = 0;
             make_items(runs, (long long)tls.size(), nsm, rank, nranks, &its, &mine);
             const PtCfg c2 = pt_cfg(std::max(tsF.max_ne, tsS.max_ne), std::max(tsF.max_np, tsS.max_np), std::max(tsF.max_nsp, tsS.max_nsp),
@@ -1072,7 +985,7 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
             tiles.upload(tls, st); items.upload(its, st);
             tileE.alloc((size_t)std::max<long long>(1, nts + nvt));
             tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-            A.tiles = tiles.p; A.ntiles = (int)nts; A.items = items.p; A.nitems = (int)its.size();
+            A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)nts; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)its.size();
             A.gbuf = nullptr; A.gslot_base = 0; A.mode = 1; A.tau = tau_energy;
             A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
             A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p; A.tileE = tileE.p;
