@@ -352,6 +352,22 @@ def test_first_order_large_determinant_path_matches_oracle(name, iorb, write_inp
     assert np.abs(Sg - So).max() < 1e-8
 
 
+def test_first_order_rayleigh_quotient_reproduces_energy_on_32_waters(write_input):
+    """Size-independent property at a size the oracle cannot reach: c^T ham c / c^T ovl c + E_nuc equals the energy
+    of the unsubstituted wave function.  (H2O)_32: 160-electron spin blocks through the GPU inverse form, integral
+    cache, contraction-only kernel; measured deviation 7e-11 Eh (1e-9 Eh at n = 256, bench.py)."""
+    from valence_b200 import api, inputs
+    inp = inputs.water_cluster(32, tol=(10, 20, 10))
+    path, _ = write_input(inp)
+    eng = api.Engine(path)
+    r = eng.energy()
+    H, S, st = eng.first_order(1)
+    eng.close()
+    c = np.array([w for _, w in inp.orbitals[0].terms])
+    assert abs(float(c @ H @ c / (c @ S @ c)) + r["enucrep"] - r["energy"]) < 1e-9
+    assert np.allclose(H, H.T, atol=0) and np.allclose(S, S.T, atol=0)
+
+
 def test_first_order_sharded_partials_add_up(write_input):
     """Two ranks' shares of ham (tiles block-cyclic over the ranks, one-electron part on rank 0) sum to the
     single-rank matrices; ovl is complete on every rank."""

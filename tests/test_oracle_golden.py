@@ -77,3 +77,21 @@ def test_memoisation_changes_nothing(write_input):
     ra, rb = a.guess_energy(), b.guess_energy()
     a.close(); b.close()
     assert ra["energy"] == rb["energy"] and ra["counters"] == rb["counters"]
+
+
+@pytest.mark.parametrize("name,iorb", [("examples__h2o", 4), ("examples__h2o.SC", 1), ("examples__li", 2), ("examples__be.DBF", 2)])
+def test_first_order_matrices_reproduce_the_energy(name, iorb, write_input):
+    """Size-independent property of first_order_opt (valence.F90:527-764): with c the current weights of the orbital,
+    c^T ham c / c^T ovl c + E_nuc is the energy of the unsubstituted wave function (the reference's goldens pin
+    first_order_opt only through converged optimisations; this pins the matrices themselves)."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    from valence_b200 import inputs
+    path, _ = write_input(name)
+    inp = inputs.parse_file(path)
+    o = Oracle(path)
+    r = o.guess_energy()
+    H, S, _ = o.first_order(iorb)
+    o.close()
+    c = np.array([w for _, w in inp.orbitals[iorb - 1].terms])
+    assert abs(float(c @ H @ c / (c @ S @ c)) + r["enucrep"] - r["energy"]) < 1e-10
