@@ -323,10 +323,6 @@ void Engine::Impl::prepare(const Input& in, int subject)
     }
 }
 
-// One vsvb_energy evaluation (valence.F90:1010-1434) for the bra/ket lists in wf.
-//   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
-//             valence.F90:667 vs 674-704); null -> run the diagonal pass (schwarz_ints)
-//   diag_only: stop after the Schwarz table (returned in sch_out)
 // Entry-level overlap / core-Hamiltonian matrices and the cofactor densities of one bra/ket list pair
 // (wfndet, the 1e loop and the density set-up of vsvb_energy): leaves Se, He, Pa/Pb or cof on the device,
 // e1 and wfnorm in the object.
@@ -433,11 +429,14 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
     *fast_out = fast; *c0_out = c0; *ndp_out = ndp;
 }
 
+// One vsvb_energy evaluation (valence.F90:1010-1434) for the bra/ket lists in wf.
+//   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
+//             valence.F90:667 vs 674-704); null -> run the diagonal pass (schwarz_ints)
+//   diag_only: stop after the Schwarz table (returned in sch_out)
 void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::vector<double>* sch_in, bool diag_only,
                             int rank, int nranks, EnergyResult* out, std::vector<double>* sch_out)
 {
-    const int nso = wf.nso, nao = bas.nao;
-    (void)nao;
+    const int nso = wf.nso;
     double t1 = now_ms();
     bool fast = false;
     double c0 = 1.0;
