@@ -465,3 +465,18 @@ def test_lif_cluster_matches_oracle_and_full_lif128_runs(write_input):
     assert 0.0 < a["wfnorm"] <= 1.0
     per_pair = a["energy"] / 64.0            # 64 LiF units
     assert -108.0 < per_pair < -105.0        # 8 units: -427.96 Eh = -107.0 per unit
+
+
+def test_translation_invariance_on_32_waters(write_input):
+    """Size-independent property at a size the oracle cannot reach ((H2O)_32, 96 atoms): a rigid shift of the whole
+    cluster through the geometry-update call of the API leaves the energy unchanged."""
+    from valence_b200 import api, inputs
+    inp = inputs.water_cluster(32, tol=(10, 20, 10), rotate=True)
+    path, _ = write_input(inp)
+    eng = api.Engine(path)
+    r0 = eng.energy()
+    x = np.array(inp.coords, dtype=float) + np.array([1.37, -2.11, 0.59])
+    r1 = eng.energy(x.flatten())
+    eng.close()
+    assert abs(r1["energy"] - r0["energy"]) < 5e-9
+    assert abs(r1["enucrep"] - r0["enucrep"]) < 1e-9

@@ -95,3 +95,19 @@ def test_first_order_matrices_reproduce_the_energy(name, iorb, write_input):
     o.close()
     c = np.array([w for _, w in inp.orbitals[iorb - 1].terms])
     assert abs(float(c @ H @ c / (c @ S @ c)) + r["enucrep"] - r["energy"]) < 1e-10
+
+
+def test_oracle_energy_is_translation_invariant(write_input):
+    """Size-independent property used for the clusters no golden covers: a rigid shift of the whole system (the
+    geometry update of valence_api_calculate_energy, valence_api.F90:57-63) leaves the energy unchanged."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    from valence_b200 import inputs
+    inp = inputs.water_cluster(2, tol=(10, 20, 10), rotate=True)
+    path, _ = write_input(inp)
+    o = Oracle(path)
+    e0 = o.guess_energy()["energy"]
+    o.set_coords((np.array(inp.coords, dtype=float) + np.array([1.37, -2.11, 0.59])).flatten())
+    e1 = o.guess_energy()["energy"]
+    o.close()
+    assert abs(e1 - e0) < 1e-11
