@@ -354,6 +354,31 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         if (np == 0) return;
         std::vector<TmpSP> tsp;
         const size_t nshG = G.shells.size(), nshH = H.shells.size();
+        tsp.reserve(nshG * nshH);
+        if (pass == 1 && g != h) {
+            // whole group pair out of range: the shell-pair test below, bounded from above over all shell pairs of
+            // (G, H) (most diffuse exponents, largest weights, shortest / longest centre distance)
+            double eG = 1e300, eH = 1e300, cG = 0.0, cH = 0.0, d2min = 1e300, d2max = 0.0, dcmax = 0.0;
+            int lG = 0, lH = 0;
+            for (int X : G.shells) { eG = std::min(eG, sh_emin[X]); cG = std::max(cG, sh_cmax[X]); lG = std::max(lG, bas.shells[X].l); }
+            for (int Y : H.shells) { eH = std::min(eH, sh_emin[Y]); cH = std::max(cH, sh_cmax[Y]); lH = std::max(lH, bas.shells[Y].l); }
+            for (int X : G.shells)
+                for (int Y : H.shells) {
+                    const double dx = bas.shells[X].r[0] - bas.shells[Y].r[0], dy = bas.shells[X].r[1] - bas.shells[Y].r[1],
+                                 dz = bas.shells[X].r[2] - bas.shells[Y].r[2];
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    d2min = std::min(d2min, d2); d2max = std::max(d2max, d2);
+                    dcmax = std::max(dcmax, std::max(std::fabs(dx), std::max(std::fabs(dy), std::fabs(dz))));
+                }
+            const double pmin = eG + eH;
+            const double kb = cG * cH * std::exp(-eG * eH / pmin * d2min) * SQ2PI54 / pmin;
+            const double len = std::sqrt(d2max) + 1.0 / std::sqrt(pmin);
+            double db = dsum;
+            for (int k = 0; k < std::max(lG, lH); ++k) db *= 1.0 + dcmax;
+            double poly = 0.0, lp = 1.0;
+            for (int L = 0; L <= lG + lH; ++L) { poly += db * lp * ncart(L); lp *= 2.0 * len; }
+            if (!(kb * std::pow(2.0 * pmin, -0.25) * poly * wcut * 1.0001 * 1.01 >= tau)) return;
+        }
         for (size_t xi = 0; xi < nshG; ++xi)
             for (size_t yi = 0; yi < nshH; ++yi) {
                 const int X = G.shells[xi], Y = H.shells[yi];
@@ -392,6 +417,24 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                     if (!cX || !cY) continue;
                     const OrbShell* cA = sp.swapped ? cY : cX;
                     const OrbShell* cB = sp.swapped ? cX : cY;
+                    if (sb.l == 0) {
+                        // nothing to fold (e = a): same arithmetic as the general branch, without its scaffolding
+                        const double fb = bas.angn[coff(0)];
+                        bool nz0 = false;
+                        for (int a = 0; a < na; ++a) {
+                            const double v = cA->c[a] * bas.angn[coff(sa.l) + a] * cB->c[0] * fb;
+                            dcart[a] = v;
+                            nz0 = nz0 || v != 0.0;
+                        }
+                        if (!nz0) continue;
+                        for (int a = 0; a < na; ++a) {
+                            const double v = 0.0 + dcart[a];
+                            sp.dt[(size_t)a * np + ip] = v;
+                            dmaxL[sa.l] = std::max(dmaxL[sa.l], std::fabs(v));
+                            any = any || v != 0.0;
+                        }
+                        continue;
+                    }
                     bool nz = false;
                     for (int a = 0; a < na; ++a)
                         for (int b = 0; b < nb; ++b) {
@@ -411,10 +454,12 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                 }
                 if (!any) continue;   // no orbital pair has density on this shell pair
                 sp.wmax = 0.0;
+                if (pass == 1) sp.pp.reserve((size_t)sa.nprim * sb.nprim);
                 for (int ia = 0; ia < sa.nprim; ++ia)
                     for (int ib = 0; ib < sb.nprim; ++ib) {
                         double a = bas.exps[sa.prim_off + ia], b = bas.exps[sb.prim_off + ib], p = a + b;
-                        double K = bas.coefs[sa.prim_off + ia] * bas.coefs[sb.prim_off + ib] * std::exp(-a * b / p * AB2) * SQ2PI54;
+                        const double ex = AB2 == 0.0 ? 1.0 : std::exp(-a * b / p * AB2);   // exp(-0) = 1 exactly
+                        double K = bas.coefs[sa.prim_off + ia] * bas.coefs[sb.prim_off + ib] * ex * SQ2PI54;
                         if (K == 0.0) continue;
                         PrimPair pp;
                         pp.Px = (a * sa.r[0] + b * sb.r[0]) / p;
@@ -438,7 +483,18 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                     }
                 if (pass == 0) { out.wmax = std::max(out.wmax, sp.wmax); continue; }
                 if (sp.pp.empty()) continue;
-                std::stable_sort(sp.pp.begin(), sp.pp.end(), [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
+                // by decreasing weight, stable; a few primitives per shell pair on average: insertion sort (std::stable_sort
+                // allocates a buffer per call)
+                if (sp.pp.size() <= 12) {
+                    for (size_t i = 1; i < sp.pp.size(); ++i) {
+                        const PrimPair x = sp.pp[i];
+                        size_t j = i;
+                        for (; j > 0 && x.w > sp.pp[j - 1].w; --j) sp.pp[j] = sp.pp[j - 1];
+                        sp.pp[j] = x;
+                    }
+                } else {
+                    std::stable_sort(sp.pp.begin(), sp.pp.end(), [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
+                }
                 tsp.push_back(std::move(sp));
             }
         if (pass == 0 || tsp.empty()) return;
