@@ -82,6 +82,10 @@ int vb_engine_energy(vb_engine* e, vb_energy_result* out);
  * doubles at vb_engine_accum_device() over ranks (one NCCL all-reduce); every rank calls _finish. */
 int vb_engine_energy_partial(vb_engine* e, int rank, int nranks, vb_energy_result* out);
 int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out);
+/* optional, ranks of ONE node, before _partial: build this rank's share of the host tables and publish it as the file
+ * <prefix><rank> (use a /dev/shm path unique to the job); barrier; then _partial merges all shares instead of every
+ * rank building everything (the reference's ranks likewise split the set-up work by task index, valence.F90:1162). */
+int vb_engine_shard_tables(vb_engine* e, int rank, int nranks, const char* prefix);
 /* first_order_opt matrices (valence.F90:527-764) of 1-based orbital iorb: ham/ovl receive the
  * norbas x norbas column-major matrices <Psi[chi_ib]|H_el|Psi[chi_jb]>, <Psi[chi_ib]|Psi[chi_jb]>
  * (numerators: not divided by the norm, no nuclear repulsion); cap = doubles available in each. */

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <stdexcept>
 #include <vector>
 #include "../../valence_b200/csrc/vb_setup.h"
 using namespace vb;
@@ -91,6 +93,25 @@ int main(int argc, char** argv)
             for (int y = 0; y < nfree && !found; ++y) found = f.pgs[y].g == f.pgs[x].h && f.pgs[y].h == f.pgs[x].g && f.pgs[y].np == f.pgs[x].np;
             if (!found) { std::printf("free pair group (%d,%d) has no mirror\n", f.pgs[x].g, f.pgs[x].h); ++bad; break; }
         }
+    }
+    // table build shared by the ranks of one node (TileOpts::shard_mode): every rank publishes its share, then each
+    // merges all shares -- bitwise the tables of the plain build, for any number of ranks
+    for (int nranks : {2, 3}) {
+        const std::string prefix = std::string(argv[1]) + ".share" + std::to_string(nranks) + "_";
+        for (int r = 0; r < nranks; ++r) {
+            TileOpts o;
+            o.shard_mode = 1; o.shard_rank = r; o.shard_nranks = nranks; o.shard_prefix = prefix;
+            build(in, "2", true, o);
+        }
+        TileOpts o;
+        o.shard_mode = 2; o.shard_rank = nranks - 1; o.shard_nranks = nranks; o.shard_prefix = prefix;
+        TileSetup c = build(in, "3", true, o);
+        if (!same(a.pg_pairs, c.pg_pairs) || !same(a.sps, c.sps) || !same(a.pps, c.pps) || !same(a.pps_flat, c.pps_flat) ||
+            !same(a.dmat, c.dmat) || !same(a.pgs, c.pgs)) { std::printf("sharded build (%d ranks) differs from the plain build\n", nranks); ++bad; }
+        for (int r = 0; r < nranks; ++r) std::remove((prefix + std::to_string(r)).c_str());
+        bool threw = false;
+        try { build(in, "1", true, o); } catch (const std::exception&) { threw = true; }
+        if (!threw) { std::printf("missing shares are not detected\n"); ++bad; }
     }
     // compact Boys table against the exact series
     std::vector<double> tab(BOYS_S_SIZE);

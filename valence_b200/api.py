@@ -75,6 +75,7 @@ def load(build_if_needed: bool = True):
     L.vb_engine_stream.restype = C.c_void_p
     L.vb_engine_stream.argtypes = [C.c_void_p]
     L.vb_engine_first_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(CEnergyResult)]
+    L.vb_engine_shard_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
     L.vb_engine_first_order_sharded.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                                 C.POINTER(CEnergyResult)]
     L.vb_engine_run.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int)] * 2
@@ -190,7 +191,16 @@ class Engine:
         return r.asdict()
 
     def energy_distributed(self, rank: int, nranks: int) -> dict:
-        """Shard the tile list over ranks, one NCCL all-reduce of the accumulators."""
+        """Shard the tile list over ranks, one NCCL all-reduce of the accumulators.
+
+        VB_SHARD_SETUP=1 (ranks of ONE node): the host-side pair tables are built once per node instead of once per
+        rank -- every rank publishes its share under /dev/shm, a barrier, then each rank merges all shares."""
+        if nranks > 1 and os.environ.get("VB_SHARD_SETUP") == "1":
+            import torch.distributed as dist
+            key = os.environ.get("VB_SHARD_KEY") or f"{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}"
+            prefix = f"/dev/shm/valence_b200_{key}_"
+            self._check(self.L.vb_engine_shard_tables(self.h, rank, nranks, prefix.encode()))
+            dist.barrier()
         r = self.energy_partial(rank, nranks)
         if nranks > 1:
             import torch

@@ -176,6 +176,11 @@ int vb_engine_energy_partial(vb_engine* e, int rank, int nranks, vb_energy_resul
     });
 }
 
+int vb_engine_shard_tables(vb_engine* e, int rank, int nranks, const char* prefix)
+{
+    return guarded([&] { e->eng->shard_tables(rank, nranks, prefix ? prefix : ""); });
+}
+
 int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out)
 {
     return guarded([&] {

@@ -140,6 +140,10 @@ struct Engine::Impl {
     bool first_order_cached(const Input& in, const Wavefunction& wf, int es, int iorb, const std::vector<double>& sch, int rank, int nranks,
                             std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* acc);
     TileSetup ts_keep;                               // host tables of the last evaluation (storage kept)
+    // table build shared by the ranks of a node (Engine::shard_tables): consumed by the next energy_partial
+    bool shard_pending = false, prepared = false;
+    int shard_rank = 0, shard_nranks = 1;
+    std::string shard_prefix, shard_file;
     DBuf<double> gcache;                             // first_order_opt: orbital-level integrals of the subject-free tiles
     DBuf<int4> vtiles;
     DBuf<int> fo_perm;
@@ -185,6 +189,7 @@ Engine::~Engine()
 {
     if (!impl_) return;
     Impl& I = *impl_;
+    if (!I.shard_file.empty()) std::remove(I.shard_file.c_str());
     cudaSetDevice(I.device);
     if (I.st) cudaStreamSynchronize(I.st);
     for (cudaEvent_t ev : {I.ev0, I.ev1, I.ev2, I.ev3}) if (ev) cudaEventDestroy(ev);
@@ -452,7 +457,12 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     for (const GShell& gs : bas.shells) bas_lmax = std::max(bas_lmax, gs.l);
     const bool gen = bas_lmax >= 2;   // d shells: shell-pair kernel with the loop-based recurrence (k_tile<true>)
     TileSetup& ts = ts_keep;    // storage reused across calls (no zero-fill / page faults of ~0.6 GB per energy)
-    build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts);
+    TileOpts topts;
+    if (shard_pending) {       // every rank published its share of the pair groups (shard_tables); merge them
+        topts.shard_mode = 2; topts.shard_rank = shard_rank; topts.shard_nranks = shard_nranks; topts.shard_prefix = shard_prefix;
+        shard_pending = false;
+    }
+    build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts, topts);
     const double t_bt = now_ms();
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
@@ -671,14 +681,43 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
     Impl& I = *impl_;
     CK(cudaSetDevice(I.device));
     *out = EnergyResult();
-    I.launches = 0;
-    I.t_begin = now_ms();
-    g_h2d_bytes = 0; g_d2h_bytes = 0;
-    I.prepare(in_, -1);
+    if (!I.prepared) {      // otherwise shard_tables opened this evaluation
+        I.launches = 0;
+        I.t_begin = now_ms();
+        g_h2d_bytes = 0; g_d2h_bytes = 0;
+        I.prepare(in_, -1);
+    }
+    I.prepared = false;
     double t1 = now_ms();
     out->t_1e = t1 - I.t_begin;
     Wavefunction wf = default_wavefunction(in_);
     I.evaluate(in_, wf, nullptr, false, rank, nranks, out, nullptr);
+}
+
+// Table build shared by the ranks of one node.  One process per GPU means N ranks on one host build the same pair
+// tables N times per energy (the largest host cost of an 8-GPU step).  Here every rank builds the pair groups
+// i with (i / 16) mod N == rank and publishes them as the file prefix + rank (put the prefix on /dev/shm); after a
+// barrier of the caller (api.py: Engine.energy_distributed) the next energy_partial maps all N files and merges them:
+// the tables are bitwise those of an unsharded build (tests/host/test_setup_host.cpp).
+void Engine::shard_tables(int rank, int nranks, const std::string& prefix)
+{
+    Impl& I = *impl_;
+    CK(cudaSetDevice(I.device));
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("shard_tables: bad rank / nranks");
+    I.launches = 0;
+    I.t_begin = now_ms();
+    g_h2d_bytes = 0; g_d2h_bytes = 0;
+    I.prepare(in_, -1);
+    I.prepared = true;
+    int bas_lmax = 0;
+    for (const GShell& gs : I.bas.shells) bas_lmax = std::max(bas_lmax, gs.l);
+    const double tau_diag = std::min(I.tau, 0.01 * I.itol * I.itol);
+    TileOpts o;
+    o.shard_mode = 1; o.shard_rank = rank; o.shard_nranks = nranks; o.shard_prefix = prefix;
+    TileSetup scratch;
+    build_tiles(in_, I.bas, default_wavefunction(in_), I.orbs2e, tau_diag, bas_lmax < 2, &scratch, o);
+    I.shard_pending = true; I.shard_rank = rank; I.shard_nranks = nranks; I.shard_prefix = prefix;
+    I.shard_file = prefix + std::to_string(rank);
 }
 
 namespace {

@@ -1,9 +1,17 @@
 #include "vb_setup.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <functional>
+#include <cstdint>
+#include <stdexcept>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -329,6 +337,11 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         std::vector<PrimPair> pps;
         std::vector<double> dmat;
         double wmax = 0.0;
+        // what the merge reads: this object's own vectors, or a mapped share published by another rank
+        const int* v_pairs = nullptr; const SPRec* v_sps = nullptr; const PrimPair* v_pps = nullptr; const double* v_dmat = nullptr;
+        size_t n_pairs = 0, n_sps = 0, n_pps = 0, n_d = 0;
+        void view_own() { v_pairs = pairs.data(); v_sps = sps.data(); v_pps = pps.data(); v_dmat = dmat.data();
+                          n_pairs = pairs.size(); n_sps = sps.size(); n_pps = pps.size(); n_d = dmat.size(); }
     };
     // one pair group; pass 0 only measures the largest primitive weight, pass 1 emits
     auto do_pair_group = [&](int g, int h, int pass, double wcut, PGOut& out) {
@@ -538,6 +551,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             }
         }
         out.used = true;
+        out.view_own();
     };
     const bool dbg_t = std::getenv("VB_DEBUG_SETUP") != nullptr;
     auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -566,23 +580,123 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             for (int h = 0; h < (wf.sym ? g + 1 : ng); ++h)
                 if (g == g_iso || h == g_iso) gh.emplace_back(g, h);
     std::vector<PGOut> outs(gh.size());
-    {
+    auto host_threads = [&](size_t nwork, size_t serial_below) {
         int nthr = (int)std::thread::hardware_concurrency();
         if (const char* e = std::getenv("VB_HOST_THREADS")) nthr = std::atoi(e);
         nthr = std::max(1, std::min(nthr, 32));
-        if (gh.size() < 64) nthr = 1;
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            for (;;) {
-                size_t i0 = next.fetch_add(16);
-                if (i0 >= gh.size()) break;
-                for (size_t i = i0; i < std::min(gh.size(), i0 + 16); ++i) do_pair_group(gh[i].first, gh[i].second, 1, wcut, outs[i]);
-            }
-        };
+        if (nwork < serial_below) nthr = 1;
+        return nthr;
+    };
+    auto run_pool = [&](int nthr, const std::function<void()>& work) {
         std::vector<std::thread> pool;
         for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
         work();
         for (std::thread& t : pool) t.join();
+    };
+    // ownership of the pair groups when the build is shared by the ranks of a node: blocks of 16, round-robin
+    const int sh_n = opts.shard_mode ? std::max(1, opts.shard_nranks) : 1, sh_r = opts.shard_rank;
+    auto owned = [&](size_t i) { return (int)((i / 16) % (size_t)sh_n) == sh_r; };
+    // payload of a record: pps, sps, dmat, pairs -- every section 16-byte aligned (PrimPair / SPRec are)
+    struct alignas(16) ShardRec { uint64_t i, off, n_pairs, n_sps, n_pps, n_d; double wmax; PGDesc pg; };
+    constexpr size_t SHARD_HEAD = 32;
+    constexpr uint64_t SHARD_MAGIC = 0x56425348415244ull;
+    if (opts.shard_mode != 2) {
+        std::atomic<size_t> next{0};
+        run_pool(host_threads(gh.size(), 64), [&]() {
+            for (;;) {
+                size_t i0 = next.fetch_add(16);
+                if (i0 >= gh.size()) break;
+                if (opts.shard_mode == 1 && !owned(i0)) continue;
+                for (size_t i = i0; i < std::min(gh.size(), i0 + 16); ++i) do_pair_group(gh[i].first, gh[i].second, 1, wcut, outs[i]);
+            }
+        });
+    }
+    if (opts.shard_mode == 1) {
+        // publish this rank's pair groups: [magic, # group pairs, # records] records payload; written to a temporary
+        // name and renamed, so a reader never sees a partial file
+        std::vector<ShardRec> recs;
+        uint64_t off = 0;
+        for (size_t i = 0; i < outs.size(); ++i) {
+            const PGOut& o = outs[i];
+            if (!owned(i) || !o.used) continue;
+            ShardRec r;
+            std::memset(&r, 0, sizeof r);
+            r.i = i; r.off = off; r.n_pairs = o.pairs.size(); r.n_sps = o.sps.size(); r.n_pps = o.pps.size(); r.n_d = o.dmat.size();
+            r.wmax = o.wmax; r.pg = o.pg;
+            off += r.n_pairs * sizeof(int) + r.n_sps * sizeof(SPRec) + r.n_pps * sizeof(PrimPair) + r.n_d * sizeof(double);
+            off = (off + 15) & ~(uint64_t)15;
+            recs.push_back(r);
+        }
+        const uint64_t head[4] = {SHARD_MAGIC, (uint64_t)gh.size(), (uint64_t)recs.size(), 0};
+        static_assert(sizeof head == SHARD_HEAD && sizeof(ShardRec) % 16 == 0, "share layout");
+        const size_t base = SHARD_HEAD + recs.size() * sizeof(ShardRec), total = base + off;
+        const std::string fin = opts.shard_prefix + std::to_string(sh_r), tmp = fin + ".tmp";
+        const int fd = open(tmp.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0600);
+        char* buf = nullptr;
+        if (fd >= 0 && ftruncate(fd, (off_t)total) == 0) {
+            void* mp = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            if (mp != MAP_FAILED) buf = static_cast<char*>(mp);
+        }
+        if (fd >= 0) close(fd);
+        if (!buf) throw std::runtime_error("valence_b200: cannot create the table share " + tmp);
+        std::memcpy(buf, head, sizeof head);
+        if (!recs.empty()) std::memcpy(buf + SHARD_HEAD, recs.data(), recs.size() * sizeof(ShardRec));
+        {
+            std::atomic<size_t> nx{0};
+            run_pool(host_threads(recs.size(), 256), [&]() {
+                for (size_t k; (k = nx.fetch_add(1)) < recs.size();) {
+                    const ShardRec& r = recs[k];
+                    const PGOut& o = outs[r.i];
+                    char* p = buf + base + r.off;
+                    std::memcpy(p, o.pps.data(), r.n_pps * sizeof(PrimPair)); p += r.n_pps * sizeof(PrimPair);
+                    std::memcpy(p, o.sps.data(), r.n_sps * sizeof(SPRec)); p += r.n_sps * sizeof(SPRec);
+                    std::memcpy(p, o.dmat.data(), r.n_d * sizeof(double)); p += r.n_d * sizeof(double);
+                    std::memcpy(p, o.pairs.data(), r.n_pairs * sizeof(int));
+                }
+            });
+        }
+        munmap(buf, total);
+        if (std::rename(tmp.c_str(), fin.c_str()) != 0) throw std::runtime_error("valence_b200: cannot publish the table share " + fin);
+        return;
+    }
+    struct Mapping { void* p; size_t n; };
+    struct Mappings { std::vector<Mapping> v; ~Mappings() { for (Mapping& m : v) munmap(m.p, m.n); } } maps;
+    if (opts.shard_mode == 2) {
+        // the shares are mapped, not copied: the merge below reads them straight from the page cache
+        std::vector<char> seen(gh.size(), 0);
+        for (int r = 0; r < sh_n; ++r) {
+            const std::string fn = opts.shard_prefix + std::to_string(r);
+            const int fd = open(fn.c_str(), O_RDONLY);
+            if (fd < 0) throw std::runtime_error("valence_b200: table share " + fn + " is missing");
+            struct stat sb;
+            void* mp = MAP_FAILED;
+            if (fstat(fd, &sb) == 0 && sb.st_size >= (off_t)SHARD_HEAD) mp = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            close(fd);
+            if (mp == MAP_FAILED) throw std::runtime_error("valence_b200: cannot map the table share " + fn);
+            maps.v.push_back({mp, (size_t)sb.st_size});
+            const char* buf = static_cast<const char*>(mp);
+            const size_t bsz = (size_t)sb.st_size;
+            uint64_t head[4];
+            std::memcpy(head, buf, sizeof head);
+            if (head[0] != SHARD_MAGIC || head[1] != gh.size() || SHARD_HEAD + head[2] * sizeof(ShardRec) > bsz)
+                throw std::runtime_error("valence_b200: table share " + fn + " does not belong to this build");
+            const ShardRec* recs = reinterpret_cast<const ShardRec*>(buf + SHARD_HEAD);
+            const size_t nrec = (size_t)head[2], base = SHARD_HEAD + nrec * sizeof(ShardRec);
+            for (size_t k = 0; k < nrec; ++k) {
+                const ShardRec& rc = recs[k];
+                if (rc.i >= gh.size() || seen[rc.i]) throw std::runtime_error("valence_b200: table shares overlap");
+                seen[rc.i] = 1;
+                PGOut& o = outs[rc.i];
+                const char* p = buf + base + rc.off;
+                if (base + rc.off + rc.n_pairs * sizeof(int) + rc.n_sps * sizeof(SPRec) + rc.n_pps * sizeof(PrimPair) + rc.n_d * sizeof(double) > bsz)
+                    throw std::runtime_error("valence_b200: table share " + fn + " is truncated");
+                o.v_pps = reinterpret_cast<const PrimPair*>(p); o.n_pps = rc.n_pps; p += rc.n_pps * sizeof(PrimPair);
+                o.v_sps = reinterpret_cast<const SPRec*>(p); o.n_sps = rc.n_sps; p += rc.n_sps * sizeof(SPRec);
+                o.v_dmat = reinterpret_cast<const double*>(p); o.n_d = rc.n_d; p += rc.n_d * sizeof(double);
+                o.v_pairs = reinterpret_cast<const int*>(p); o.n_pairs = rc.n_pairs;
+                o.pg = rc.pg; o.wmax = rc.wmax; o.used = true;
+            }
+        }
     }
     const double tt2 = tnow();
     // merge: offsets by a serial scan, the copies (and the magnitude sort of the flat lists) on the host cores
@@ -594,7 +708,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             offs[i] = run;
             const PGOut& o = outs[i];
             if (!o.used) continue;
-            run.pairs += o.pairs.size(); run.sps += o.sps.size(); run.pps += o.pps.size(); run.d += o.dmat.size(); run.pg += 1;
+            run.pairs += o.n_pairs; run.sps += o.n_sps; run.pps += o.n_pps; run.d += o.n_d; run.pg += 1;
             if (i < n_free_gh) { ts.n_free_pg = run.pg; ts.n_free_pairs = run.pairs / 2; ts.n_free_sps = run.sps; ts.n_free_pps = run.pps; ts.n_free_d = run.d; }
         }
         ts.pg_pairs.resize(run.pairs); ts.sps.resize(run.sps); ts.pps.resize(run.pps); ts.dmat.resize(run.d); ts.pgs.resize(run.pg);
@@ -616,19 +730,19 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                     pg.pair_beg = (int)(f.pairs / 2);
                     pg.d_off = (long long)f.d;
                     for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += pp0; pg.sp_beg[t] += sp0; }
-                    for (SPRec& r : o.sps) r.pp_beg += pp0;
-                    std::copy(o.pairs.begin(), o.pairs.end(), ts.pg_pairs.begin() + f.pairs);
-                    std::copy(o.sps.begin(), o.sps.end(), ts.sps.begin() + f.sps);
-                    std::copy(o.pps.begin(), o.pps.end(), ts.pps.begin() + f.pps);
-                    std::copy(o.dmat.begin(), o.dmat.end(), ts.dmat.begin() + f.d);
+                    std::copy(o.v_pairs, o.v_pairs + o.n_pairs, ts.pg_pairs.begin() + f.pairs);
+                    std::copy(o.v_sps, o.v_sps + o.n_sps, ts.sps.begin() + f.sps);
+                    for (size_t k = 0; k < o.n_sps; ++k) ts.sps[f.sps + k].pp_beg += pp0;
+                    std::copy(o.v_pps, o.v_pps + o.n_pps, ts.pps.begin() + f.pps);
+                    std::copy(o.v_dmat, o.v_dmat + o.n_d, ts.dmat.begin() + f.d);
                     if (flat) {   // one magnitude-sorted list per pair type (each primitive carries its shell pair's e-offset)
                         std::vector<int> idx;
                         for (int t = 0; t < NPTYPE; ++t) {
                             const int b0 = pg.pp_beg[t] - pp0, b1 = pg.pp_beg[t + 1] - pp0;
                             idx.resize(b1 - b0);
                             for (int k = 0; k < b1 - b0; ++k) idx[k] = b0 + k;
-                            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return o.pps[x].w > o.pps[y].w; });
-                            for (int k = 0; k < b1 - b0; ++k) ts.pps_flat[f.pps + b0 + k] = o.pps[idx[k]];
+                            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return o.v_pps[x].w > o.v_pps[y].w; });
+                            for (int k = 0; k < b1 - b0; ++k) ts.pps_flat[f.pps + b0 + k] = o.v_pps[idx[k]];
                         }
                     }
                     ts.pgs[f.pg] = pg;
@@ -650,9 +764,9 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         if (!o.used) continue;
         const PGDesc& pg = ts.pgs[offs[i].pg];
         ts.max_npp = std::max(ts.max_npp, pg.pp_beg[NPTYPE] - pg.pp_beg[0]);
-        ts.max_nsp = std::max(ts.max_nsp, (int)o.sps.size());
+        ts.max_nsp = std::max(ts.max_nsp, (int)o.n_sps);
         int ks[NPTYPE] = {0, 0, 0, 0, 0, 0};
-        for (const SPRec& r : o.sps) ks[r.type] += pt_ne(r.type);
+        for (size_t k = 0; k < o.n_sps; ++k) ks[o.v_sps[k].type] += pt_ne(o.v_sps[k].type);
         for (int t = 0; t < NPTYPE; ++t) ts.max_ks = std::max(ts.max_ks, ks[t]);
         ts.max_ne = std::max(ts.max_ne, pg.ne);
         ts.max_np = std::max(ts.max_np, pg.np);

@@ -3,6 +3,7 @@
 // primitive-pair tables and HRR-folded pair densities for the GPU kernels.
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 
 #include "vb_eri.cuh"
@@ -99,6 +100,13 @@ struct TileOpts {
     bool only_subject = false;
     double wcut = 0.0;
     bool measure_only = false;      // only compute TileSetup::wmax (of the isolated group alone with only_subject)
+    // Table build shared by the ranks of one node (one process per GPU builds the same tables: N ranks on one host would
+    // do the same work N times).  shard_mode 1: build this rank's share of the pair groups and publish it as the file
+    // shard_prefix + rank (shared memory, e.g. /dev/shm/...), nothing else; shard_mode 2: take every pair group from the
+    // published files of all ranks and merge -- tables bitwise identical to an unsharded build.  The caller
+    // synchronises the ranks between the two calls.
+    int shard_mode = 0, shard_rank = 0, shard_nranks = 1;
+    std::string shard_prefix;
 };
 
 double dblfac(int n);
