@@ -181,6 +181,7 @@ def run_ours(args) -> None:
     # cluster, tiles sharded over the ranks, one all-reduce of the accumulators and one of ham.  The (ib,jb) loop reuses
     # the integrals of all tiles that do not touch the substituted orbital from an HBM cache.
     grad = None
+    os.environ.setdefault("VB_FO_REQUIRE_CACHE", "1")      # never fall back to 36 full tile passes inside the bench
     if args.grad_waters != 0:
         gw = args.waters if args.grad_waters < 0 else args.grad_waters
         ge, gp = eng, None
@@ -190,16 +191,19 @@ def run_ours(args) -> None:
             ge.energy_distributed(rank, world)
         barrier()
         t0g = time.perf_counter()
-        rg = ge.energy_distributed(rank, world)
-        Hg, Sg, st = ge.first_order_distributed(1, rank, world)
-        barrier()
-        tg = red(time.perf_counter() - t0g, R.MAX if R else None)
-        import numpy as np
-        cw = np.array([w for _, w in vin.water_cluster(gw, tol=(10, 20, 10)).orbitals[0].terms])
-        grad = {"waters": gw, "ms": 1e3 * tg, "orbital": 1, "matrix_order": int(Hg.shape[0]),
-                "first_order_kernel_ms": red(st["t_tiles_ms"], R.MAX if R else None),
-                "kernel_launches": int(st["launches"]),
-                "rayleigh_quotient_minus_energy": float(cw @ Hg @ cw / (cw @ Sg @ cw)) + rg["enucrep"] - rg["energy"]}
+        try:
+            rg = ge.energy_distributed(rank, world)
+            Hg, Sg, st = ge.first_order_distributed(1, rank, world)
+            barrier()
+            tg = red(time.perf_counter() - t0g, R.MAX if R else None)
+            import numpy as np
+            cw = np.array([w for _, w in vin.water_cluster(gw, tol=(10, 20, 10)).orbitals[0].terms])
+            grad = {"waters": gw, "ms": 1e3 * tg, "orbital": 1, "matrix_order": int(Hg.shape[0]),
+                    "first_order_kernel_ms": red(st["t_tiles_ms"], R.MAX if R else None),
+                    "kernel_launches": int(st["launches"]),
+                    "rayleigh_quotient_minus_energy": float(cw @ Hg @ cw / (cw @ Sg @ cw)) + rg["enucrep"] - rg["energy"]}
+        except RuntimeError as ex:      # metric 2 must never cost the headline line
+            grad = {"waters": gw, "error": str(ex)[:200]}
         if gp is not None:
             ge.close(); os.unlink(gp)
     dev_ms = sum(r["t_1e_ms"] + r["t_density_ms"] + r["t_diag_ms"] + r["t_tiles_ms"] for r in results) / args.steps

@@ -155,15 +155,25 @@ class Engine:
         ovl = np.zeros(cap)
         n = C.c_int(0)
         r = CEnergyResult()
-        self._check(self.L.vb_engine_first_order_sharded(self.h, iorb, rank, nranks, ham.ctypes.data, ovl.ctypes.data, cap, C.byref(n),
-                                                         C.byref(r)))
+        err = None
+        try:
+            self._check(self.L.vb_engine_first_order_sharded(self.h, iorb, rank, nranks, ham.ctypes.data, ovl.ctypes.data, cap, C.byref(n),
+                                                             C.byref(r)))
+        except RuntimeError as ex:      # keep the ranks in step: agree on failure before the all-reduce of ham
+            err = ex
         k = n.value
         if nranks > 1:
             import torch
             import torch.distributed as dist
+            ok = torch.tensor([0.0 if err else 1.0], dtype=torch.float64, device=f"cuda:{self.device}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 0.5:
+                raise RuntimeError(f"first_order failed on a rank: {err}" if err else "first_order failed on another rank")
             t = torch.from_numpy(ham[:k * k].copy()).to(f"cuda:{self.device}")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             ham[:k * k] = t.cpu().numpy()
+        elif err:
+            raise err
         return ham[:k * k].reshape(k, k).T.copy(), ovl[:k * k].reshape(k, k).T.copy(), r.asdict()
 
     def run(self, print_output: bool = False) -> dict:

@@ -879,7 +879,13 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
         const double need = (double)my_tiles * cfg.g_cap * 8.0;
         double cap = 0.8 * ((double)fr + (double)gcache.cap * 8.0);
         if (const char* e = std::getenv("VB_FO_CACHE_MB")) cap = std::min(cap, std::atof(e) * 1048576.0);
-        if (need > cap) return false;
+        if (need > cap) {
+            // the plain loop regenerates every integral norbas(norbas+1)/2 times: a caller that cannot afford that
+            // (bench.py on large clusters) asks for an error instead
+            if (const char* e = std::getenv("VB_FO_REQUIRE_CACHE"))
+                if (std::atoi(e) != 0) throw std::runtime_error("valence_b200: the integral cache of first_order_opt does not fit in device memory");
+            return false;
+        }
     }
     if (cfg.smem > PT_SMEM_MAX) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
     gcache.alloc((size_t)std::max<long long>(1, my_tiles) * cfg.g_cap);
