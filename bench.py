@@ -135,6 +135,9 @@ def run_ours(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # all ranks of the node build their host tables at the same time: share the cores instead of oversubscribing them
+        # (the tables do not depend on the thread count: tests/host/test_setup_host.cpp)
+        os.environ.setdefault("VB_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // world)))
     torch.cuda.set_device(local)
     path = make_input(args.waters)
     eng = api.Engine(path, device=local)
