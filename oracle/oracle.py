@@ -31,13 +31,19 @@ class Result(C.Structure):
                 ("numerator", C.c_double), ("cnt", Counters)]
 
 
+class FastResult(C.Structure):
+    _fields_ = [("enucrep", C.c_double), ("energy", C.c_double), ("wfnorm", C.c_double),
+                ("numerator", C.c_double), ("cnt", Counters), ("prim_quartets", C.c_longlong),
+                ("blocks", C.c_longlong), ("seconds", C.c_double)]
+
+
 class RunResult(C.Structure):
     _fields_ = [("enucrep", C.c_double), ("guess_energy", C.c_double), ("total_energy", C.c_double),
                 ("converged", C.c_int), ("iterations", C.c_int), ("failed", C.c_int)]
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(HERE, f) for f in ("valence_oracle.c", "vo_opt.inc", "vo_integrals.c", "vo_internal.h")]
+    src = [os.path.join(HERE, f) for f in ("valence_oracle.c", "vo_opt.inc", "vo_fast.c", "vo_integrals.c", "vo_internal.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
         subprocess.check_call(["make", "-C", HERE, "-s", "-B"])
     return LIB
@@ -56,6 +62,10 @@ def lib():
         L.vo_guess_energy.argtypes = [C.c_void_p, C.c_int, C.POINTER(Result)]
         L.vo_first_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(Counters)]
         L.vo_run.argtypes = [C.c_void_p, C.POINTER(RunResult)]
+        L.vo_fast_guess_energy.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(FastResult)]
+        L.vo_fast_first_order.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(Counters)]
+        L.vo_fast_boys.restype = C.c_double
+        L.vo_fast_boys.argtypes = [C.c_int, C.c_double]
         L.vo_count_tasks.argtypes = [C.c_void_p, C.POINTER(Counters)]
         L.vo_set_quiet.argtypes = [C.c_void_p, C.c_int]
         L.vo_set_memo.argtypes = [C.c_void_p, C.c_int]
@@ -112,6 +122,28 @@ class Oracle:
         self.L.vo_guess_energy(self.h, nrank, C.byref(r))
         return {"enucrep": r.enucrep, "energy": r.energy, "wfnorm": r.wfnorm,
                 "numerator": r.numerator, "counters": r.cnt.asdict()}
+
+    def fast_guess_energy(self, nthreads: int = 0, thr: float = 0.0) -> dict:
+        """guess_energy through the fast (inverse-form, AO-block) oracle path, vo_fast.c."""
+        r = FastResult()
+        rc = self.L.vo_fast_guess_energy(self.h, nthreads, thr, C.byref(r))
+        if rc != 0:
+            raise RuntimeError("fast oracle: input outside its limits (spin-coupled pairs or singular overlap block)")
+        return {"enucrep": r.enucrep, "energy": r.energy, "wfnorm": r.wfnorm, "numerator": r.numerator,
+                "counters": r.cnt.asdict(), "prim_quartets": int(r.prim_quartets), "seconds": r.seconds}
+
+    def fast_first_order(self, iorb: int, nthreads: int = 0, thr: float = 0.0):
+        """ham, ovl of first_order_opt for 1-based orbital iorb through the fast path."""
+        hd = C.c_int(0)
+        cnt = Counters()
+        big = 64
+        ham = np.zeros(big * big)
+        ovl = np.zeros(big * big)
+        n = self.L.vo_fast_first_order(self.h, iorb, nthreads, thr, ham.ctypes.data, ovl.ctypes.data, C.byref(hd), C.byref(cnt))
+        if n < 0:
+            raise RuntimeError("fast oracle: input outside its limits")
+        h = hd.value
+        return ham[:h * h].reshape(h, h).T[:n, :n].copy(), ovl[:h * h].reshape(h, h).T[:n, :n].copy()
 
     def count_tasks(self) -> dict:
         """Screening / task counters of guess_energy without the 2e integrals and determinants."""

@@ -1379,6 +1379,7 @@ double vo_orbital_ovl(vo_ctx *c, int io, int jo) { ovint(c, io, jo); return c->s
 double vo_orbital_h(vo_ctx *c, int io, int jo) { int1e(c, io, jo); return c->hint; }
 
 #include "vo_opt.inc"
+#include "vo_fast.c"
 
 void vo_free(vo_ctx *c)
 {

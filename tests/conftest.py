@@ -17,7 +17,18 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json"))
+    """Reference inputs with the reference's golden numbers (make_golden.py); the fast__*.json files are the fast
+    oracle's fixtures for the synthetic benchmark inputs (make_fast_fixtures.py)."""
+    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json") and not f.startswith("fast__"))
+
+
+def fast_fixture(case):
+    with open(os.path.join(GOLDEN, f"fast__{case}.json")) as fh:
+        return json.load(fh)
+
+
+def fast_fixture_names():
+    return sorted(f[6:-5] for f in os.listdir(GOLDEN) if f.startswith("fast__") and f.endswith(".json"))
 
 
 def load_golden(name):

@@ -55,7 +55,7 @@ def load(build_if_needed: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_needed and _build.stale():
+    if build_if_needed and not os.environ.get("VB_LIB_SUFFIX") and _build.stale():   # experiment variants are prebuilt
         _build.build()
     if not os.path.exists(_build.LIB):
         raise RuntimeError("libvalence_b200.so is missing: the CUDA extension is required (no CPU path)")

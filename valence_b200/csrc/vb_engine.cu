@@ -19,6 +19,7 @@
 #include "vb_kernels.cuh"
 #include "vb_tilelist.h"
 #include "vb_ptile.cuh"
+#include "vb_pclass.cuh"
 #include "vb_tile.cuh"
 
 namespace vb {
@@ -104,6 +105,92 @@ double flops_prim_quartet(int tb, int tk)
     }
     f += (double)(NE - coff(LA)) * (NF - coff(LC));   // accumulation into the contracted block
     return f;
+}
+
+
+// ---- class-split tile pass (vb_pclass.cuh): one launch per integral class into gbuf, then (optionally) the contraction ----
+struct ClassPlan {
+    bool present[3][3];
+    ClassCfg cfg[3];
+    size_t smem[3][3];
+    bool ok = true;
+};
+
+ClassPlan plan_classes(const std::vector<PGDesc>& pgs)
+{
+    ClassPlan pl;
+    int mx_d[3] = {0, 0, 0}, mx_sp[3] = {0, 0, 0}, mx_pp[3] = {0, 0, 0};
+    bool bra[3] = {false, false, false};
+    for (const PGDesc& pg : pgs)
+        for (int t = 0; t < 3; ++t) {
+            const int nsp = pg.sp_beg[t + 1] - pg.sp_beg[t], npp = pg.pp_beg[t + 1] - pg.pp_beg[t];
+            if (nsp > 0 && npp > 0) bra[t] = true;
+            mx_d[t] = std::max(mx_d[t], nsp * pt_ne(t) * pg.np);
+            mx_sp[t] = std::max(mx_sp[t], nsp);
+            mx_pp[t] = std::max(mx_pp[t], npp);
+        }
+    for (int tb = 0; tb < 3; ++tb) {
+        pl.cfg[tb].d_cap = ((mx_d[tb] + 3) & ~1) + 2;
+        pl.cfg[tb].sp_cap = std::max(1, mx_sp[tb]);
+        pl.cfg[tb].pp_cap = std::max(1, mx_pp[tb]);
+        for (int tk = 0; tk < 3; ++tk) {
+            pl.present[tb][tk] = bra[tb] && bra[tk];
+            const int nw = pc_threads(tb, tk) / 32;
+            pl.smem[tb][tk] = ((size_t)pl.cfg[tb].d_cap + (size_t)nw * PT_SCRATCH + BOYS_S_SIZE) * sizeof(double) +
+                              (size_t)pl.cfg[tb].sp_cap * sizeof(SPRec) + (size_t)pl.cfg[tb].pp_cap * sizeof(PrimPair);
+            if (pl.present[tb][tk] && pl.smem[tb][tk] > PT_SMEM_MAX) pl.ok = false;
+        }
+    }
+    return pl;
+}
+
+template <int TB, int TK>
+void launch_class(const TileArgs& A, const ClassPlan& pl, int nsm, int nitems, cudaStream_t st)
+{
+    const size_t smem = pl.smem[TB][TK];
+    CK(cudaFuncSetAttribute(k_pclass<TB, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pclass<TB, TK>, pc_threads(TB, TK), smem));
+    per_sm = std::max(1, per_sm);
+    const int grid = std::max(1, std::min(nsm * per_sm, nitems));
+    k_pclass<TB, TK><<<grid, pc_threads(TB, TK), smem, st>>>(A, pl.cfg[TB]);
+    CK(cudaGetLastError());
+}
+
+// all classes of the items A.items[0 .. A.nitems) into A.gbuf (zeroed here); returns the number of launches
+int run_class_pass(TileArgs A, const ClassPlan& pl, int nsm, long long ntile_slots, unsigned int* counter, cudaStream_t st, float* ms_class /* 9 or null */,
+                   cudaEvent_t e0, cudaEvent_t e1)
+{
+    CK(cudaMemsetAsync(A.gbuf, 0, (size_t)ntile_slots * A.g_cap * sizeof(double), st));
+    int n = 0;
+    // heaviest classes first
+    static const int order[9][2] = {{2, 2}, {2, 1}, {1, 2}, {2, 0}, {0, 2}, {1, 1}, {1, 0}, {0, 1}, {0, 0}};
+    for (const auto& c : order) {
+        const int tb = c[0], tk = c[1];
+        if (!pl.present[tb][tk]) continue;
+        CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+        if (ms_class) CK(cudaEventRecord(e0, st));
+        switch (tb * 3 + tk) {
+            case 0: launch_class<0, 0>(A, pl, nsm, A.nitems, st); break;
+            case 1: launch_class<0, 1>(A, pl, nsm, A.nitems, st); break;
+            case 2: launch_class<0, 2>(A, pl, nsm, A.nitems, st); break;
+            case 3: launch_class<1, 0>(A, pl, nsm, A.nitems, st); break;
+            case 4: launch_class<1, 1>(A, pl, nsm, A.nitems, st); break;
+            case 5: launch_class<1, 2>(A, pl, nsm, A.nitems, st); break;
+            case 6: launch_class<2, 0>(A, pl, nsm, A.nitems, st); break;
+            case 7: launch_class<2, 1>(A, pl, nsm, A.nitems, st); break;
+            default: launch_class<2, 2>(A, pl, nsm, A.nitems, st); break;
+        }
+        if (ms_class) {
+            CK(cudaEventRecord(e1, st));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            ms_class[tb * 3 + tk] += ms;
+        }
+        ++n;
+    }
+    return n;
 }
 
 }  // namespace
@@ -594,9 +681,39 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.sch = this->sch.p; A.tileE = tileE.p;
     bool split = false;   // VB_SPLIT=1: separate heavy / light launches (measured slower: 5.97 s vs 5.46 s on (H2O)_256)
     if (const char* e = std::getenv("VB_SPLIT")) split = std::atoi(e) != 0;
+    bool csplit = !gen;   // class-split pass (vb_pclass.cuh); VB_CLASS_SPLIT=0 selects the all-in-one kernel
+    if (const char* e = std::getenv("VB_CLASS_SPLIT")) csplit = csplit && std::atoi(e) != 0;
+    ClassPlan cplan;
+    if (csplit) { cplan = plan_classes(ts.pgs); csplit = cplan.ok; }
     CK(cudaEventRecord(ev2, st));
     if (gen) {
         if (mine > 0) launch((int)mine, PART_ALL);
+    } else if (mine > 0 && csplit) {
+        long long cap_mb = 24576;
+        if (const char* e = std::getenv("VB_GBUF_MB")) cap_mb = std::max(1, std::atoi(e));
+        const long long chunk_tiles = std::max<long long>(PT_MAXQ, cap_mb * 1024 * 1024 / ((long long)g_cap * 8));
+        gbuf.alloc((size_t)std::min(my_tiles, chunk_tiles) * g_cap);
+        A.gbuf = gbuf.p; A.tile_first = 0; A.tile_stride = 1;
+        float msc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ms_con = 0.f;
+        for (size_t i0 = 0; i0 < itl.size();) {
+            size_t i1 = i0;
+            long long nt = 0;
+            while (i1 < itl.size() && nt + itl[i1].y <= chunk_tiles) { nt += itl[i1].y; ++i1; }
+            A.items = reinterpret_cast<const int4*>(items.p + i0); A.nitems = (int)(i1 - i0); A.gslot_base = itl[i0].z;
+            launches += run_class_pass(A, cplan, nsm, nt, counter.p, st, dbg_time ? msc : nullptr, ev0, ev1);
+            if (dbg_time) CK(cudaEventRecord(ev0, st));
+            k_contract_items<<<std::max(1, (int)std::min<long long>(((long long)A.nitems * PT_MAXQ + 7) / 8, (long long)nsm * 16)), CI_THREADS, 0, st>>>(A, nt);
+            CK(cudaGetLastError());
+            launches++;
+            if (dbg_time) { CK(cudaEventRecord(ev1, st)); CK(cudaEventSynchronize(ev1)); float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev0, ev1)); ms_con += ms; }
+            out->tile_launches += 1;
+            i0 = i1;
+        }
+        if (dbg_time) {
+            std::printf("[time] class pass:");
+            for (int c = 0; c < 9; ++c) std::printf(" (%d|%d) %.1f", c / 3, c % 3, msc[c]);
+            std::printf(" ms; contraction %.1f ms\n", ms_con);
+        }
     } else if (mine > 0 && !split) {
         A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itl.size(); A.tile_first = 0; A.tile_stride = 1;
         launch((int)mine, PART_ALL);
@@ -615,9 +732,18 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             while (i1 < itl.size() && nt + itl[i1].y <= chunk_tiles) { nt += itl[i1].y; ++i1; }
             A.items = reinterpret_cast<const int4*>(items.p + i0); A.nitems = (int)(i1 - i0); A.gslot_base = itl[i0].z;
             counter.zero(st);
+            if (dbg_time) CK(cudaEventRecord(ev0, st));
             launch((int)(i1 - i0), PART_HEAVY);
+            if (dbg_time) CK(cudaEventRecord(ev1, st));
             counter.zero(st);
             launch((int)(i1 - i0), PART_LIGHT);
+            if (dbg_time) {
+                CK(cudaEventRecord(ev3, st));
+                CK(cudaStreamSynchronize(st));
+                float mh = 0.f, ml = 0.f;
+                CK(cudaEventElapsedTime(&mh, ev0, ev1)); CK(cudaEventElapsedTime(&ml, ev1, ev3));
+                std::printf("[time] split chunk: heavy %.1f ms, light %.1f ms\n", mh, ml);
+            }
             out->tile_launches += 1;
             i0 = i1;
         }

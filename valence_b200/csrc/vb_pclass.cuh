@@ -1,0 +1,262 @@
+// Class-split form of the fused hot path (s/p basis sets): ONE launch per integral class (TB|TK), TB/TK in
+// {ss, ps, pp}, all of them accumulating the orbital-level integrals G[q][p] of every tile in an HBM/L2-resident
+// buffer with FP64 reductions, followed by one contraction launch (k_contract_items) that screens and contracts
+// the tiles with the cofactor densities exactly as the reference does (contract_tile, vb_ptile.cuh).
+//
+// Why (measured on B200, profiles/r2_*): the all-in-one kernel k_ptile<PART_ALL> is 250 KB of unrolled code in
+// which 12 warps per SM sit in nine different class bodies (instruction-fetch stalls as frequent as issues), and
+// its register allocation is dictated by the (pp|pp) body (168 registers + 5.5 KB of spills per thread) although
+// 90 % of the primitive quartets belong to the four light classes.  Here every class is its own small kernel with
+// its own register budget and occupancy, only the tables of ITS pair types are staged (TMA bulk), and the inner
+// loop can afford instruction-level parallelism.
+//
+// The arithmetic is that of vb_ptile.cuh (same formulation: lane = ket primitive x bra shell pair, in-lane
+// contraction over the bra primitives, two DMMA transforms); pruning is per lane (own ket weight).
+// (replaces int2e, valence.F90:3184-3438, and the 2e loop of vsvb_energy, :1153-1433)
+#pragma once
+#include "vb_ptile.cuh"
+
+namespace vb {
+
+struct ClassCfg {           // shared-memory capacities of one class launch (host: max over the pair groups)
+    int d_cap;              // doubles for the staged bra densities of pair type TB (+2 slack for the alignment shift)
+    int sp_cap, pp_cap;     // bra shell pairs / primitive pairs of type TB
+};
+
+#ifndef VB_PC_ILP
+#define VB_PC_ILP 1
+#endif
+
+// One warp task: a ket octet of pair type TK against every bra primitive of type TB of P.
+template <int TB, int TK>
+__device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP, int pp_base, int e_beg, const PGDesc& Q, int oct,
+                                            const PrimPair* __restrict__ bpps, const SPRec* __restrict__ spss,
+                                            const double* __restrict__ Dp_s /* first row = e_beg */, const double* __restrict__ Dq_g,
+                                            const double* __restrict__ boys_tab, double* __restrict__ scratch,
+                                            double* __restrict__ Gglob, int lane, unsigned long long* __restrict__ s_pq)
+{
+    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    const int g = lane >> 2, t = lane & 3;
+    const int nk = Q.pp_beg[TK + 1] - Q.pp_beg[TK];
+    const PrimPair* __restrict__ kl = A.pps_flat + Q.pp_beg[TK];
+    const int k0 = 8 * oct;
+    const bool kact = k0 + g < nk;
+    PrimPair b = kl[k0 + (kact ? g : 0)];
+    if (!kact) { b.Kp = 0.0; b.w = 0.0; }
+    const double wk = kl[k0].w;                        // the octet's largest magnitude (lists are sorted)
+    const double wl = b.w;                             // this lane's own ket magnitude
+    double X[NF][4][2];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { X[f][j][0] = 0.0; X[f][j][1] = 0.0; }
+    unsigned nq = 0;                                    // primitive quartets evaluated by this lane
+    for (int q0 = 0; q0 < nsp; q0 += 4) {
+        // shell pairs are sorted by contraction length, not by weight: test the quad's own bound
+        const bool sact = q0 + t < nsp;
+        const SPRec sp = spss[q0 + (sact ? t : 0)];
+        const bool swanted = sact && sp.wmax * wl >= A.tau;
+        if (!__any_sync(0xffffffffu, sact && sp.wmax * wk >= A.tau)) continue;
+        const int cnt = swanted ? sp.pp_cnt : 0;
+        const PrimPair* __restrict__ bl = bpps + (sp.pp_beg - pp_base);
+        double acc[NE * NF];
+#pragma unroll
+        for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+        int ip = 0;
+        for (;; ++ip) {
+            // primitives of a shell pair are sorted by magnitude: a lane that stops stays stopped
+            PrimPair a = bl[ip < cnt ? ip : 0];
+            const bool act = ip < cnt && a.w * wl >= A.tau;
+            if (!__any_sync(0xffffffffu, act)) break;
+            if (!act) a.Kp = 0.0;
+            quartet_values<TB, TK>(boys_tab, a, b, acc);
+            nq += act ? 1u : 0u;
+        }
+        if (ip > 0) feed_dmma<TB, TK>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
+    }
+    for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
+    if (!nq) return;
+    if (lane == 0) atomicAdd(s_pq, (unsigned long long)nq);
+    // G[q][p] += sum_{k,f} Dq[e_k + f][q] X_f[k][p]:  A'[q][k] from the ket densities, B'[k][p] = X_f re-laid out
+    // through the warp's scratch (C fragment -> B fragment)
+    double C[4][4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
+    const int eo_own = b.eoff;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            scratch[g * PT_SLD + 8 * j + 2 * t] = X[f][j][0];
+            scratch[g * PT_SLD + 8 * j + 2 * t + 1] = X[f][j][1];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int kk = 4 * s + t;                                   // ket primitive this lane supplies
+            const int eo = __shfl_sync(0xffffffffu, eo_own, 4 * kk);    // lane 4*kk evaluates primitive kk
+            double bfr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bfr[j] = scratch[kk * PT_SLD + 8 * j + g];
+            const double* arow = Dq_g + (eo + f) * Q.np;                // read once per task: straight from L2
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int q = 8 * m + g;
+                const double af = q < Q.np ? arow[q] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_884(C[m][j][0], C[m][j][1], af, bfr[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int q = 8 * m + g;
+        if (q >= Q.np) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int p = 8 * j + 2 * t + i;
+                if (p < npP) atomicAdd(&Gglob[q * npP + p], C[m][j][i]);
+            }
+    }
+}
+
+__host__ __device__ constexpr int pc_threads(int tb, int tk) { return (tb == 2 || tk == 2) ? 256 : 256; }
+__host__ __device__ constexpr int pc_minblocks(int tb, int tk) { return (tb == 2 || tk == 2) ? 1 : ((tb + tk == 0) ? 3 : 2); }
+
+// Persistent kernel of one class.  Work item = bra pair group P with up to PT_MAXQ ket pair groups (consecutive tiles);
+// G of tile j of the item lives at gbuf[(item.z + j - gslot_base) * g_cap].
+template <int TB, int TK>
+__global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pclass(const TileArgs A, const ClassCfg C)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int THREADS = pc_threads(TB, TK), nw = THREADS / 32, NE = pt_ne(TB);
+    double* Dp_s = smem;                                                   // bra densities of type TB
+    double* scr = Dp_s + C.d_cap;                                          // per-warp X scratch
+    double* boys_sm = scr + nw * PT_SCRATCH;                               // compact Boys table
+    SPRec* sps_s = reinterpret_cast<SPRec*>(boys_sm + BOYS_S_SIZE);        // bra shell pairs of type TB
+    PrimPair* bpp_s = reinterpret_cast<PrimPair*>(sps_s + C.sp_cap);       // bra primitive pairs of type TB
+    for (int i = threadIdx.x; i < BOYS_S_SIZE; i += THREADS) boys_sm[i] = A.boys_small[i];
+    __shared__ unsigned long long s_bar;
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __shared__ int s_item, s_unit;
+    __shared__ int s_cum[PT_MAXQ + 1];
+    __shared__ unsigned long long s_pq;
+    __shared__ PGDesc s_P, s_Q[PT_MAXQ];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_pq = 0ull;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
+        __syncthreads();
+        const long long it = (long long)s_item;
+        if (it >= A.nitems) break;
+        const int4 item = A.items[it];                          // first tile, # tiles, slot of the first tile in gbuf
+        const int tl0 = item.x, ntl = item.y;
+        {
+            constexpr int W = sizeof(PGDesc) / 4;
+            const int2 t0 = A.tiles[tl0];
+            if (warp == 0)
+                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_P)[i] = reinterpret_cast<const int*>(A.pgs + t0.x)[i];
+            for (int qi = warp; qi < ntl; qi += nw) {
+                const int y = A.tiles[tl0 + qi].y;
+                for (int i = lane; i < W; i += 32) reinterpret_cast<int*>(&s_Q[qi])[i] = reinterpret_cast<const int*>(A.pgs + y)[i];
+            }
+        }
+        __syncthreads();
+        const PGDesc& P = s_P;
+        const int nsp = P.sp_beg[TB + 1] - P.sp_beg[TB], nbpp = P.pp_beg[TB + 1] - P.pp_beg[TB];
+        if (nsp == 0 || nbpp == 0) continue;
+        int e_beg = 0;                                          // first e-row of pair type TB inside P's density block
+#pragma unroll
+        for (int t = 0; t < TB; ++t) e_beg += (P.sp_beg[t + 1] - P.sp_beg[t]) * pt_ne(t);
+        const long long o = P.d_off + (long long)e_beg * P.np;  // TMA wants 16-byte alignment: copy from the even element below
+        const int shift = (int)(o & 1);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned bd = (unsigned)(((shift + nsp * NE * P.np + 1) & ~1) * sizeof(double));
+            const unsigned bb = (unsigned)(nbpp * sizeof(PrimPair));
+            const unsigned bs = (unsigned)(nsp * sizeof(SPRec));
+            mbar_expect_tx(&s_bar, bd + bb + bs);
+            tma_bulk_g2s(Dp_s, A.dmat + (o - shift), bd, &s_bar);
+            tma_bulk_g2s(sps_s, A.sps + P.sp_beg[TB], bs, &s_bar);
+            tma_bulk_g2s(bpp_s, A.pps + P.pp_beg[TB], bb, &s_bar);
+            int n = 0;
+            for (int qi = 0; qi < PT_MAXQ; ++qi) {
+                s_cum[qi] = n;
+                if (qi < ntl) {
+                    const int nk = s_Q[qi].pp_beg[TK + 1] - s_Q[qi].pp_beg[TK];
+                    if (nk > 0 && P.kwmax[TB] * s_Q[qi].kwmax[TK] >= A.tau) n += (nk + 7) >> 3;
+                }
+            }
+            s_cum[PT_MAXQ] = n;
+            s_unit = 0;
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        __syncthreads();
+        const int nunits = s_cum[PT_MAXQ];
+        double* scratch = scr + warp * PT_SCRATCH;
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_unit, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= nunits) break;
+            int qi = 0;
+            while (s_cum[qi + 1] <= u) ++qi;
+            const int oct = u - s_cum[qi];
+            const PGDesc& Q = s_Q[qi];
+            double* Gglob = A.gbuf + ((size_t)item.z + qi - A.gslot_base) * A.g_cap;
+            pclass_task<TB, TK>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, &s_pq);
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_pq) atomicAdd(&A.pq_counters[TB * NPTYPE + TK], s_pq);
+}
+
+// Contraction of the finished tiles of a chunk of work items with the cofactor densities: one tile per warp,
+// reference screening / bookkeeping in contract_tile (valence.F90:1153-1433).
+constexpr int CI_THREADS = 256;
+__global__ void __launch_bounds__(CI_THREADS, 2) k_contract_items(const TileArgs A, long long ntile_slots)
+{
+    __shared__ unsigned long long s_cnt[CNT_N];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < CNT_N) s_cnt[tid] = 0ull;
+    __syncthreads();
+    unsigned long long cnt[CNT_N];
+#pragma unroll
+    for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
+    const long long nwarps = (long long)gridDim.x * (CI_THREADS / 32);
+    for (long long w = (long long)blockIdx.x * (CI_THREADS / 32) + (tid >> 5); w < (long long)A.nitems * PT_MAXQ; w += nwarps) {
+        const int4 item = A.items[w / PT_MAXQ];
+        const int j = (int)(w % PT_MAXQ);
+        if (j >= item.y) continue;
+        const int2 tq = A.tiles[item.x + j];
+        const TileIdx P{A.pgs[tq.x].np, A.pgs[tq.x].pair_beg}, Q{A.pgs[tq.y].np, A.pgs[tq.y].pair_beg};
+        const double* __restrict__ src = A.gbuf + ((size_t)item.z + j - A.gslot_base) * A.g_cap;
+        const int npP = P.np;
+        auto gv = [&](int p, int q) { return __ldcs(&src[q * npP + p]); };
+        double epart = A.sym ? contract_tile<32, true>(A, P, Q, gv, lane, cnt) : contract_tile<32, false>(A, P, Q, gv, lane, cnt);
+        for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
+        if (lane == 0) A.tileE[item.x + j] = epart * A.c0;
+    }
+    (void)ntile_slots;
+#pragma unroll
+    for (int i = 0; i < CNT_N; ++i) {
+        unsigned long long c = cnt[i];
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(&s_cnt[i], c);
+    }
+    __syncthreads();
+    if (tid < CNT_N && s_cnt[tid]) atomicAdd(&A.counters[tid], s_cnt[tid]);
+}
+
+}  // namespace vb

@@ -47,6 +47,9 @@ __host__ __device__ constexpr bool pt_class_in_part(int part, int tb, int tk)
 {
     return part == PART_ALL || ((tb < 2 && tk < 2) == (part == PART_LIGHT));
 }
+#ifndef VB_EXP_SKIP
+#define VB_EXP_SKIP 0     // experiment builds only: 1 no contraction, 2 no second transform / G reduction, 4 no first transform, 8 no integrals
+#endif
 constexpr int PT_SLD = 33;                      // row stride of the per-warp X scratch (8 x 32 doubles)
 constexpr int PT_SCRATCH = 8 * PT_SLD + 1;      // doubles per warp (odd row stride, even total keeps the next region aligned)
 
@@ -145,10 +148,16 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
                 const bool act = ip < cnt && a.w * wk >= A.tau;
                 if (!__any_sync(0xffffffffu, act)) break;
                 if (!act) a.Kp = 0.0;
-                quartet_values<TB, TK>(boys_tab, a, b, acc);
+                if ((VB_EXP_SKIP & 8) && A.mode == 1) acc[0] += a.Kp * b.Kp;
+                else quartet_values<TB, TK>(boys_tab, a, b, acc);
                 nq += (act && kact) ? 1u : 0u;
             }
-            if (ip > 0) feed_dmma<TB, TK>(acc, sp.eoff, Dp_s, P.np, g, X);
+            if ((VB_EXP_SKIP & 4) && A.mode == 1) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NE * NF; ++i) sacc += acc[i];
+                X[0][0][0] += sacc;
+            } else if (ip > 0) feed_dmma<TB, TK>(acc, sp.eoff, Dp_s, P.np, g, X);
         }
         for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
         if (nq) {
@@ -157,6 +166,15 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
         }
     });
     if (!any) return;
+    if ((VB_EXP_SKIP & 2) && A.mode == 1) {
+        double sx = 0.0;
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sx += X[f][j][0] + X[f][j][1];
+        if (sx == 1.2345e301) scratch[lane] = sx;
+        return;
+    }
     // G[q][p] += sum_{k,f} Dq[e_k + f][q] X_f[k][p]:  A'[q][k] from the staged ket densities, B'[k][p] = X_f
     // re-laid out through the warp's scratch (C fragment -> B fragment).
     double C[4][4][2];
@@ -459,7 +477,7 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
         unsigned long long cnt[CNT_N];
 #pragma unroll
         for (int i = 0; i < CNT_N; ++i) cnt[i] = 0ull;
-        for (int qi = 0; qi < ntl; ++qi) {
+        for (int qi = 0; qi < (((VB_EXP_SKIP & 1) && A.mode == 1) ? 0 : ntl); ++qi) {
             const double* G_s = Gs + qi * A.g_cap;
             const int npP = P.np;
             const TileIdx Pi{P.np, P.pair_beg}, Qi{s_Q[qi].np, s_Q[qi].pair_beg};
