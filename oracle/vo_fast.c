@@ -749,7 +749,7 @@ static void f_block(const f_pg *P, const f_pg *Q, double thr, double *E, long lo
 }
 
 /* ---- the reference's task bookkeeping for one integral value ------------------------------------------- */
-typedef struct { double e2; vo_counters cnt; } f_acc;
+typedef struct { long double e2; vo_counters cnt; } f_acc;   /* extended-precision accumulation of the task sum */
 
 static long long f_tri(int a, int b) { return (long long)a * (a - 1) / 2 + b; }   /* xm_dtriang: ij = i(i-1)/2 + j, i >= j, 1-based */
 #define F_SCH(F, a, b) ((F)->c->schwarz[indx(a, b)])
@@ -814,8 +814,8 @@ static void f_visit(const f_ctx *F, int a, int b, int c_, int d, double V, f_acc
         }
         if (!(fabs(val) > c->itol)) continue;                                              /* :1286-1287 */
         if (role == 0) acc->cnt.value_erep++; else acc->cnt.value_exch++;
-        double s = f_spin_sum(F, io, jo, ko, lo, role) * val;
-        if (sym && !(ko == io && lo == jo)) s = s * 2.0;                                   /* :1420-1428 */
+        long double s = (long double)f_spin_sum(F, io, jo, ko, lo, role) * val;
+        if (sym && !(ko == io && lo == jo)) s = s * 2.0L;                                   /* :1420-1428 */
         acc->e2 += s;                           /* erep_sum - exchanged_erep_sum: the exchange sign sits in the cofactor */
     }
 }
@@ -953,7 +953,7 @@ static void f_set_smax(f_ctx *F)
     }
 }
 
-typedef struct { f_ctx *F; long long *blk; double *eblk; f_acc *accs; long long *npq; } f_blk_job;
+typedef struct { f_ctx *F; long long *blk; long double *eblk; f_acc *accs; long long *npq; } f_blk_job;
 static void f_blk_one(void *ctx, long long k, int tid)
 {
     f_blk_job *J = (f_blk_job *)ctx;
@@ -972,11 +972,9 @@ static void f_blk_one(void *ctx, long long k, int tid)
         J->npq[tid] += npq;
         if (cacheable) { double *keep = DARR((size_t)P->np * Q->np); memcpy(keep, E, sizeof(double) * (size_t)P->np * Q->np); F->cache[J->blk[k]] = keep; }
     }
-    double before = acc->e2;
-    acc->e2 = 0.0;
+    acc->e2 = 0.0L;
     f_visit_block(F, P, Q, P == Q, Eu, acc);
     J->eblk[k] = acc->e2;
-    acc->e2 = before;
 }
 
 /* vsvb_energy (valence.F90:1010-1434) for the current lists: numerator energy and wfnorm, counters into c->cnt */
@@ -986,7 +984,7 @@ static int f_vsvb_energy(f_ctx *F, double *energy_out, double *wfnorm_out, long 
     if (!f_cofactors(F)) return -1;
     const int nnd = F->nnd, nelec = c->nelec, nso = F->nso;
     /* 1e part (:1072-1106) */
-    double e1 = 0.0, wn = 0.0;
+    long double e1 = 0.0L, wn = 0.0L;
     for (int i = 1; i <= nelec; ++i) {
         int i_is_docc = i > nnd;
         for (int j = 1; j <= nelec; ++j) {
@@ -994,10 +992,10 @@ static int f_vsvb_energy(f_ctx *F, double *energy_out, double *wfnorm_out, long 
             if (i_is_docc && j_is_docc && (i % 2) != (j % 2)) continue;
             double d1 = f_c1(F, i, j);
             size_t k = (size_t)(f_entry_of_slot(F, i) - 1) * nso + (f_entry_of_slot(F, j) - 1);
-            wn += F->Se[k] * d1; e1 += F->He[k] * d1;
+            wn += (long double)F->Se[k] * d1; e1 += (long double)F->He[k] * d1;
         }
     }
-    wn = wn / (double)nelec;
+    wn = wn / (long double)nelec;
     /* 2e part: blocks (P,Q), P >= Q, that can hold an integral passing the Schwarz screen */
     f_set_smax(F);
     const long long npg = F->npg;
@@ -1006,7 +1004,7 @@ static int f_vsvb_energy(f_ctx *F, double *energy_out, double *wfnorm_out, long 
     for (long long p = 0; p < npg; ++p)
         for (long long q = 0; q <= p; ++q)
             if (F->pg[p].np && F->pg[q].np && F->pg[p].smax * F->pg[q].smax > c->itol) blk[nblk++] = p * npg + q;
-    double *eblk = DARR(nblk);
+    long double *eblk = (long double *)xcalloc((size_t)nblk + 1, sizeof(long double));
     const int nthr = 64;
     f_acc *accs = (f_acc *)xcalloc((size_t)nthr, sizeof(f_acc));
     long long npq_tot = 0;
@@ -1014,9 +1012,9 @@ static int f_vsvb_energy(f_ctx *F, double *energy_out, double *wfnorm_out, long 
     f_parfor(nblk, 16, f_blk_one, &J);
     for (int t = 0; t < 64; ++t) npq_tot += J.npq[t];
     free(J.npq);
-    /* fixed-order compensated sum of the block energies: reproducible for any thread count */
-    double e2 = 0.0, comp = 0.0;
-    for (long long k = 0; k < nblk; ++k) { double y = eblk[k] - comp, t = e2 + y; comp = (t - e2) - y; e2 = t; }
+    /* fixed-order extended-precision sum of the block energies: reproducible for any thread count */
+    long double e2 = 0.0L;
+    for (long long k = 0; k < nblk; ++k) e2 += eblk[k];
     for (int t = 0; t < nthr; ++t) {
         c->cnt.schwarz_erep += accs[t].cnt.schwarz_erep; c->cnt.schwarz_exch += accs[t].cnt.schwarz_exch;
         c->cnt.shortcut += accs[t].cnt.shortcut; c->cnt.int2e_calls += accs[t].cnt.int2e_calls;
@@ -1024,8 +1022,9 @@ static int f_vsvb_energy(f_ctx *F, double *energy_out, double *wfnorm_out, long 
         c->cnt.shell_quartets += accs[t].cnt.shell_quartets; c->cnt.shell_quartets_2e += accs[t].cnt.shell_quartets_2e;
     }
     free(accs); free(eblk); free(blk);
-    *energy_out = F->c0 * (e1 + e2);
-    *wfnorm_out = F->c0 * wn;
+    if (getenv("VO_FAST_DEBUG")) fprintf(stderr, "[fast] e1/c0 %.17Lg e2/c0 %.17Lg trace/nelec %.17Lg c0 %.17g\n", e1, e2, wn, F->c0);
+    *energy_out = (double)(F->c0 * (e1 + e2));
+    *wfnorm_out = (double)(F->c0 * wn);
     if (npq_out) *npq_out = npq_tot;
     return 0;
 }

@@ -203,7 +203,7 @@ struct Engine::Impl {
     std::vector<std::vector<double>> coeff;          // current orbital weights (normalised in energy())
     std::vector<double> xyz_angs;
     // device data
-    DBuf<double> boys, boys_small, gbuf, gred, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
+    DBuf<double> boys, boys_small, gbuf, gred, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, gj_res, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket;
     DBuf<double> oc;
@@ -473,9 +473,24 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
                 CK(cudaLaunchCooperativeKernel((void*)k_gj_inverse_grid, dim3(grid), dim3(1024), args, 0, st));
                 launches++;
             };
+            // one refinement step with a double-double residual (k_inv_residual_dd): M is gathered again (the
+            // elimination destroyed it), R = I - M X, X <- X + X R; the buffers swap roles
+            auto refine = [&](DBuf<double>& M, DBuf<double>& Minv, const DBuf<int>& ent, int n) {
+                if (n == 0) return;
+                if (const char* e = std::getenv("VB_INV_REFINE")) if (std::atoi(e) == 0) return;
+                k_gather_block<<<(n * n + 255) / 256, 256, 0, st>>>(Se.p, nso, ent.p, ent.p, n, M.p);
+                gj_res.alloc((size_t)n * n);
+                const dim3 g((n + RF_T - 1) / RF_T, (n + RF_T - 1) / RF_T), b(RF_T, RF_T);
+                k_inv_residual_dd<<<g, b, 0, st>>>(M.p, Minv.p, n, gj_res.p);
+                k_inv_update<<<g, b, 0, st>>>(Minv.p, gj_res.p, n, M.p);
+                CK(cudaGetLastError());
+                launches += 3;
+                std::swap(M.p, Minv.p); std::swap(M.cap, Minv.cap); std::swap(M.n, Minv.n);
+            };
             invert(Ma, Mai, na, gjout.p);
+            refine(Ma, Mai, ea_bra, na);
             if (same) CK(cudaMemcpyAsync(gjout.p + 2, gjout.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            else invert(Mb, Mbi, nb, gjout.p + 2);
+            else { invert(Mb, Mbi, nb, gjout.p + 2); refine(Mb, Mbi, eb_bra, nb); }
             std::vector<double> g;
             gjout.download(g, st);
             out->min_pivot_ratio = std::min(g[1], g[3]);

@@ -361,6 +361,52 @@ __global__ void __launch_bounds__(1024) k_gj_inverse_grid(double* __restrict__ A
     }
 }
 
+// One step of iterative refinement of the Gauss-Jordan inverse: R = I - M X with every dot product accumulated
+// in double-double (error-free products through FMA, two-sum accumulation), then X' = X + X R.  The inverse
+// enters E = numerator / wfnorm with weights of order |E| ~ 1e4 Eh, so its n * eps ~ 1e-13 relative error would
+// show at the 1e-10 Eh level for clusters of a few hundred orbitals; after this step X is accurate to a few ulp.
+constexpr int RF_T = 16;
+__global__ void __launch_bounds__(RF_T * RF_T) k_inv_residual_dd(const double* __restrict__ M, const double* __restrict__ X, int n,
+                                                                 double* __restrict__ R)
+{
+    __shared__ double sm[RF_T][RF_T + 1], sx[RF_T][RF_T + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * RF_T + ty, j = blockIdx.x * RF_T + tx;
+    double hi = 0.0, lo = 0.0;
+    for (int k0 = 0; k0 < n; k0 += RF_T) {
+        sm[ty][tx] = (i < n && k0 + tx < n) ? M[(size_t)i * n + k0 + tx] : 0.0;
+        sx[ty][tx] = (k0 + ty < n && j < n) ? X[(size_t)(k0 + ty) * n + j] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RF_T; ++k) {
+            const double a = sm[ty][k], b = sx[k][tx];
+            const double p = __dmul_rn(a, b), e = __fma_rn(a, b, -p);
+            const double t = __dadd_rn(hi, p), bp = __dsub_rn(t, hi);
+            const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(t, bp)), __dsub_rn(p, bp));
+            hi = t;
+            lo = __dadd_rn(lo, __dadd_rn(err, e));
+        }
+        __syncthreads();
+    }
+    if (i < n && j < n) R[(size_t)i * n + j] = __dsub_rn(__dsub_rn(i == j ? 1.0 : 0.0, hi), lo);
+}
+__global__ void __launch_bounds__(RF_T * RF_T) k_inv_update(const double* __restrict__ X, const double* __restrict__ R, int n, double* __restrict__ Xn)
+{
+    __shared__ double sa[RF_T][RF_T + 1], sb[RF_T][RF_T + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * RF_T + ty, j = blockIdx.x * RF_T + tx;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < n; k0 += RF_T) {
+        sa[ty][tx] = (i < n && k0 + tx < n) ? X[(size_t)i * n + k0 + tx] : 0.0;
+        sb[ty][tx] = (k0 + ty < n && j < n) ? R[(size_t)(k0 + ty) * n + j] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RF_T; ++k) acc += sa[ty][k] * sb[k][tx];
+        __syncthreads();
+    }
+    if (i < n && j < n) Xn[(size_t)i * n + j] = X[(size_t)i * n + j] + acc;
+}
+
 // entry-level density of one spin block: P[s][t] = Minv[pos_ket(t)][pos_bra(s)], 0 when an entry has no slot of this spin
 __global__ void k_entry_density(const double* __restrict__ Minv, int n, const int* __restrict__ pos_bra,
                                 const int* __restrict__ pos_ket, int nso, double* __restrict__ P)

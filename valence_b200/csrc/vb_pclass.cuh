@@ -23,12 +23,47 @@ struct ClassCfg {           // shared-memory capacities of one class launch (hos
     int sp_cap, pp_cap;     // bra shell pairs / primitive pairs of type TB
 };
 
-#ifndef VB_PC_ILP
-#define VB_PC_ILP 1
+// kets per lane (KB): every lane carries KB ket primitives through the bra loop -- KB independent dependency chains
+// per lane (the loop is latency-bound: 8 resident warps per scheduler at most), one bra-primitive load, one loop
+// head and one density-fragment load for KB quartets, and one reduction of G per KB octets.
+#ifndef VB_KB_SS
+#define VB_KB_SS 2
 #endif
+#ifndef VB_KB_SP
+#define VB_KB_SP 2
+#endif
+#ifndef VB_KB_PSPS
+#define VB_KB_PSPS 1
+#endif
+#ifndef VB_KB_PP
+#define VB_KB_PP 1
+#endif
+__host__ __device__ constexpr int pc_kb(int tb, int tk)
+{
+    return (tb == 2 || tk == 2) ? VB_KB_PP : (tb + tk == 0 ? VB_KB_SS : (tb + tk == 1 ? VB_KB_SP : VB_KB_PSPS));
+}
 
-// One warp task: a ket octet of pair type TK against every bra primitive of type TB of P.
-template <int TB, int TK>
+// the quartet values of KB kets go straight into the tensor cores: X[kb]_f[k][p] += sum_b A[k][b] Dp[e_b + e][p]
+template <int TB, int TK, int KB>
+__device__ __forceinline__ void feed_dmma_kb(const double (&acc)[KB][pt_ne(TB) * pt_ne(TK)], int eoff, const double* __restrict__ Dp_s,
+                                             int npP, int g, double (&X)[KB][pt_ne(TK)][4][2])
+{
+    constexpr int NE = pt_ne(TB), NF = pt_ne(TK);
+    const double* drow = Dp_s + eoff * npP + g;        // B[t][n = 8j + g] = Dp[e_sp + e][8j + g]
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double bf = drow[e * npP + 8 * j];
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) dmma_884(X[kb][f][j][0], X[kb][f][j][1], acc[kb][e * NF + f], bf);
+        }
+}
+
+// One warp task: KB consecutive ket octets of pair type TK against every bra primitive of type TB of P.
+template <int TB, int TK, int KB>
 __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP, int pp_base, int e_beg, const PGDesc& Q, int oct,
                                             const PrimPair* __restrict__ bpps, const SPRec* __restrict__ spss,
                                             const double* __restrict__ Dp_s /* first row = e_beg */, const double* __restrict__ Dq_g,
@@ -39,75 +74,91 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
     const int g = lane >> 2, t = lane & 3;
     const int nk = Q.pp_beg[TK + 1] - Q.pp_beg[TK];
     const PrimPair* __restrict__ kl = A.pps_flat + Q.pp_beg[TK];
-    const int k0 = 8 * oct;
-    const bool kact = k0 + g < nk;
-    PrimPair b = kl[k0 + (kact ? g : 0)];
-    if (!kact) { b.Kp = 0.0; b.w = 0.0; }
-    const double wk = kl[k0].w;                        // the octet's largest magnitude (lists are sorted)
-    const double wl = b.w;                             // this lane's own ket magnitude
-    double X[NF][4][2];
+    const int k0 = 8 * KB * oct;
+    PrimPair b[KB];
+    double wl[KB];                                     // this lane's own ket magnitudes (non-increasing in kb: the list is sorted)
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
+    for (int kb = 0; kb < KB; ++kb) {
+        const bool kact = k0 + 8 * kb + g < nk;
+        b[kb] = kl[kact ? k0 + 8 * kb + g : k0];
+        if (!kact) { b[kb].Kp = 0.0; b[kb].w = 0.0; }
+        wl[kb] = b[kb].w;
+    }
+    const double wk = kl[k0].w;                        // the task's largest magnitude
+    double X[KB][NF][4][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { X[f][j][0] = 0.0; X[f][j][1] = 0.0; }
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { X[kb][f][j][0] = 0.0; X[kb][f][j][1] = 0.0; }
     unsigned nq = 0;                                    // primitive quartets evaluated by this lane
     for (int q0 = 0; q0 < nsp; q0 += 4) {
         // shell pairs are sorted by contraction length, not by weight: test the quad's own bound
         const bool sact = q0 + t < nsp;
         const SPRec sp = spss[q0 + (sact ? t : 0)];
-        const bool swanted = sact && sp.wmax * wl >= A.tau;
         if (!__any_sync(0xffffffffu, sact && sp.wmax * wk >= A.tau)) continue;
-        const int cnt = swanted ? sp.pp_cnt : 0;
+        const int cnt = (sact && sp.wmax * wl[0] >= A.tau) ? sp.pp_cnt : 0;
         const PrimPair* __restrict__ bl = bpps + (sp.pp_beg - pp_base);
-        double acc[NE * NF];
+        double acc[KB][NE * NF];
 #pragma unroll
-        for (int i = 0; i < NE * NF; ++i) acc[i] = 0.0;
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int i = 0; i < NE * NF; ++i) acc[kb][i] = 0.0;
         int ip = 0;
         for (;; ++ip) {
             // primitives of a shell pair are sorted by magnitude: a lane that stops stays stopped
-            PrimPair a = bl[ip < cnt ? ip : 0];
-            const bool act = ip < cnt && a.w * wl >= A.tau;
+            const PrimPair a = bl[ip < cnt ? ip : 0];
+            const bool act = ip < cnt && a.w * wl[0] >= A.tau;
             if (!__any_sync(0xffffffffu, act)) break;
-            if (!act) a.Kp = 0.0;
-            quartet_values<TB, TK>(boys_tab, a, b, acc);
-            nq += act ? 1u : 0u;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                const bool actk = kb == 0 ? act : (act && a.w * wl[kb] >= A.tau);
+                PrimPair ak = a;
+                if (!actk) ak.Kp = 0.0;
+                quartet_values<TB, TK>(boys_tab, ak, b[kb], acc[kb]);
+                nq += actk ? 1u : 0u;
+            }
         }
-        if (ip > 0) feed_dmma<TB, TK>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
+        if (ip > 0) feed_dmma_kb<TB, TK, KB>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
     }
     for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
     if (!nq) return;
     if (lane == 0) atomicAdd(s_pq, (unsigned long long)nq);
     // G[q][p] += sum_{k,f} Dq[e_k + f][q] X_f[k][p]:  A'[q][k] from the ket densities, B'[k][p] = X_f re-laid out
-    // through the warp's scratch (C fragment -> B fragment)
+    // through the warp's scratch (C fragment -> B fragment); all KB octets accumulate into one C
     double C[4][4][2];
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
-    const int eo_own = b.eoff;
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        __syncwarp();
+    for (int kb = 0; kb < KB; ++kb) {
+        const int eo_own = b[kb].eoff;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            scratch[g * PT_SLD + 8 * j + 2 * t] = X[f][j][0];
-            scratch[g * PT_SLD + 8 * j + 2 * t + 1] = X[f][j][1];
-        }
-        __syncwarp();
+        for (int f = 0; f < NF; ++f) {
+            __syncwarp();
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int kk = 4 * s + t;                                   // ket primitive this lane supplies
-            const int eo = __shfl_sync(0xffffffffu, eo_own, 4 * kk);    // lane 4*kk evaluates primitive kk
-            double bfr[4];
+            for (int j = 0; j < 4; ++j) {
+                scratch[g * PT_SLD + 8 * j + 2 * t] = X[kb][f][j][0];
+                scratch[g * PT_SLD + 8 * j + 2 * t + 1] = X[kb][f][j][1];
+            }
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bfr[j] = scratch[kk * PT_SLD + 8 * j + g];
-            const double* arow = Dq_g + (eo + f) * Q.np;                // read once per task: straight from L2
+            for (int s = 0; s < 2; ++s) {
+                const int kk = 4 * s + t;                                   // ket primitive this lane supplies
+                const int eo = __shfl_sync(0xffffffffu, eo_own, 4 * kk);    // lane 4*kk evaluates primitive kk
+                double bfr[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int q = 8 * m + g;
-                const double af = q < Q.np ? arow[q] : 0.0;
+                for (int j = 0; j < 4; ++j) bfr[j] = scratch[kk * PT_SLD + 8 * j + g];
+                const double* arow = Dq_g + (eo + f) * Q.np;                // read once per task: straight from L2
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_884(C[m][j][0], C[m][j][1], af, bfr[j]);
+                for (int m = 0; m < 4; ++m) {
+                    const int q = 8 * m + g;
+                    const double af = q < Q.np ? arow[q] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma_884(C[m][j][0], C[m][j][1], af, bfr[j]);
+                }
             }
         }
     }
@@ -125,8 +176,20 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
     }
 }
 
-__host__ __device__ constexpr int pc_threads(int tb, int tk) { return (tb == 2 || tk == 2) ? 256 : 256; }
-__host__ __device__ constexpr int pc_minblocks(int tb, int tk) { return (tb == 2 || tk == 2) ? 1 : ((tb + tk == 0) ? 3 : 2); }
+#ifndef VB_MB_SS
+#define VB_MB_SS 2
+#endif
+#ifndef VB_MB_SP
+#define VB_MB_SP 2
+#endif
+#ifndef VB_MB_PSPS
+#define VB_MB_PSPS 2
+#endif
+__host__ __device__ constexpr int pc_threads(int tb, int tk) { return 256; }
+__host__ __device__ constexpr int pc_minblocks(int tb, int tk)
+{
+    return (tb == 2 || tk == 2) ? 1 : (tb + tk == 0 ? VB_MB_SS : (tb + tk == 1 ? VB_MB_SP : VB_MB_PSPS));
+}
 
 // Persistent kernel of one class.  Work item = bra pair group P with up to PT_MAXQ ket pair groups (consecutive tiles);
 // G of tile j of the item lives at gbuf[(item.z + j - gslot_base) * g_cap].
@@ -134,7 +197,7 @@ template <int TB, int TK>
 __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pclass(const TileArgs A, const ClassCfg C)
 {
     extern __shared__ __align__(16) double smem[];
-    constexpr int THREADS = pc_threads(TB, TK), nw = THREADS / 32, NE = pt_ne(TB);
+    constexpr int THREADS = pc_threads(TB, TK), nw = THREADS / 32, NE = pt_ne(TB), KB = pc_kb(TB, TK);
     double* Dp_s = smem;                                                   // bra densities of type TB
     double* scr = Dp_s + C.d_cap;                                          // per-warp X scratch
     double* boys_sm = scr + nw * PT_SCRATCH;                               // compact Boys table
@@ -194,7 +257,7 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
                 s_cum[qi] = n;
                 if (qi < ntl) {
                     const int nk = s_Q[qi].pp_beg[TK + 1] - s_Q[qi].pp_beg[TK];
-                    if (nk > 0 && P.kwmax[TB] * s_Q[qi].kwmax[TK] >= A.tau) n += (nk + 7) >> 3;
+                    if (nk > 0 && P.kwmax[TB] * s_Q[qi].kwmax[TK] >= A.tau) n += (nk + 8 * KB - 1) / (8 * KB);
                 }
             }
             s_cum[PT_MAXQ] = n;
@@ -215,7 +278,7 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
             const int oct = u - s_cum[qi];
             const PGDesc& Q = s_Q[qi];
             double* Gglob = A.gbuf + ((size_t)item.z + qi - A.gslot_base) * A.g_cap;
-            pclass_task<TB, TK>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, &s_pq);
+            pclass_task<TB, TK, KB>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, &s_pq);
         }
     }
     __syncthreads();
