@@ -34,7 +34,10 @@ extern "C" {
 /* ---- (1) reference-compatible entry points ------------------------------------------------ */
 /* Reads the input file named by argv[1] of the host process (valence_initialize_module.F90:49);
  * the environment variable VALENCE_INPUT, when set, names the file instead (for hosts such as
- * Python whose argv is not ours).  *info = 0 on return, like the reference. */
+ * Python whose argv is not ours).  *info = 0 on return, like the reference.
+ * Parallel runs: launch one process per GPU (torchrun / mpirun / srun); rank, size and local rank are read from the
+ * launcher's environment, the ranks form an NCCL communicator and every later call is collective (the reference's
+ * `call_mpi_init` / `comm` hand-off, valence_api.F90:22-27, has no MPI to act on here and is accepted unused). */
 void valence_api_initialize_(int* info, int* call_mpi_init, int* comm);
 /* x: 3*natom cartesians, atom-major, Angstrom.  v: total VSVB energy in Hartree incl. nuclear
  * repulsion.  Prints the reference's stdout lines and rewrites the `orbitals` file. */
@@ -75,6 +78,16 @@ int vb_engine_create(const char* input_path, int device, vb_engine** out);
 void vb_engine_destroy(vb_engine* e);
 int vb_engine_natom(const vb_engine* e);
 int vb_engine_nelec(const vb_engine* e);
+/* number of expansion terms of 1-based orbital iorb = order of the first_order_opt matrices (-1: no such orbital) */
+int vb_engine_norbas(const vb_engine* e, int iorb);
+/* One process per GPU of a node (replaces xm_propagate / xm_equalize*, /root/reference/src/xm_module.F90:711-910): the ranks
+ * of the job form an NCCL communicator (libnccl is loaded at run time; the id travels through
+ * /dev/shm/valence_b200_nccl_<key>, key NULL/"" = derived from the launcher's environment).  Afterwards vb_engine_energy,
+ * vb_engine_first_order and vb_engine_run are COLLECTIVE: the tile pass is sharded, the packed accumulators are summed by
+ * one all-reduce per energy (ham: one per orbital), every rank returns the full result.  vb_engine_attach_nccl adopts a
+ * communicator of the host (an ncclComm_t) instead of creating one. */
+int vb_engine_attach_comm(vb_engine* e, int rank, int nranks, const char* key);
+int vb_engine_attach_nccl(vb_engine* e, int rank, int nranks, void* nccl_comm);
 int vb_engine_set_coords(vb_engine* e, const double* x_angstrom);
 /* guess_energy on one GPU */
 int vb_engine_energy(vb_engine* e, vb_energy_result* out);

@@ -59,3 +59,30 @@ def test_first_order_matrices_match_fast_oracle(case, write_input):
     assert np.abs(H - Hf).max() < 1e-8 * scale and np.abs(S - Sf).max() < 1e-8 * max(1.0, np.abs(Sf).max())
     # the Rayleigh quotient of the current weights is the energy: both sides to 1e-9
     assert H.shape == Hf.shape
+
+
+def test_reference_api_through_c_host_one_and_two_ranks(tmp_path):
+    """A plain C host (tests/host/test_capi_ranks.c) drives the reference-compatible entry points with one process per GPU:
+    every rank returns the single-rank energy (the all-reduce lives inside the library, vb_nccl.cpp).  Two ranks need two
+    GPUs; on a one-GPU box only the one-rank run is made."""
+    import os
+    import subprocess
+    import torch
+    from valence_b200 import api, build, inputs
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_capi_ranks")
+    subprocess.check_call(["gcc", "-O2", "-o", exe, os.path.join(root, "tests", "host", "test_capi_ranks.c"), "-ldl"])
+    inp = tmp_path / "w8.inp"
+    inp.write_text(inputs.write(inputs.water_cluster(8, tol=(10, 20, 10))))
+    fx = fast_fixture("w8")
+    for nranks in (1, 2):
+        if nranks > torch.cuda.device_count():
+            continue
+        out = subprocess.run([exe, build.LIB, str(inp), str(nranks)], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        vals = [float(l.split()[-1]) for l in out.stdout.splitlines() if l.startswith("RANK")]
+        assert len(vals) == nranks
+        for v in vals:
+            assert abs(v - fx["energy"]) < 1e-10
+        assert "guess energy" in out.stdout          # rank 0 prints the reference's lines, the other ranks stay silent
+        assert out.stdout.count("guess energy") == 1

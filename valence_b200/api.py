@@ -16,6 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import build as _build
+from . import distributed as _dist
 
 CNT_NAMES = ("schwarz_erep", "schwarz_exch", "value_erep", "value_exch", "int2e_calls",
              "shell_quartets_2e", "shortcut", "entries")
@@ -65,6 +66,9 @@ def load(build_if_needed: bool = True):
     L.vb_engine_destroy.argtypes = [C.c_void_p]
     L.vb_engine_natom.argtypes = [C.c_void_p]
     L.vb_engine_nelec.argtypes = [C.c_void_p]
+    L.vb_engine_norbas.argtypes = [C.c_void_p, C.c_int]
+    L.vb_engine_attach_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    L.vb_engine_attach_nccl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.vb_engine_set_coords.argtypes = [C.c_void_p, C.c_void_p]
     L.vb_engine_energy.argtypes = [C.c_void_p, C.POINTER(CEnergyResult)]
     L.vb_engine_energy_partial.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(CEnergyResult)]
@@ -103,6 +107,7 @@ class Engine:
             raise RuntimeError(self.L.vb_last_error().decode())
         self.h = h
         self.device = device
+        self.comm = None      # (rank, nranks) once the library holds an NCCL communicator (attach_comm)
 
     def close(self):
         if getattr(self, "h", None):
@@ -123,6 +128,19 @@ class Engine:
     def nelec(self) -> int:
         return self.L.vb_engine_nelec(self.h)
 
+    def norbas(self, iorb: int) -> int:
+        """Number of expansion terms of 1-based orbital iorb (order of its first_order_opt matrices)."""
+        n = self.L.vb_engine_norbas(self.h, iorb)
+        if n < 0:
+            raise RuntimeError(f"no orbital {iorb}")
+        return n
+
+    def attach_comm(self, rank: int, nranks: int, key: Optional[str] = None):
+        """One process per GPU: the ranks of the job form an NCCL communicator INSIDE the library (no torch.distributed
+        needed); energy(), first_order() and run() are collective afterwards.  Replaces xm_propagate / xm_equalize*."""
+        self._check(self.L.vb_engine_attach_comm(self.h, rank, nranks, (key or "").encode()))
+        self.comm = (rank, nranks) if nranks > 1 else None
+
     def set_coords(self, x_angstrom: Sequence[float]):
         x = np.ascontiguousarray(x_angstrom, dtype=np.float64).ravel()
         assert x.size == 3 * self.natom
@@ -138,7 +156,7 @@ class Engine:
 
     def first_order(self, iorb: int):
         """ham, ovl (norbas x norbas) of first_order_opt for 1-based orbital iorb, plus run statistics."""
-        cap = 64 * 64
+        cap = self.norbas(iorb) ** 2
         ham = np.zeros(cap)
         ovl = np.zeros(cap)
         n = C.c_int(0)
@@ -150,7 +168,9 @@ class Engine:
     def first_order_distributed(self, iorb: int, rank: int, nranks: int):
         """first_order_opt matrices with the tiles sharded over the ranks and ONE all-reduce of ham
         (the reference equalizes ham the same way, valence.F90:755-764)."""
-        cap = 64 * 64
+        if self.comm is not None:          # the library's own communicator shards and sums
+            return self.first_order(iorb)
+        cap = self.norbas(iorb) ** 2
         ham = np.zeros(cap)
         ovl = np.zeros(cap)
         n = C.c_int(0)
@@ -170,7 +190,7 @@ class Engine:
             if ok.item() < 0.5:
                 raise RuntimeError(f"first_order failed on a rank: {err}" if err else "first_order failed on another rank")
             t = torch.from_numpy(ham[:k * k].copy()).to(f"cuda:{self.device}")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            _dist.allreduce_sum(t)
             ham[:k * k] = t.cpu().numpy()
         elif err:
             raise err
@@ -205,7 +225,9 @@ class Engine:
 
         VB_SHARD_SETUP=1 (ranks of ONE node): the host-side pair tables are built once per node instead of once per
         rank -- every rank publishes its share under /dev/shm, a barrier, then each rank merges all shares."""
-        if nranks > 1 and os.environ.get("VB_SHARD_SETUP") == "1":
+        if self.comm is not None:          # the library's own communicator: one collective call
+            return self.energy()
+        if nranks > 1 and os.environ.get("VB_SHARD_SETUP", "1") != "0":
             import torch.distributed as dist
             key = os.environ.get("VB_SHARD_KEY") or f"{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}"
             prefix = f"/dev/shm/valence_b200_{key}_"
@@ -217,7 +239,7 @@ class Engine:
             import torch.distributed as dist
             acc = self.accumulator()
             torch.cuda.synchronize(self.device)
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            _dist.allreduce_sum(acc)
             torch.cuda.synchronize(self.device)
         return self.energy_finish(r)
 

@@ -12,8 +12,8 @@ CLI = os.path.join(HERE, "valence")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-SOURCES = ["vb_engine.cu", "vb_setup.cpp", "vb_tilelist.cpp", "vb_cofactor.cpp", "vb_input.cpp", "vb_capi.cpp"]
-HEADERS = ["vb_engine.h", "vb_setup.h", "vb_cofactor.h", "vb_input.h", "vb_eri.cuh", "vb_kernels.cuh", "vb_tile.cuh", "vb_ptile.cuh", "vb_tilelist.h",
+SOURCES = ["vb_engine.cu", "vb_setup.cpp", "vb_tilelist.cpp", "vb_cofactor.cpp", "vb_input.cpp", "vb_capi.cpp", "vb_nccl.cpp"]
+HEADERS = ["vb_engine.h", "vb_setup.h", "vb_cofactor.h", "vb_input.h", "vb_eri.cuh", "vb_kernels.cuh", "vb_tile.cuh", "vb_ptile.cuh", "vb_pclass.cuh", "vb_nccl.h", "vb_tilelist.h",
            os.path.join("..", "..", "include", "valence_b200.h")]
 
 
@@ -28,7 +28,7 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [NVCC, *FLAGS, *os.environ.get("VB_EXTRA_FLAGS", "").split(), "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [NVCC, *FLAGS, *os.environ.get("VB_EXTRA_FLAGS", "").split(), "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(log)
     cmd = [NVCC, "-O2", "-std=c++17", "-o", CLI, os.path.join(CSRC, "vb_cli.cpp"),
-           "-L" + HERE, "-lvalence_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+           "-L" + HERE, "-lvalence_b200", "-ldl", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

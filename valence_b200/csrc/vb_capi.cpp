@@ -12,6 +12,7 @@
 
 #include "../../include/valence_b200.h"
 #include "vb_engine.h"
+#include "vb_nccl.h"
 
 struct vb_engine {
     std::unique_ptr<vb::Engine> eng;
@@ -54,7 +55,7 @@ std::unique_ptr<vb::Engine> g_api;
 // xm_abort (xm_module.F90:942-950): `error` line from this rank, then stop
 [[noreturn]] void api_abort(const std::string& msg)
 {
-    std::printf("%-40s from rank %8d\n", msg.c_str(), 0);
+    std::printf("%-40s from rank %8d\n", msg.c_str(), g_api ? g_api->comm_rank() : vb::launch_env().rank);
     std::fflush(stdout);
     std::exit(1);
 }
@@ -150,6 +151,19 @@ int vb_engine_create(const char* input_path, int device, vb_engine** out)
 
 void vb_engine_destroy(vb_engine* e) { delete e; }
 int vb_engine_natom(const vb_engine* e) { return e->eng->input().natom; }
+int vb_engine_norbas(const vb_engine* e, int iorb)
+{
+    const vb::Input& in = e->eng->input();
+    return (iorb >= 1 && iorb <= in.norbs()) ? (int)in.orbitals[iorb - 1].xp.size() : -1;
+}
+int vb_engine_attach_comm(vb_engine* e, int rank, int nranks, const char* key)
+{
+    return guarded([&] { e->eng->attach_comm(rank, nranks, key && *key ? key : vb::launch_env().key); });
+}
+int vb_engine_attach_nccl(vb_engine* e, int rank, int nranks, void* nccl_comm)
+{
+    return guarded([&] { e->eng->attach_nccl(rank, nranks, nccl_comm); });
+}
 int vb_engine_nelec(const vb_engine* e) { return e->eng->input().nelec(); }
 
 int vb_engine_set_coords(vb_engine* e, const double* x)
@@ -201,9 +215,11 @@ int vb_engine_first_order(vb_engine* e, int iorb, double* ham, double* ovl, int 
     return guarded([&] {
         std::vector<double> h, s;
         vb::EnergyResult r;
+        const int nb = vb_engine_norbas(e, iorb);
+        if (nb < 0) throw std::runtime_error("first_order: orbital index out of range");
+        *norbas = nb;
+        if (nb * nb > cap) throw std::runtime_error("first_order: output buffers too small (vb_engine_norbas gives the order)");
         int n = e->eng->first_order(iorb - 1, &h, &s, &r);
-        *norbas = n;
-        if (n * n > cap) throw std::runtime_error("first_order: output buffers too small");
         std::copy(h.begin(), h.end(), ham);
         std::copy(s.begin(), s.end(), ovl);
         if (stats) to_c(r, stats);
@@ -217,9 +233,12 @@ int vb_engine_first_order_sharded(vb_engine* e, int iorb, int rank, int nranks, 
         if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("first_order: bad rank / nranks");
         std::vector<double> h, s;
         vb::EnergyResult r;
+        const int nb = vb_engine_norbas(e, iorb);
+        if (nb < 0) throw std::runtime_error("first_order: orbital index out of range");
+        *norbas = nb;
+        if (nb * nb > cap) throw std::runtime_error("first_order: output buffers too small (vb_engine_norbas gives the order)");
         int n = e->eng->first_order(iorb - 1, &h, &s, &r, rank, nranks);
-        *norbas = n;
-        if (n * n > cap) throw std::runtime_error("first_order: output buffers too small");
+        (void)n;
         std::copy(h.begin(), h.end(), ham);
         std::copy(s.begin(), s.end(), ovl);
         if (stats) to_c(r, stats);
@@ -250,14 +269,21 @@ int vb_measure_fp64_peak(int device, double* tflops)
 /* ---- reference-compatible layer ------------------------------------------------------------- */
 void valence_api_initialize_(int* info, int* call_mpi_init, int* comm)
 {
-    (void)call_mpi_init; (void)comm;   // single process per GPU; no MPI inside the engine
+    // The reference either initialises MPI itself or adopts the host's communicator (valence_api.F90:22-27,
+    // xm_module.F90:727-732).  Here ranks are one process per GPU of a node: rank / size / local rank are taken from the
+    // launcher's environment (torchrun, mpirun, srun) and the ranks form an NCCL communicator; an MPI handle in `comm`
+    // cannot be used (there is no MPI in this library) and is only accepted.
+    (void)call_mpi_init; (void)comm;
     std::string path = host_argv1();
     if (path.empty()) api_abort("must have one input file");            // valence_initialize_module.F90:50
     try {
         vb::Input in = vb::parse_input_file(path);
-        int dev = 0;
-        if (const char* lr = std::getenv("LOCAL_RANK")) dev = std::atoi(lr);
-        g_api.reset(new vb::Engine(in, dev));
+        const vb::LaunchEnv le = vb::launch_env();
+        g_api.reset(new vb::Engine(in, le.local_rank));
+        if (le.nranks > 1) {
+            g_api->attach_comm(le.rank, le.nranks, le.key);
+            if (le.rank == 0) std::printf(" %-32s  %8d\n", "number of processors", le.nranks);   // xm_propagate, xm_module.F90:744-750
+        }
     } catch (const vb::InputError& ex) {
         api_abort(ex.what());
     } catch (const std::exception& ex) {
@@ -271,12 +297,16 @@ void valence_api_calculate_energy_(double* x, double* v)
     if (!g_api) api_abort("valence_api_calculate_energy before valence_api_initialize");
     try {
         g_api->set_coords_angstrom(x);                                   // valence_api.F90:57-63
+        // `orbitals` is rewritten after the guess energy, after every orbital / spin-coupling update ('save') and at
+        // convergence ('done' with the last feathering tolerance): valence.F90:192,2823,2859,2882.  The weights written are
+        // the normalised ones the reference holds after normal() (valence.F90:144-145,807).
+        vb::Engine* eng = g_api.get();
+        eng->on_save = [eng](double energy, bool done) {
+            const std::vector<std::vector<double>> w = eng->normalized_weights();
+            write_orbitals_file(eng->input(), &w, &eng->coupling_weights(), energy, done, std::pow(10.0, -(double)eng->input().ntol_e_max));
+        };
         vb::Engine::RunResult r;
         g_api->run(&r, true);                                            // calculate_vsvb_energy, valence_api.F90:96-97
-        // valence.F90:192,2823,2859 ('save') and :2882 ('done' with the last feathering tolerance, :2771-2772)
-        const bool done = r.converged && g_api->input().max_iter > 0;
-        write_orbitals_file(g_api->input(), &g_api->weights(), &g_api->coupling_weights(), r.total_energy, done,
-                            std::pow(10.0, -(double)g_api->input().ntol_e_max));
         *v = r.total_energy;
     } catch (const std::exception& ex) {
         api_abort(ex.what());

@@ -16,6 +16,7 @@
 #include <atomic>
 
 #include "vb_cofactor.h"
+#include "vb_nccl.h"
 #include "vb_kernels.cuh"
 #include "vb_tilelist.h"
 #include "vb_ptile.cuh"
@@ -236,11 +237,18 @@ struct Engine::Impl {
     DBuf<int> fo_perm;
     void cofactor_stage(const Input& in, const Wavefunction& wf, bool diag_only, EnergyResult* out, bool* fast_out, double* c0_out, int* ndp_out);
     int only_isc = -1, only_jsc = -1;                 // spin_opt: restrict the cofactors to one coupling pair
+    bool use_gather = false;                         // energy(): table shares are exchanged on the device (all-gather)
+    bool fo_collective = false;                      // first_order through the engine's communicator: decisions are agreed on
     std::vector<double> coeff_sc;                    // current spin-coupling weights
     double enuc = 0, e1 = 0, wfnorm = 0;
-    double tau = 1e-22;   // primitive-quartet magnitude cut; VB_PRIM_TAU overrides
+    // primitive-quartet magnitude cut (VB_PRIM_TAU overrides).  Measured on (H2O)_64 / (H2O)_128: the energy is the same to
+    // 13 digits for every cut between 1e-24 and 1e-18 (profiles/r2_tau_sweep.log); the screening counters do not depend on it.
+    double tau = 1e-20;
     int launches = 0;
     double t_begin = 0;
+    std::unique_ptr<Comm> comm;                      // one process per GPU: NCCL communicator of the job (null = alone)
+    int crank() const { return comm ? comm->rank() : 0; }
+    int csize() const { return comm ? comm->nranks() : 1; }
 };
 
 Engine::Engine(const Input& in, int device) : in_(in), impl_(new Impl)
@@ -353,9 +361,14 @@ void Engine::Impl::prepare(const Input& in, int subject)
     {
         long long npair = (long long)nshell * (nshell + 1) / 2;
         const int wpb = 4;   // warps (= shell pairs) per block
-        k_ao_1e<<<(unsigned)((npair + wpb - 1) / wpb), 32 * wpb, 0, st>>>(shells.p, nshell, exps.p, coefs.p, this->nuc.p, in.natom, boys.p, nao, 1e-30, S.p, H.p);
+        // with a communicator every rank takes the shell pairs k = rank (mod N) and the matrices are summed (NVLink)
+        const int cr = crank(), cn = csize();
+        if (cn > 1) { S.zero(st); H.zero(st); }
+        const long long mine = (npair - cr + cn - 1) / cn;
+        if (mine > 0) k_ao_1e<<<(unsigned)((mine + wpb - 1) / wpb), 32 * wpb, 0, st>>>(shells.p, nshell, exps.p, coefs.p, this->nuc.p, in.natom, boys.p, nao, 1e-30, S.p, H.p, cr, cn);
         CK(cudaGetLastError());
         launches++;
+        if (cn > 1) { comm->allreduce_sum(S.p, (size_t)nao * nao, st); comm->allreduce_sum(H.p, (size_t)nao * nao, st); }
     }
     // normalise DBFs, then orbitals (valence.F90:144-145, normal :2157-2182); the raw weights stay untouched
     cnorm = coeff;
@@ -564,7 +577,50 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         topts.shard_mode = 2; topts.shard_rank = shard_rank; topts.shard_nranks = shard_nranks; topts.shard_prefix = shard_prefix;
         shard_pending = false;
     }
+    const bool gather = use_gather && comm && comm->nranks() > 1 && !gen && !shard_pending;
+    if (gather) { topts.shard_mode = 3; topts.shard_rank = comm->rank(); topts.shard_nranks = comm->nranks(); }
     build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts, topts);
+    if (gather) {
+        // Every rank has built the pair groups it owns (blocks of 16, round-robin) with local offsets.  The shares meet on
+        // the DEVICE: sizes by one small all-reduce, then each table is all-gathered over NVLink into a layout with one
+        // equal-sized slot per rank (holes are pair groups with np = 0, which no tile ever references).  Host build and H2D
+        // traffic per rank are 1/N of the single-GPU ones; the descriptors come back to the host for the tile list.
+        const int N = comm->nranks(), r = comm->rank();
+        constexpr int NX = 10;
+        std::vector<double> x((size_t)N * NX, 0.0);
+        const double mine[NX] = {(double)ts.pgs.size(), (double)(ts.pg_pairs.size() / 2), (double)ts.sps.size(), (double)ts.pps.size(), (double)ts.dmat.size(),
+                                 (double)ts.max_ne, (double)ts.max_np, (double)ts.max_npp, (double)ts.max_nsp, (double)ts.max_ks};
+        for (int k = 0; k < NX; ++k) x[(size_t)r * NX + k] = mine[k];
+        one_e.alloc(x.size());
+        CK(cudaMemcpyAsync(one_e.p, x.data(), x.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        comm->allreduce_sum(one_e.p, x.size(), st);
+        CK(cudaMemcpyAsync(x.data(), one_e.p, x.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        size_t cap[5] = {0, 0, 0, 0, 0};
+        for (int q = 0; q < N; ++q) {
+            for (int k = 0; k < 5; ++k) cap[k] = std::max(cap[k], (size_t)x[(size_t)q * NX + k]);
+            ts.max_ne = std::max(ts.max_ne, (int)x[(size_t)q * NX + 5]); ts.max_np = std::max(ts.max_np, (int)x[(size_t)q * NX + 6]);
+            ts.max_npp = std::max(ts.max_npp, (int)x[(size_t)q * NX + 7]); ts.max_nsp = std::max(ts.max_nsp, (int)x[(size_t)q * NX + 8]);
+            ts.max_ks = std::max(ts.max_ks, (int)x[(size_t)q * NX + 9]);
+        }
+        for (int k = 0; k < 5; ++k) cap[k] = (cap[k] + 15) & ~(size_t)15;
+        const size_t cpg = cap[0], cpr = cap[1], csp = cap[2], cpp = cap[3], cd = cap[4];
+        if ((cpp + 1) * (size_t)N > 2000000000ull || (csp + 1) * (size_t)N > 2000000000ull) throw std::runtime_error("valence_b200: tables too large for 32-bit offsets");
+        for (PGDesc& pg : ts.pgs) {
+            pg.pair_beg += (int)(r * cpr); pg.d_off += (long long)(r * cd);
+            for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += (int)(r * cpp); pg.sp_beg[t] += (int)(r * csp); }
+        }
+        for (SPRec& sr : ts.sps) sr.pp_beg += (int)(r * cpp);
+        pgs.alloc(N * cpg); pg_pairs.alloc(2 * N * cpr); sps.alloc(N * csp); pps.alloc(N * cpp); pps_flat.alloc(N * cpp); dmat.alloc(N * cd);
+        pgs.zero(st);
+        pgs.upload_at(r * cpg, ts.pgs, st); pg_pairs.upload_at(2 * r * cpr, ts.pg_pairs, st); sps.upload_at(r * csp, ts.sps, st);
+        pps.upload_at(r * cpp, ts.pps, st); pps_flat.upload_at(r * cpp, ts.pps_flat, st); dmat.upload_at(r * cd, ts.dmat, st);
+        comm->allgather_bytes(pgs.p, cpg * sizeof(PGDesc), st); comm->allgather_bytes(pg_pairs.p, 2 * cpr * sizeof(int), st);
+        comm->allgather_bytes(sps.p, csp * sizeof(SPRec), st); comm->allgather_bytes(pps.p, cpp * sizeof(PrimPair), st);
+        comm->allgather_bytes(pps_flat.p, cpp * sizeof(PrimPair), st); comm->allgather_bytes(dmat.p, cd * sizeof(double), st);
+        pgs.download(ts.pgs, st);
+        pg_pairs.download(ts.pg_pairs, st);
+    }
     const double t_bt = now_ms();
     const int npg = (int)ts.pgs.size();
     if (ts.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
@@ -593,8 +649,11 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         nshb[s] = (int)orbs2e[wf.bra[wf.slot(s, 0)]].sh.size();
         nshk[s] = (int)orbs2e[wf.ket[wf.slot(s, 0)]].sh.size();
     }
-    pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
-    pps.upload(ts.pps, st); pps_flat.upload(ts.pps_flat, st); dmat.upload(ts.dmat, st); nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
+    if (!gather) {
+        pgs.upload(ts.pgs, st); pg_pairs.upload(ts.pg_pairs, st); sps.upload(ts.sps, st);
+        pps.upload(ts.pps, st); pps_flat.upload(ts.pps_flat, st); dmat.upload(ts.dmat, st);
+    }
+    nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
     if (!gen) { gred.alloc((size_t)nsm * PT_MAXQ * g_cap); A_gred = gred.p; }
     int grid_cap = nsm;
@@ -634,15 +693,17 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         sch = *sch_in;
     } else {
         std::vector<double> dg;
-        std::vector<TilePair> dt(npg);
-        std::vector<WorkItem> di(npg);
-        for (int i = 0; i < npg; ++i) { dt[i] = TilePair{i, i}; di[i] = WorkItem{i, 1, 0, 0}; }
+        std::vector<TilePair> dt;
+        std::vector<WorkItem> di;
+        for (int i = 0; i < npg; ++i)
+            if (ts.pgs[i].np > 0) { di.push_back(WorkItem{(int)dt.size(), 1, 0, 0}); dt.push_back(TilePair{i, i}); }
+        const int ndiag = (int)dt.size();
         tiles.upload(dt, st); items.upload(di, st);
         diag.alloc((size_t)nso * nso);
         diag.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-        A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = npg; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = npg; A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
+        A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = ndiag; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = ndiag; A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = 0; A.tile_stride = 1; A.mode = 0; A.diag = diag.p;
         CK(cudaEventRecord(ev0, st));
-        launch(npg, PART_ALL);
+        launch(ndiag, PART_ALL);
         CK(cudaEventRecord(ev1, st));
         out->diag_launches++;
         diag.download(dg, st);
@@ -675,16 +736,16 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     std::iota(all.begin(), all.end(), 0);
     std::vector<TilePair> tl;
     std::vector<std::pair<long long, int>> runs;      // (first tile, # tiles) of every non-empty (a, chunk)
-    make_tile_list(ts.pgs, all, all, itol, &tl, &runs);
+    make_tile_list(ts.pgs, all, all, itol, &tl, &runs, rank, nranks);      // this rank's bra blocks only
     const long long ntiles = (long long)tl.size();
     // work items of the s/p kernel: pieces of <= m tiles of a run (they share the bra pair group); the d-shell
     // kernel takes single tiles.  Only this rank's items are kept (block-cyclic over the ranks; z = slot of the
     // item's first tile in the G hand-over buffer).
     std::vector<WorkItem> itl;
     long long my_tiles = 0;
-    if (!gen) make_items(runs, ntiles, nsm, rank, nranks, &itl, &my_tiles);
+    if (!gen) make_items(runs, ntiles, nsm, 0, 1, &itl, &my_tiles);
     long long mine = (long long)itl.size();
-    if (gen) { mine = 0; for (long long k = rank; k < ntiles; k += nranks) mine++; }
+    if (gen) mine = ntiles;
     double t4 = now_ms();
     if (dbg_time) std::printf("[time] diag pass + tile list %.1f ms (tiles %lld items %zu)\n", t4 - t3, ntiles, itl.size());
     // ---- energy pass ---------------------------------------------------------------------------------
@@ -692,7 +753,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     tiles.upload(tl, st); items.upload(itl, st);
     tileE.alloc((size_t)std::max<long long>(ntiles, 1));
     tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
-    A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)ntiles; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itl.size(); A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = rank; A.tile_stride = nranks; A.mode = 1; A.tau = tau_energy;
+    A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)ntiles; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itl.size(); A.gbuf = nullptr; A.gslot_base = 0; A.tile_first = 0; A.tile_stride = 1; A.mode = 1; A.tau = tau_energy;
     A.sch = this->sch.p; A.tileE = tileE.p;
     bool split = false;   // VB_SPLIT=1: separate heavy / light launches (measured slower: 5.97 s vs 5.46 s on (H2O)_256)
     if (const char* e = std::getenv("VB_SPLIT")) split = std::atoi(e) != 0;
@@ -783,6 +844,9 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             }
         out->flops_model += fl; out->n_prim_quartets += npq;
         if (std::getenv("VB_DEBUG_PQ"))
+            for (int c = 0; c < 9; ++c)
+                if (pq[18 + c]) std::printf("class (%d|%d): lane slots %llu, quartets %llu, lane efficiency %.3f\n", c / 3, c % 3, pq[18 + c], pq[(c / 3) * NPTYPE + c % 3], (double)pq[(c / 3) * NPTYPE + c % 3] / (double)pq[18 + c]);
+        if (std::getenv("VB_DEBUG_PQ"))
             for (int a = 0; a < NPTYPE; ++a)
                 for (int b = 0; b < NPTYPE; ++b)
                     if (pq[a * NPTYPE + b])
@@ -816,6 +880,49 @@ Wavefunction default_wavefunction(const Input& in)   // guess_energy, valence.F9
 }
 
 }  // namespace
+
+void Engine::attach_comm(int rank, int nranks, const std::string& key)
+{
+    CK(cudaSetDevice(impl_->device));
+    impl_->comm.reset(nranks > 1 ? new Comm(rank, nranks, key) : nullptr);
+}
+void Engine::attach_nccl(int rank, int nranks, void* nccl_comm)
+{
+    CK(cudaSetDevice(impl_->device));
+    impl_->comm.reset(nranks > 1 ? new Comm(rank, nranks, nccl_comm) : nullptr);
+}
+int Engine::comm_rank() const { return impl_->crank(); }
+int Engine::comm_size() const { return impl_->csize(); }
+
+// guess_energy; collective when a communicator is attached
+void Engine::energy(EnergyResult* out)
+{
+    Impl& I = *impl_;
+    if (I.csize() == 1) { energy_partial(0, 1, out); energy_finish(out); return; }
+    const int r = I.crank(), n = I.csize();
+    bool shard = true;                         // host tables once per node (VB_SHARD_SETUP=0: every rank builds everything)
+    if (const char* e = std::getenv("VB_SHARD_SETUP")) shard = std::atoi(e) != 0;
+    bool gather = shard;                       // exchange the shares on the device (VB_GATHER_TABLES=0: host shared memory)
+    if (const char* e = std::getenv("VB_GATHER_TABLES")) gather = gather && std::atoi(e) != 0;
+    if (gather) {
+        I.use_gather = true;
+        try { energy_partial(r, n, out); } catch (...) { I.use_gather = false; throw; }
+        I.use_gather = false;
+        I.comm->allreduce_sum(I.accum.p, 1 + CNT_N, I.st);
+        energy_finish(out);
+        return;
+    }
+    if (shard) {
+        std::string key = "job";
+        if (const char* k = std::getenv("VB_SHARD_KEY")) key = k;
+        else if (const char* p = std::getenv("MASTER_PORT")) key = std::string("port") + p;
+        shard_tables(r, n, "/dev/shm/valence_b200_tables_" + key + "_");
+        I.comm->barrier(I.st);
+    }
+    energy_partial(r, n, out);
+    I.comm->allreduce_sum(I.accum.p, 1 + CNT_N, I.st);
+    energy_finish(out);
+}
 
 void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
 {
@@ -1020,11 +1127,23 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
         const double need = (double)my_tiles * cfg.g_cap * 8.0;
         double cap = 0.8 * ((double)fr + (double)gcache.cap * 8.0);
         if (const char* e = std::getenv("VB_FO_CACHE_MB")) cap = std::min(cap, std::atof(e) * 1048576.0);
-        if (need > cap) {
+        // The cached and the plain loop split the tiles over the ranks differently, so every rank must take the same one:
+        // with the engine's communicator the verdicts are summed; a caller that does its own all-reduce (nranks > 1, no
+        // communicator) gets an error instead of a silent mix.
+        double misfit = need > cap ? 1.0 : 0.0;
+        if (fo_collective) {
+            one_e.alloc(1);
+            CK(cudaMemcpyAsync(one_e.p, &misfit, sizeof(double), cudaMemcpyHostToDevice, st));
+            comm->allreduce_sum(one_e.p, 1, st);
+            CK(cudaMemcpyAsync(&misfit, one_e.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (misfit > 0.0) {
             // the plain loop regenerates every integral norbas(norbas+1)/2 times: a caller that cannot afford that
             // (bench.py on large clusters) asks for an error instead
-            if (const char* e = std::getenv("VB_FO_REQUIRE_CACHE"))
-                if (std::atoi(e) != 0) throw std::runtime_error("valence_b200: the integral cache of first_order_opt does not fit in device memory");
+            bool require = nranks > 1 && !fo_collective;
+            if (const char* e = std::getenv("VB_FO_REQUIRE_CACHE")) require = require || std::atoi(e) != 0;
+            if (require) throw std::runtime_error("valence_b200: the integral cache of first_order_opt does not fit in device memory");
             return false;
         }
     }
@@ -1060,10 +1179,18 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
         A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)tlc.size(); A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)itc.size();
         A.gbuf = gcache.p; A.gslot_base = 0; A.mode = 2; A.tau = tau_energy;
         CK(cudaEventRecord(ev2, st));
-        k_ptile<PART_ALL><<<std::max(1, std::min(nsm, (int)itc.size())), pt_threads(PART_ALL), cfg.smem, st>>>(A);
-        CK(cudaGetLastError());
+        bool csplit = true;
+        if (const char* e = std::getenv("VB_CLASS_SPLIT")) csplit = std::atoi(e) != 0;
+        ClassPlan cplan;
+        if (csplit) { cplan = plan_classes(std::vector<PGDesc>(hp.begin(), hp.begin() + nfree)); csplit = cplan.ok; }
+        if (csplit) {
+            launches += run_class_pass(A, cplan, nsm, my_tiles, counter.p, st, nullptr, ev0, ev1);
+        } else {
+            k_ptile<PART_ALL><<<std::max(1, std::min(nsm, (int)itc.size())), pt_threads(PART_ALL), cfg.smem, st>>>(A);
+            CK(cudaGetLastError());
+            launches++;
+        }
         CK(cudaEventRecord(ev3, st));
-        launches++;
         acc->tile_launches++;
         add_pq();
         float ms = 0.f;
@@ -1223,6 +1350,9 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
     CK(cudaSetDevice(I.device));
     const Input& in = in_;
     if (iorb < 0 || iorb >= in.norbs() - in.ndf) throw std::runtime_error("first_order: orbital index out of range");
+    const bool internal = rank < 0;            // the engine's own communicator shards the tiles and sums ham
+    if (internal) { rank = I.crank(); nranks = I.csize(); }
+    I.fo_collective = internal && nranks > 1;
     EnergyResult acc;
     I.launches = 0;
     I.t_begin = now_ms();
@@ -1290,6 +1420,13 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
                 for (int i = 0; i < CNT_N; ++i) acc.counters[i] += (long long)(a[1 + i] + 0.5);
             }
         }
+    }
+    if (internal && nranks > 1) {              // xm_equalize(ham), valence.F90:763
+        I.one_e.alloc(ham->size());
+        CK(cudaMemcpyAsync(I.one_e.p, ham->data(), ham->size() * sizeof(double), cudaMemcpyHostToDevice, I.st));
+        I.comm->allreduce_sum(I.one_e.p, ham->size(), I.st);
+        CK(cudaMemcpyAsync(ham->data(), I.one_e.p, ham->size() * sizeof(double), cudaMemcpyDeviceToHost, I.st));
+        CK(cudaStreamSynchronize(I.st));
     }
     for (int i = 0; i < norbas; ++i)
         for (int j = 0; j < i; ++j) {
@@ -1371,6 +1508,15 @@ int gen_eig(int n, const std::vector<double>& A, const std::vector<double>& B, s
 }  // namespace
 
 const std::vector<std::vector<double>>& Engine::weights() const { return impl_->coeff; }
+std::vector<std::vector<double>> Engine::normalized_weights()
+{
+    Impl& I = *impl_;
+    CK(cudaSetDevice(I.device));
+    Comm* keep = I.comm.release();             // a local evaluation: not every rank writes files
+    try { I.prepare(in_, -1); } catch (...) { I.comm.reset(keep); throw; }
+    I.comm.reset(keep);
+    return I.cnorm;
+}
 const std::vector<double>& Engine::coupling_weights() const { return impl_->coeff_sc; }
 
 void Engine::run(RunResult* out, bool print)
@@ -1379,6 +1525,7 @@ void Engine::run(RunResult* out, bool print)
     const Input& in = in_;
     const double tokcal = 627.509469;
     *out = RunResult();
+    print = print && I.crank() == 0;           // xm_print: rank 0 only (xm_module.F90:356-458)
     EnergyResult r;
     energy(&r);
     out->enucrep = r.enucrep;
@@ -1390,6 +1537,7 @@ void Engine::run(RunResult* out, bool print)
         std::fflush(stdout);
     }
     out->total_energy = energy_now;
+    if (on_save && I.crank() == 0) on_save(energy_now, false);                               // valence.F90:192
     if (in.max_iter <= 0) return;
     if (in.ptbnmax > 0.0 && in.nxorb == 0)
         throw std::runtime_error("direct energy minimisation (demgs_opt) is not supported (under development in the reference, README.md:108)");
@@ -1427,6 +1575,7 @@ void Engine::run(RunResult* out, bool print)
                             const double relaxn = (energy_now - eprev) * tokcal;
                             cumulx += relaxn;
                             if (print) { std::printf("%5d  %4d      %14.6f      %12.4E\n", num_iter, iorb, cumulx, relaxn / etol); std::fflush(stdout); }
+                            if (on_save && I.crank() == 0) on_save(energy_now, false);               // valence.F90:2823
                         }
                         setconv = std::fabs(energy_now - eprv_set) * tokcal < etol;
                     }
@@ -1465,6 +1614,7 @@ void Engine::run(RunResult* out, bool print)
                 const double relaxn = (energy_now - eprev) * tokcal;
                 cumulx += relaxn;
                 if (print) { std::printf("%5d  %4d      %14.6f      %12.4E\n", num_iter, 0, cumulx, relaxn / etol); std::fflush(stdout); }
+                if (on_save && I.crank() == 0) on_save(energy_now, false);                           // valence.F90:2859
                 finished = std::fabs(energy_now - eprv_sc) * tokcal < etol;
             } else {
                 finished = true;
@@ -1479,6 +1629,7 @@ void Engine::run(RunResult* out, bool print)
         if (print) std::printf("\n %-71s\n\n", "reached maximum number of iterations");
     } else if (std::fabs(energy_now - eprev) * tokcal < etol) {
         out->converged = 1;
+        if (on_save && I.crank() == 0) on_save(energy_now, true);                                    // valence.F90:2882
         if (print) {
             std::printf("\n %-71s\n\n", "calculation converged");
             std::printf(" %-32s  %24.16f\n", "total energy", energy_now);

@@ -142,10 +142,11 @@ __device__ __forceinline__ void nuc_aux(const DevShell& A, const DevShell& B, do
 // kcut (1e-30: far below anything that reaches 1e-10 Eh) are skipped.
 __global__ void __launch_bounds__(128) k_ao_1e(const DevShell* __restrict__ sh, int nshell, const double* __restrict__ exps,
                         const double* __restrict__ coefs, const double* __restrict__ nuc /* x,y,z,Z per atom */, int natom,
-                        const double* __restrict__ boys_tab, int nao, double kcut, double* __restrict__ S, double* __restrict__ H)
+                        const double* __restrict__ boys_tab, int nao, double kcut, double* __restrict__ S, double* __restrict__ H,
+                        int first = 0, int stride = 1 /* shell pairs first, first + stride, ... (one process per GPU) */)
 {
     const int lane = threadIdx.x & 31;
-    const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long idx = first + (long long)stride * (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const long long npair = (long long)nshell * (nshell + 1) / 2;
     if (idx >= npair) return;
     int i = (int)floor(sqrt(2.0 * (double)idx + 0.25) - 0.5);

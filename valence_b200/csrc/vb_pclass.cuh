@@ -29,8 +29,11 @@ struct ClassCfg {           // shared-memory capacities of one class launch (hos
 #ifndef VB_KB_SS
 #define VB_KB_SS 2
 #endif
-#ifndef VB_KB_SP
-#define VB_KB_SP 2
+#ifndef VB_KB_PSSS
+#define VB_KB_PSSS 2
+#endif
+#ifndef VB_KB_SSPS
+#define VB_KB_SSPS 1     // three ket components: two kets per lane do not fit 128 registers (measured slower)
 #endif
 #ifndef VB_KB_PSPS
 #define VB_KB_PSPS 1
@@ -40,7 +43,42 @@ struct ClassCfg {           // shared-memory capacities of one class launch (hos
 #endif
 __host__ __device__ constexpr int pc_kb(int tb, int tk)
 {
-    return (tb == 2 || tk == 2) ? VB_KB_PP : (tb + tk == 0 ? VB_KB_SS : (tb + tk == 1 ? VB_KB_SP : VB_KB_PSPS));
+    return (tb == 2 || tk == 2) ? VB_KB_PP : (tb + tk == 0 ? VB_KB_SS : (tb + tk == 1 ? (tb == 1 ? VB_KB_PSSS : VB_KB_SSPS) : VB_KB_PSPS));
+}
+
+// 1/sqrt(x) for normal positive x without the special-case branch of the library routine (that branch and the
+// far/near branches of the Boys function keep the scheduler from interleaving the KB dependency chains):
+// hardware seed (2^-22) + one third-order correction y0 (1 + e/2 + 3 e^2/8), e = 1 - x y0^2.
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(x, -(y0 * y0), 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+// quartet_geom (vb_eri.cuh) with the branch-free reciprocal square root
+__device__ __forceinline__ void quartet_geom_fast(const PrimPair& a, const PrimPair& b, QuartetGeom& g, double& T, double& pref)
+{
+    const double p = a.p, q = b.p;
+    const double r = rsqrt_fast(p + q), ipq = r * r;
+    const double wq = q * ipq, wp = p * ipq;             // rho/p, rho/q
+    const double dx = a.Px - b.Px, dy = a.Py - b.Py, dz = a.Pz - b.Pz;
+    T = p * wq * (dx * dx + dy * dy + dz * dz);
+    pref = a.Kp * b.Kp * r;
+    g.PA[0] = a.PAx; g.PA[1] = a.PAy; g.PA[2] = a.PAz;
+    g.QC[0] = b.PAx; g.QC[1] = b.PAy; g.QC[2] = b.PAz;
+    g.WP[0] = -wq * dx; g.WP[1] = -wq * dy; g.WP[2] = -wq * dz;
+    g.WQ[0] = wp * dx; g.WQ[1] = wp * dy; g.WQ[2] = wp * dz;
+    g.h2p = 0.5 * a.ip; g.h2q = 0.5 * b.ip; g.h2pq = 0.5 * ipq; g.rp = wq; g.rq = wp;
+}
+// Boys values in the asymptotic regime T >= BOYS_S_TMAX (exp(-T) < 5e-18 dropped, as boys_s does), branch-free
+template <int M>
+__device__ __forceinline__ void boys_far(double T, double* F)
+{
+    const double r = rsqrt_fast(T), rt = r * r;
+    F[0] = 0.88622692545275801365 * r;
+#pragma unroll
+    for (int m = 0; m < M; ++m) F[m + 1] = (m + 0.5) * F[m] * rt;
 }
 
 // the quartet values of KB kets go straight into the tensor cores: X[kb]_f[k][p] += sum_b A[k][b] Dp[e_b + e][p]
@@ -62,9 +100,10 @@ __device__ __forceinline__ void feed_dmma_kb(const double (&acc)[KB][pt_ne(TB) *
         }
 }
 
-// One warp task: KB consecutive ket octets of pair type TK against every bra primitive of type TB of P.
-template <int TB, int TK, int KB>
-__device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP, int pp_base, int e_beg, const PGDesc& Q, int oct,
+// One warp task: noct groups of KB consecutive ket octets of pair type TK (starting with group oct) against every bra
+// primitive of type TB of P; the groups accumulate into one G fragment that is reduced into the tile's G once.
+template <int TB, int TK, int KB, int KO>
+__device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP, int pp_base, int e_beg, const PGDesc& Q, int oct0,
                                             const PrimPair* __restrict__ bpps, const SPRec* __restrict__ spss,
                                             const double* __restrict__ Dp_s /* first row = e_beg */, const double* __restrict__ Dq_g,
                                             const double* __restrict__ boys_tab, double* __restrict__ scratch,
@@ -74,7 +113,17 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
     const int g = lane >> 2, t = lane & 3;
     const int nk = Q.pp_beg[TK + 1] - Q.pp_beg[TK];
     const PrimPair* __restrict__ kl = A.pps_flat + Q.pp_beg[TK];
+    double C[4][4][2];
+    if constexpr (KO > 1) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
+    }
+    unsigned long long nq_task = 0ull;
+    auto octet_group = [&](const int oct) -> bool {     // false: nothing left further down the (sorted) ket list
     const int k0 = 8 * KB * oct;
+    if (k0 >= nk) return false;
     PrimPair b[KB];
     double wl[KB];                                     // this lane's own ket magnitudes (non-increasing in kb: the list is sorted)
 #pragma unroll
@@ -93,6 +142,9 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
 #pragma unroll
             for (int j = 0; j < 4; ++j) { X[kb][f][j][0] = 0.0; X[kb][f][j][1] = 0.0; }
     unsigned nq = 0;                                    // primitive quartets evaluated by this lane
+#ifdef VB_EXP_EFF
+    unsigned ntrip = 0;
+#endif
     for (int q0 = 0; q0 < nsp; q0 += 4) {
         // shell pairs are sorted by contraction length, not by weight: test the quad's own bound
         const bool sact = q0 + t < nsp;
@@ -111,27 +163,86 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
             const PrimPair a = bl[ip < cnt ? ip : 0];
             const bool act = ip < cnt && a.w * wl[0] >= A.tau;
             if (!__any_sync(0xffffffffu, act)) break;
+#ifdef VB_EXP_EFF
+            ntrip += KB;
+#endif
+            // All lanes and all KB kets in the asymptotic regime (true for most trips of a large cluster): straight-line
+            // code without a table look-up, so the KB chains interleave; otherwise the general routine per ket.
+            constexpr int M = pt_E(TB) + pt_E(TK);
+            bool actk[KB];
+            PrimPair ak[KB];
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
-                const bool actk = kb == 0 ? act : (act && a.w * wl[kb] >= A.tau);
-                PrimPair ak = a;
-                if (!actk) ak.Kp = 0.0;
-                quartet_values<TB, TK>(boys_tab, ak, b[kb], acc[kb]);
-                nq += actk ? 1u : 0u;
+                actk[kb] = kb == 0 ? act : (act && a.w * wl[kb] >= A.tau);
+                ak[kb] = a;
+                if (!actk[kb]) ak[kb].Kp = 0.0;
+                nq += actk[kb] ? 1u : 0u;
+            }
+            if constexpr (M == 0) {
+                double sv[KB];
+                bool far = true;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const double u = a.p + b[kb].p;
+                    const double dx = a.Px - b[kb].Px, dy = a.Py - b[kb].Py, dz = a.Pz - b[kb].Pz;
+                    const double sq = a.p * b[kb].p * (dx * dx + dy * dy + dz * dz);
+                    far = far && (!actk[kb] || sq >= BOYS_S_TMAX * u);
+                    sv[kb] = actk[kb] ? sq : 1.0;
+                }
+                if (__all_sync(0xffffffffu, far)) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) acc[kb][0] += ak[kb].Kp * b[kb].Kp * 0.88622692545275801365 * rsqrt_fast(sv[kb]);
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) quartet_values<TB, TK>(boys_tab, ak[kb], b[kb], acc[kb]);
+                }
+            } else {
+                constexpr int LA = pt_la(TB), EA = pt_E(TB), LC = pt_la(TK), EC = pt_E(TK);
+                QuartetGeom geo[KB];
+                double T[KB], pref[KB];
+                bool far = true;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    quartet_geom_fast(ak[kb], b[kb], geo[kb], T[kb], pref[kb]);
+                    far = far && (!actk[kb] || T[kb] >= BOYS_S_TMAX);
+                }
+                if (__all_sync(0xffffffffu, far)) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+                        double F[M + 1];
+                        boys_far<M>(actk[kb] ? T[kb] : 64.0, F);
+#pragma unroll
+                        for (int m = 0; m <= M; ++m) F[m] *= pref[kb];
+                        vrr_unrolled<LA, EA, LC, EC>(geo[kb], F, acc[kb]);
+                    }
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+                        double F[M + 1];
+                        boys_s<M>(boys_tab, T[kb], F);
+#pragma unroll
+                        for (int m = 0; m <= M; ++m) F[m] *= pref[kb];
+                        vrr_unrolled<LA, EA, LC, EC>(geo[kb], F, acc[kb]);
+                    }
+                }
             }
         }
         if (ip > 0) feed_dmma_kb<TB, TK, KB>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
     }
+#ifdef VB_EXP_EFF
+    if (lane == 0) atomicAdd(&A.pq_counters[18 + TB * 3 + TK], 32ull * ntrip);     // lane slots executed (experiment builds)
+#endif
     for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
-    if (!nq) return;
-    if (lane == 0) atomicAdd(s_pq, (unsigned long long)nq);
+    if (!nq) return false;                             // the ket list is sorted by magnitude: nothing further down either
+    nq_task += nq;
+    if constexpr (KO == 1) {                           // single-octet tasks: C only lives from here
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
+    }
     // G[q][p] += sum_{k,f} Dq[e_k + f][q] X_f[k][p]:  A'[q][k] from the ket densities, B'[k][p] = X_f re-laid out
-    // through the warp's scratch (C fragment -> B fragment); all KB octets accumulate into one C
-    double C[4][4][2];
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
+    // through the warp's scratch (C fragment -> B fragment); all octets of the task accumulate into one C
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) {
         const int eo_own = b[kb].eoff;
@@ -162,6 +273,16 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
             }
         }
     }
+    return true;
+    };   // octet groups of the task
+    if constexpr (KO == 1) octet_group(oct0);
+    else {
+#pragma unroll 1
+        for (int oct = oct0; oct < oct0 + KO; ++oct)
+            if (!octet_group(oct)) break;
+    }
+    if (!nq_task) return;
+    if (lane == 0) atomicAdd(s_pq, nq_task);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int q = 8 * m + g;
@@ -185,6 +306,12 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
 #ifndef VB_MB_PSPS
 #define VB_MB_PSPS 2
 #endif
+// octet groups per task (KO): classes with a pp bra pair have ONE quad of bra shell pairs, i.e. a few trips per octet --
+// their tasks take many octets so that the reduction of G into L2 (20 atomics per lane) is paid once per task
+#ifndef VB_KO_BPP
+#define VB_KO_BPP 64
+#endif
+__host__ __device__ constexpr int pc_ko(int tb, int tk) { return tb == 2 ? VB_KO_BPP : 1; }
 __host__ __device__ constexpr int pc_threads(int tb, int tk) { return 256; }
 __host__ __device__ constexpr int pc_minblocks(int tb, int tk)
 {
@@ -197,7 +324,7 @@ template <int TB, int TK>
 __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pclass(const TileArgs A, const ClassCfg C)
 {
     extern __shared__ __align__(16) double smem[];
-    constexpr int THREADS = pc_threads(TB, TK), nw = THREADS / 32, NE = pt_ne(TB), KB = pc_kb(TB, TK);
+    constexpr int THREADS = pc_threads(TB, TK), nw = THREADS / 32, NE = pt_ne(TB), KB = pc_kb(TB, TK), KO = pc_ko(TB, TK);
     double* Dp_s = smem;                                                   // bra densities of type TB
     double* scr = Dp_s + C.d_cap;                                          // per-warp X scratch
     double* boys_sm = scr + nw * PT_SCRATCH;                               // compact Boys table
@@ -257,7 +384,7 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
                 s_cum[qi] = n;
                 if (qi < ntl) {
                     const int nk = s_Q[qi].pp_beg[TK + 1] - s_Q[qi].pp_beg[TK];
-                    if (nk > 0 && P.kwmax[TB] * s_Q[qi].kwmax[TK] >= A.tau) n += (nk + 8 * KB - 1) / (8 * KB);
+                    if (nk > 0 && P.kwmax[TB] * s_Q[qi].kwmax[TK] >= A.tau) n += (nk + 8 * KB * KO - 1) / (8 * KB * KO);
                 }
             }
             s_cum[PT_MAXQ] = n;
@@ -275,10 +402,10 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
             if (u >= nunits) break;
             int qi = 0;
             while (s_cum[qi + 1] <= u) ++qi;
-            const int oct = u - s_cum[qi];
+            const int oct = (u - s_cum[qi]) * KO;
             const PGDesc& Q = s_Q[qi];
             double* Gglob = A.gbuf + ((size_t)item.z + qi - A.gslot_base) * A.g_cap;
-            pclass_task<TB, TK, KB>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, &s_pq);
+            pclass_task<TB, TK, KB, KO>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, &s_pq);
         }
     }
     __syncthreads();

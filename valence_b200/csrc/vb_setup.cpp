@@ -606,7 +606,7 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
             for (;;) {
                 size_t i0 = next.fetch_add(16);
                 if (i0 >= gh.size()) break;
-                if (opts.shard_mode == 1 && !owned(i0)) continue;
+                if ((opts.shard_mode == 1 || opts.shard_mode == 3) && !owned(i0)) continue;
                 for (size_t i = i0; i < std::min(gh.size(), i0 + 16); ++i) do_pair_group(gh[i].first, gh[i].second, 1, wcut, outs[i]);
             }
         });

@@ -105,6 +105,8 @@ struct TileOpts {
     // shard_prefix + rank (shared memory, e.g. /dev/shm/...), nothing else; shard_mode 2: take every pair group from the
     // published files of all ranks and merge -- tables bitwise identical to an unsharded build.  The caller
     // synchronises the ranks between the two calls.
+    // shard_mode 3: build this rank's share only and merge it alone (local offsets): the shares are exchanged on the DEVICE
+    // (NCCL all-gather over NVLink, vb_engine.cu: gather_tables) instead of through host shared memory.
     int shard_mode = 0, shard_rank = 0, shard_nranks = 1;
     std::string shard_prefix;
 };

@@ -14,10 +14,11 @@ namespace vb {
 // blocks of bra pair groups against chunks of ket pair groups (L2 residency), partners by decreasing Schwarz bound.
 // runs: (first tile, # tiles) of every non-empty (a, chunk).
 void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec, const std::vector<int>& bvec, double itol,
-                    std::vector<TilePair>* tl, std::vector<std::pair<long long, int>>* runs)
+                    std::vector<TilePair>* tl, std::vector<std::pair<long long, int>>* runs, int rank, int nranks)
 {
     tl->clear(); runs->clear();
-    const int PB = 128, QC = 1024;
+    const int PB = nranks > 1 ? 64 : 128, QC = 1024;
+    auto owner = [&](int blk) { const int k = blk % nranks; return ((blk / nranks) & 1) ? nranks - 1 - k : k; };
     const int na = (int)avec.size(), nb = (int)bvec.size();
     const int nchunks = (nb + QC - 1) / QC;
     std::vector<int> order(bvec);
@@ -33,6 +34,7 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
     std::vector<std::vector<TilePair>> btl(nblocks);
     std::vector<std::vector<std::pair<long long, int>>> bruns(nblocks);
     auto do_block = [&](int blk) {
+        if (nranks > 1 && owner(blk) != rank) return;
         const int B0 = blk * PB, B1 = std::min(na, B0 + PB);
         std::vector<TilePair>& t = btl[blk];
         std::vector<std::pair<long long, int>>& r = bruns[blk];
