@@ -11,5 +11,5 @@ e = api.Engine(p); r = e.energy(); e.close(); os.unlink(p)
 """ % ROOT
 env = dict(os.environ); env["VB_LIB_SUFFIX"] = "_eff"; env["VB_DEBUG_PQ"] = "1"
 out = subprocess.run([sys.executable, "-c", CHILD, sys.argv[1]], env=env, capture_output=True, text=True)
-print("\n".join(l for l in out.stdout.splitlines() if "lane efficiency" in l))
+print("\n".join(l for l in out.stdout.splitlines() if "lane efficiency" in l or "tasks" in l))
 print(out.stderr[-800:])

@@ -237,6 +237,11 @@ struct Engine::Impl {
     DBuf<int> fo_perm;
     void cofactor_stage(const Input& in, const Wavefunction& wf, bool diag_only, EnergyResult* out, bool* fast_out, double* c0_out, int* ndp_out);
     int only_isc = -1, only_jsc = -1;                 // spin_opt: restrict the cofactors to one coupling pair
+    // GPU inverse + determinant of Se[ent][ent] (Gauss-Jordan, then one double-double refinement step); res_dev[0] = det,
+    // res_dev[1] = smallest / largest pivot
+    void gpu_inverse(int nso, const std::vector<int>& ent, DBuf<int>& ent_dev, DBuf<double>& M, DBuf<double>& Minv, double* res_dev);
+    DBuf<double> Fmat, r1x, r1y, Qd, Rd, Ni;       // first_order_opt in rank-one form
+    DBuf<int> en_dev, eo_dev, posn_dev, poso_dev;
     bool use_gather = false;                         // energy(): table shares are exchanged on the device (all-gather)
     bool fo_collective = false;                      // first_order through the engine's communicator: decisions are agreed on
     std::vector<double> coeff_sc;                    // current spin-coupling weights
@@ -549,6 +554,29 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
     *fast_out = fast; *c0_out = c0; *ndp_out = ndp;
 }
 
+
+void Engine::Impl::gpu_inverse(int nso, const std::vector<int>& ent, DBuf<int>& ent_dev, DBuf<double>& M, DBuf<double>& Minv, double* res_dev)
+{
+    const int n = (int)ent.size();
+    ent_dev.upload(ent, st);
+    M.alloc((size_t)n * n + 1); Minv.alloc((size_t)n * n + 1);
+    if (n == 0) { const double one[2] = {1.0, 1.0}; CK(cudaMemcpyAsync(res_dev, one, sizeof one, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); return; }
+    k_gather_block<<<(n * n + 255) / 256, 256, 0, st>>>(Se.p, nso, ent_dev.p, ent_dev.p, n, M.p);
+    gj_ws.alloc(2 * (size_t)n); piv.alloc(2 * (size_t)n + 2);
+    int grid = std::max(1, std::min(nsm, n / 4));
+    double* Ap = M.p; double* Ip = Minv.p; double* wsp = gj_ws.p; int* iwp = piv.p; int nn = n;
+    void* args[] = {&Ap, &nn, &Ip, &wsp, &iwp, &res_dev};
+    CK(cudaLaunchCooperativeKernel((void*)k_gj_inverse_grid, dim3(grid), dim3(1024), args, 0, st));
+    k_gather_block<<<(n * n + 255) / 256, 256, 0, st>>>(Se.p, nso, ent_dev.p, ent_dev.p, n, M.p);
+    gj_res.alloc((size_t)n * n);
+    const dim3 g((n + RF_T - 1) / RF_T, (n + RF_T - 1) / RF_T), b(RF_T, RF_T);
+    k_inv_residual_dd<<<g, b, 0, st>>>(M.p, Minv.p, n, gj_res.p);
+    k_inv_update<<<g, b, 0, st>>>(Minv.p, gj_res.p, n, M.p);
+    CK(cudaGetLastError());
+    launches += 5;
+    std::swap(M.p, Minv.p); std::swap(M.cap, Minv.cap); std::swap(M.n, Minv.n);
+}
+
 // One vsvb_energy evaluation (valence.F90:1010-1434) for the bra/ket lists in wf.
 //   sch_in  : Schwarz table to screen with (first_order_opt reuses the unsubstituted one,
 //             valence.F90:667 vs 674-704); null -> run the diagonal pass (schwarz_ints)
@@ -843,6 +871,8 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
                 npq += (long long)pq[a * NPTYPE + b];
             }
         out->flops_model += fl; out->n_prim_quartets += npq;
+        if (std::getenv("VB_DEBUG_PQ") && pq[27])
+            std::printf("class (0|0): tasks %llu, empty %llu, bra quads run %llu, skipped %llu\n", pq[27], pq[28], pq[29], pq[30]);
         if (std::getenv("VB_DEBUG_PQ"))
             for (int c = 0; c < 9; ++c)
                 if (pq[18 + c]) std::printf("class (%d|%d): lane slots %llu, quartets %llu, lane efficiency %.3f\n", c / 3, c % 3, pq[18 + c], pq[(c / 3) * NPTYPE + c % 3], (double)pq[(c / 3) * NPTYPE + c % 3] / (double)pq[18 + c]);
@@ -1236,6 +1266,238 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     A.sch = this->sch.p;
     double tm2 = now_ms();
     if (dbg_time) { CK(cudaStreamSynchronize(st)); std::printf("[fo] tables %.1f ms, cache pass %.1f ms (%lld canonical tiles, %lld mine, %.2f GB), %lld variant tiles\n", tm1 - tm0, tm2 - tm1, (long long)tlc.size(), my_tiles, (double)my_tiles * cfg.g_cap * 8e-9, nvt); }
+    // ---- rank-one form of the (ib,jb) loop (large single-determinant wavefunctions) ------------------------------
+    // Substituting slot e of the bra by chi_ib and of the ket by chi_jb borders the block N (the spin block of the subject
+    // without it) by one row and one column:  det M' = det N * sigma,  M'^-1 = Nbar^-1 + abar bbar^T / sigma  with
+    // a = N^-1 c_jb, b = N^-T r_ib, sigma = <chi_ib|chi_jb> - r_ib^T a.  sigma * W' is then sigma * W0 plus terms bilinear in
+    // (x, y) = (bbar, abar): for the tiles free of the subject entry  sum G W' sigma = sigma E0 + x^T F y  with ONE Fock-like
+    // matrix F for all norbas(norbas+1)/2 elements (contract_tile<FMODE>); only the subject tiles are walked per element,
+    // with W' in rank-one form.  Nothing is divided by sigma, so a singular substituted block (a basis function orthogonal
+    // to the space it replaces, which Givens determinants handle silently) needs no special treatment.
+    {
+        int fast_min = 64;
+        if (const char* e = std::getenv("VB_FAST_MIN_N")) fast_min = std::atoi(e);
+        bool r1path = in.npair == 0 && std::max(in.nalpha(), in.nbeta()) > fast_min;
+        if (const char* e = std::getenv("VB_FO_RANK1")) r1path = r1path && std::atoi(e) != 0;
+        if (r1path) {
+            const int nelec = in.nelec(), nao = bas.nao;
+            // entry-level overlap / core-Hamiltonian of the unsubstituted lists
+            {
+                std::vector<int2> prs((size_t)nso * nso);
+                for (int a = 0; a < nso; ++a)
+                    for (int b = 0; b < nso; ++b) prs[(size_t)a * nso + b] = make_int2(wb.bra[wb.slot(a, 0)], wb.ket[wb.slot(b, 0)]);
+                opairs.upload(prs, st);
+                Se.alloc(prs.size()); He.alloc(prs.size());
+                k_orb_1e<<<(unsigned)((prs.size() + 127) / 128), 128, 0, st>>>(optr.p, oao.p, oc.p, opairs.p, (int)prs.size(), nao, S.p, H.p, Se.p, He.p);
+                CK(cudaGetLastError());
+                launches++;
+            }
+            // spin lists by slot position (set_up_unpaired_docc, valence.F90:2461-2480)
+            std::vector<int> entry_of_slot(wb.bra.size());
+            for (int a = 0; a < nso; ++a)
+                for (int k = 0; k < wb.nslots(a); ++k) entry_of_slot[wb.slot(a, k)] = a;
+            std::vector<int> ea, eb;
+            for (int i = 0; i < in.nunpd; ++i) ea.push_back(entry_of_slot[i]);
+            for (int d = 0; d < in.ndocc; ++d) { ea.push_back(entry_of_slot[in.nunpd + 2 * d]); eb.push_back(entry_of_slot[in.nunpd + 2 * d + 1]); }
+            const bool in_a = std::find(ea.begin(), ea.end(), es) != ea.end();
+            const std::vector<int>& esub = in_a ? ea : eb;
+            const std::vector<int>& eoth = in_a ? eb : ea;
+            if (std::find(esub.begin(), esub.end(), es) == esub.end()) throw std::runtime_error("valence_b200: first_order: subject entry not in a spin block");
+            std::vector<int> en, posn(nso, -1), poso(nso, -1);
+            for (int a : esub) if (a != es) { posn[a] = (int)en.size(); en.push_back(a); }
+            for (size_t k = 0; k < eoth.size(); ++k) poso[eoth[k]] = (int)k;
+            const int nn = (int)en.size(), no = (int)eoth.size();
+            gjout.alloc(4);
+            gpu_inverse(nso, en, en_dev, Ma, Ni, gjout.p);
+            gpu_inverse(nso, eoth, eo_dev, Mb, Mbi, gjout.p + 2);
+            std::vector<double> gd;
+            gjout.download(gd, st);
+            if (!(gd[0] != 0.0) || !(gd[2] != 0.0) || std::min(gd[1], gd[3]) < 1e-13)
+                throw std::runtime_error("valence_b200: singular spin-block overlap matrix (linearly dependent orbitals)");
+            const double Dd = gd[0] * gd[2];
+            posn_dev.upload(posn, st); poso_dev.upload(poso, st);
+            Qd.alloc((size_t)nso * nso); Rd.alloc((size_t)nso * nso);
+            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Ni.p, nn, posn_dev.p, posn_dev.p, nso, Qd.p);
+            k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mbi.p, no, poso_dev.p, poso_dev.p, nso, Rd.p);
+            one_e.alloc(2);
+            k_one_electron_energy<<<1, 1024, 0, st>>>(Se.p, He.p, Qd.p, Rd.p, nso * nso, one_e.p);
+            CK(cudaGetLastError());
+            launches += 3;
+            std::vector<double> oe;
+            one_e.download(oe, st);
+            const double E1_0 = oe[0], S0 = oe[1];
+            // ---- F pass over the free tiles: E2_0 and F ----
+            Fmat.alloc((size_t)nso * nso);
+            Fmat.zero(st);
+            tileE.alloc((size_t)std::max<long long>(1, nvt));
+            tileE.zero(st); counters.zero(st);
+            A.tiles = nullptr; A.ntiles = 0; A.items = nullptr; A.nitems = 0; A.mode = 1; A.tau = tau_energy;
+            A.Pa = Qd.p; A.Pb = Rd.p; A.c0 = 1.0; A.cof = nullptr; A.ndp = 0; A.r1 = 0; A.Fmat = Fmat.p; A.tileE = tileE.p;
+            {
+                std::vector<int> nshb(nso), nshk(nso);
+                for (int a = 0; a < nso; ++a) { nshb[a] = (int)orbs2e[wb.bra[wb.slot(a, 0)]].sh.size(); nshk[a] = (int)orbs2e[wb.ket[wb.slot(a, 0)]].sh.size(); }
+                nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
+                A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+            }
+            double E2_0 = 0.0;
+            std::vector<unsigned long long> cfree(CNT_N, 0ull);
+            CK(cudaEventRecord(ev2, st));
+            if (nvt > 0) {
+                const int grid = (int)std::min<long long>((nvt + CT_THREADS / 32 - 1) / (CT_THREADS / 32), (long long)nsm * 16);
+                k_contract<<<grid, CT_THREADS, 0, st>>>(A, vtiles.p, nvt, fo_perm.p, gcache.p, 0);
+                k_sum<<<1, 1024, 0, st>>>(tileE.p, nvt, accum.p);
+                CK(cudaGetLastError());
+                launches += 2;
+                CK(cudaMemcpyAsync(&E2_0, accum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+                counters.download(cfree, st);
+            }
+            CK(cudaEventRecord(ev3, st));
+            CK(cudaEventSynchronize(ev3));
+            { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev2, ev3)); acc->t_tiles += ms; if (dbg_time) std::printf("[fo] F pass %.1f ms (%lld variant tiles)\n", ms, nvt); }
+            A.Fmat = nullptr;
+            std::vector<double> hF, hHe, hSe, hNi;
+            Fmat.download(hF, st); He.download(hHe, st); Se.download(hSe, st); Ni.download(hNi, st);
+            // ---- overlaps / core-Hamiltonian elements with the dummy orbitals ----
+            auto dummy = [&](int k) { const int idf = in.orbitals[iorb].xp[k]; return idf < 1 ? norbs + idf - 1 : norbs + k; };
+            std::vector<int2> prs;
+            for (int ib = 0; ib < norbas; ++ib) for (int t = 0; t < nso; ++t) prs.push_back(make_int2(dummy(ib), wb.ket[wb.slot(t, 0)]));
+            for (int jb = 0; jb < norbas; ++jb) for (int a = 0; a < nso; ++a) prs.push_back(make_int2(wb.bra[wb.slot(a, 0)], dummy(jb)));
+            for (int ib = 0; ib < norbas; ++ib) for (int jb = 0; jb < norbas; ++jb) prs.push_back(make_int2(dummy(ib), dummy(jb)));
+            opairs.upload(prs, st);
+            DBuf<double> os, oh;
+            os.alloc(prs.size()); oh.alloc(prs.size());
+            k_orb_1e<<<(unsigned)((prs.size() + 127) / 128), 128, 0, st>>>(optr.p, oao.p, oc.p, opairs.p, (int)prs.size(), nao, S.p, H.p, os.p, oh.p);
+            CK(cudaGetLastError());
+            launches++;
+            std::vector<double> vs, vh;
+            os.download(vs, st); oh.download(vh, st);
+            const double* Sx = vs.data(); const double* Sy = Sx + (size_t)norbas * nso; const double* Sd = Sy + (size_t)norbas * nso;
+            const double* Hx = vh.data(); const double* Hy = Hx + (size_t)norbas * nso; const double* Hd = Hy + (size_t)norbas * nso;
+            // x_ib (bra side), y_jb (ket side): entry-indexed, -1 at the subject
+            std::vector<std::vector<double>> xs(norbas, std::vector<double>(nso, 0.0)), ys(norbas, std::vector<double>(nso, 0.0));
+            for (int k = 0; k < norbas; ++k) {
+                for (int r = 0; r < nn; ++r) {
+                    double a = 0.0, b = 0.0;
+                    for (int c = 0; c < nn; ++c) {
+                        a += hNi[(size_t)r * nn + c] * Sy[(size_t)k * nso + en[c]];      // a[k'] = sum_r Ninv[k'][r] c[r]
+                        b += Sx[(size_t)k * nso + en[c]] * hNi[(size_t)c * nn + r];      // b[r] = sum_c rrow[c] Ninv[c][r]
+                    }
+                    ys[k][en[r]] = a; xs[k][en[r]] = b;
+                }
+                xs[k][es] = -1.0; ys[k][es] = -1.0;
+            }
+            // F y_jb, He y_jb, Se y_jb over the entries other than the subject (rows s)
+            auto bil = [&](const std::vector<double>& Mx, const std::vector<double>& x, const std::vector<double>& y) {
+                double tsum = 0.0;
+                for (int a = 0; a < nso; ++a) {
+                    if (a == es || x[a] == 0.0) continue;
+                    double rs = 0.0;
+                    const double* row = Mx.data() + (size_t)a * nso;
+                    for (int b = 0; b < nso; ++b) if (b != es) rs += row[b] * y[b];
+                    tsum += x[a] * rs;
+                }
+                return tsum;
+            };
+            r1x.alloc(nso); r1y.alloc(nso);
+            std::vector<int> avec2, bvec2;
+            for (int ib = 0; ib < norbas; ++ib)
+                for (int jb = 0; jb <= ib; ++jb) {
+                    double tp0 = now_ms();
+                    substitute(ib, jb);
+                    const std::vector<double>& x = xs[ib];
+                    const std::vector<double>& y = ys[jb];
+                    double sigma = Sd[(size_t)ib * norbas + jb];
+                    for (int c = 0; c < nn; ++c) sigma -= Sx[(size_t)ib * nso + en[c]] * y[en[c]];
+                    // x^T He' y and x^T Se' y with row / column `es` of the substituted lists
+                    double xHy = bil(hHe, x, y), xSy = bil(hSe, x, y);
+                    for (int t = 0; t < nso; ++t) if (t != es) { xHy -= Hx[(size_t)ib * nso + t] * y[t]; xSy -= Sx[(size_t)ib * nso + t] * y[t]; }
+                    for (int a = 0; a < nso; ++a) if (a != es) { xHy -= x[a] * Hy[(size_t)jb * nso + a]; xSy -= x[a] * Sy[(size_t)jb * nso + a]; }
+                    xHy += Hd[(size_t)ib * norbas + jb]; xSy += Sd[(size_t)ib * norbas + jb];
+                    const double xFy = bil(hF, x, y);
+                    // ---- subject tiles with W' in rank-one form ----
+                    TileOpts so;
+                    so.isolate = es; so.only_subject = true; so.wcut = wall;
+                    TileSetup tsS;
+                    build_tiles(in, bas, w2, orbs2e, tau_diag, true, &tsS, so);
+                    const int nS = (int)tsS.pgs.size();
+                    if (tsS.max_np > 32) throw std::runtime_error("valence_b200: pair group too large");
+                    hp.resize(nfree);
+                    for (PGDesc pg : tsS.pgs) {
+                        pg.pair_beg += (int)fPairs;
+                        pg.d_off += (long long)fD;
+                        for (int t = 0; t <= NPTYPE; ++t) { pg.pp_beg[t] += (int)fPps; pg.sp_beg[t] += (int)fSps; }
+                        hp.push_back(pg);
+                    }
+                    for (SPRec& sr : tsS.sps) sr.pp_beg += (int)fPps;
+                    set_smax(hp, tsS.pg_pairs, fPairs, nfree);
+                    {
+                        std::vector<PGDesc> tail(hp.begin() + nfree, hp.end());
+                        pgs.upload_at(nfree, tail, st);
+                        pg_pairs.upload_at(2 * fPairs, tsS.pg_pairs, st);
+                        sps.upload_at(fSps, tsS.sps, st);
+                        pps.upload_at(fPps, tsS.pps, st);
+                        pps_flat.upload_at(fPps, tsS.pps_flat, st);
+                        dmat.upload_at(fD, tsS.dmat, st);
+                    }
+                    std::vector<int> nshb(nso), nshk(nso);
+                    for (int a = 0; a < nso; ++a) {
+                        nshb[a] = (int)orbs2e[w2.bra[w2.slot(a, 0)]].sh.size();
+                        nshk[a] = (int)orbs2e[w2.ket[w2.slot(a, 0)]].sh.size();
+                    }
+                    nsh_bra.upload(nshb, st); nsh_ket.upload(nshk, st);
+                    avec2.clear(); bvec2.clear();
+                    for (int q = nfree; q < nfree + nS; ++q) avec2.push_back(q);
+                    for (int q = 0; q < nfree + nS; ++q) bvec2.push_back(q);
+                    std::vector<TilePair> tls;
+                    make_tile_list(hp, avec2, bvec2, itol, &tls, &runs);
+                    std::vector<WorkItem> its;
+                    long long mine = 0;
+                    make_items(runs, (long long)tls.size(), nsm, rank, nranks, &its, &mine);
+                    const PtCfg c2 = pt_cfg(std::max(tsF.max_ne, tsS.max_ne), std::max(tsF.max_np, tsS.max_np), std::max(tsF.max_nsp, tsS.max_nsp),
+                                            std::max(tsF.max_npp, tsS.max_npp));
+                    if (c2.smem > PT_SMEM_MAX) throw std::runtime_error("valence_b200: orbital basis set too large for one pair-group tile");
+                    CK(cudaFuncSetAttribute(k_ptile<PART_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2.smem));
+                    fill_cfg(c2);
+                    const long long nts = (long long)tls.size();
+                    tiles.upload(tls, st); items.upload(its, st);
+                    tileE.alloc((size_t)std::max<long long>(1, nts));
+                    tileE.zero(st); counter.zero(st); counters.zero(st); pq_counters.zero(st);
+                    CK(cudaMemcpyAsync(r1x.p, x.data(), nso * sizeof(double), cudaMemcpyHostToDevice, st));
+                    CK(cudaMemcpyAsync(r1y.p, y.data(), nso * sizeof(double), cudaMemcpyHostToDevice, st));
+                    A.tiles = reinterpret_cast<const int2*>(tiles.p); A.ntiles = (int)nts; A.items = reinterpret_cast<const int4*>(items.p); A.nitems = (int)its.size();
+                    A.gbuf = nullptr; A.gslot_base = 0; A.mode = 1; A.tau = tau_energy;
+                    A.Pa = Qd.p; A.Pb = Rd.p; A.c0 = Dd; A.cof = nullptr; A.ndp = 0; A.r1 = 1; A.r1x = r1x.p; A.r1y = r1y.p; A.r1sigma = sigma;
+                    A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p; A.tileE = tileE.p;
+                    CK(cudaEventRecord(ev2, st));
+                    if (mine > 0) {
+                        k_ptile<PART_ALL><<<std::max(1, std::min(nsm, (int)its.size())), pt_threads(PART_ALL), c2.smem, st>>>(A);
+                        CK(cudaGetLastError());
+                        launches++;
+                        acc->tile_launches++;
+                    }
+                    CK(cudaEventRecord(ev3, st));
+                    k_sum<<<1, 1024, 0, st>>>(tileE.p, nts, accum.p);
+                    CK(cudaGetLastError());
+                    launches++;
+                    double e2s = 0.0;
+                    CK(cudaMemcpyAsync(&e2s, accum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+                    std::vector<unsigned long long> c;
+                    counters.download(c, st);
+                    add_pq();
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, ev2, ev3));
+                    acc->t_tiles += ms;
+                    acc->n_tiles += nts + nvt;
+                    for (int i = 0; i < CNT_N; ++i) acc->counters[i] += (long long)(c[i] + cfree[i]);
+                    const double num = Dd * (sigma * E2_0 + xFy) + e2s + (rank == 0 ? Dd * (sigma * E1_0 + xHy) : 0.0);
+                    (*ham)[(size_t)jb * norbas + ib] += num;
+                    (*ovl)[(size_t)jb * norbas + ib] += Dd * (sigma * S0 + xSy) / (double)nelec;
+                    if (dbg_time) std::printf("[fo] ib %d jb %d: sigma %.3e, subject tiles %lld, kernel %.1f ms, host %.1f ms\n", ib + 1, jb + 1, sigma, nts, ms, now_ms() - tp0 - ms);
+                }
+            A.r1 = 0;
+            return true;
+        }
+    }
     // ---- the (ib,jb) loop -------------------------------------------------------------------------------
     std::vector<int> avec, bvec;
     for (int ib = 0; ib < norbas; ++ib)

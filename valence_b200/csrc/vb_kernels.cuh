@@ -71,6 +71,14 @@ struct TileArgs {
     const int* pair_index;           // mode 2: (s*nso+t) -> dense pair index, or -1
     int npairs_total;
     int debug;                       // print every contracted entry (tiny inputs only)
+    // first_order_opt in rank-one form (vb_engine.cu: first_order_cached): the substituted alpha (or beta) block differs from
+    // the block N without the subject entry by one bordered row / column, so sigma * P' = sigma * Q + x y^T (Q in Pa, the
+    // other spin in Pb) and sigma * W' is sigma * W0 plus terms bilinear in (x, y)
+    int r1;                          // != 0: W' of the entries is taken in rank-one form
+    const double* r1x;               // x[s], bra side (from chi_ib), nso
+    const double* r1y;               // y[t], ket side (from chi_jb), nso
+    double r1sigma;                  // Schur complement <chi_ib|chi_jb> - r^T N^-1 c
+    double* Fmat;                    // FMODE pass: F[s][t] accumulators (nso x nso), see contract_tile
     double* gen_scratch;             // generic (d-shell) path scratch, GEN_SCRATCH doubles per thread
 };
 

@@ -143,13 +143,21 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
             for (int j = 0; j < 4; ++j) { X[kb][f][j][0] = 0.0; X[kb][f][j][1] = 0.0; }
     unsigned nq = 0;                                    // primitive quartets evaluated by this lane
 #ifdef VB_EXP_EFF
-    unsigned ntrip = 0;
+    unsigned ntrip = 0, nquad_run = 0, nquad_skip = 0;
 #endif
     for (int q0 = 0; q0 < nsp; q0 += 4) {
         // shell pairs are sorted by contraction length, not by weight: test the quad's own bound
         const bool sact = q0 + t < nsp;
         const SPRec sp = spss[q0 + (sact ? t : 0)];
-        if (!__any_sync(0xffffffffu, sact && sp.wmax * wk >= A.tau)) continue;
+        if (!__any_sync(0xffffffffu, sact && sp.wmax * wk >= A.tau)) {
+#ifdef VB_EXP_EFF
+            ++nquad_skip;
+#endif
+            continue;
+        }
+#ifdef VB_EXP_EFF
+        ++nquad_run;
+#endif
         const int cnt = (sact && sp.wmax * wl[0] >= A.tau) ? sp.pp_cnt : 0;
         const PrimPair* __restrict__ bl = bpps + (sp.pp_beg - pp_base);
         double acc[KB][NE * NF];
@@ -230,7 +238,13 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
         if (ip > 0) feed_dmma_kb<TB, TK, KB>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
     }
 #ifdef VB_EXP_EFF
-    if (lane == 0) atomicAdd(&A.pq_counters[18 + TB * 3 + TK], 32ull * ntrip);     // lane slots executed (experiment builds)
+    if (lane == 0) {                                   // experiment builds: lane slots, tasks, empty tasks, quads run / skipped
+        atomicAdd(&A.pq_counters[18 + TB * 3 + TK], 32ull * ntrip);
+        if (TB == 0 && TK == 0) {
+            atomicAdd(&A.pq_counters[27], 1ull); atomicAdd(&A.pq_counters[28], ntrip ? 0ull : 1ull);
+            atomicAdd(&A.pq_counters[29], (unsigned long long)nquad_run); atomicAdd(&A.pq_counters[30], (unsigned long long)nquad_skip);
+        }
+    }
 #endif
     for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
     if (!nq) return false;                             // the ket list is sorted by magnitude: nothing further down either
@@ -434,7 +448,7 @@ __global__ void __launch_bounds__(CI_THREADS, 2) k_contract_items(const TileArgs
         const double* __restrict__ src = A.gbuf + ((size_t)item.z + j - A.gslot_base) * A.g_cap;
         const int npP = P.np;
         auto gv = [&](int p, int q) { return __ldcs(&src[q * npP + p]); };
-        double epart = A.sym ? contract_tile<32, true>(A, P, Q, gv, lane, cnt) : contract_tile<32, false>(A, P, Q, gv, lane, cnt);
+        double epart = A.sym ? contract_tile<32, true, false>(A, P, Q, gv, lane, cnt) : contract_tile<32, false, false>(A, P, Q, gv, lane, cnt);
         for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
         if (lane == 0) A.tileE[item.x + j] = epart * A.c0;
     }

@@ -233,7 +233,23 @@ __device__ __forceinline__ void ptask(const TileArgs& A, const PGDesc& P, const 
 // tile's entries; returns this thread's share of the tile energy and adds to its counters.
 struct TileIdx { int np, pair_beg; };     // what the contraction needs of a pair group
 // SYM = A.sym as a compile-time constant: the image loops unroll and the image table stays in registers.
-template <int THREADS, bool SYM, class GFetch>
+// sigma * W'(a,b,c,d) for P'_alpha = Q + x y^T / sigma (the 1/sigma^2 terms cancel exactly, so this stays finite for a
+// singular substituted block):  sigma W0 + x_a y_b T_cd + x_c y_d T_ab - x_a y_d Q_cb - x_c y_b Q_ad,  T = Q + R
+__device__ __forceinline__ double w_rank1(const TileArgs& A, int nso, int a, int b, int c, int d)
+{
+    const double* __restrict__ Q = A.Pa;
+    const double* __restrict__ R = A.Pb;
+    const double qab = Q[a * nso + b], qcd = Q[c * nso + d], qad = Q[a * nso + d], qcb = Q[c * nso + b];
+    const double rab = R[a * nso + b], rcd = R[c * nso + d], rad = R[a * nso + d], rcb = R[c * nso + b];
+    const double w0 = __dmul_rn(qab + rab, qcd + rcd) - __dmul_rn(qad, qcb) - __dmul_rn(rad, rcb);
+    const double xa = A.r1x[a], xc = A.r1x[c], yb = A.r1y[b], yd = A.r1y[d];
+    return A.r1sigma * w0 + xa * yb * (qcd + rcd) + xc * yd * (qab + rab) - xa * yd * qcb - xc * yb * qad;
+}
+
+// FMODE (first_order_opt, tiles free of the subject entry): besides the energy with the base densities (W0), the
+// Fock-like matrix F[s][t] with  sum_entries val * (bilinear part of sigma W') = x^T F y  is accumulated, so that every
+// (ib,jb) element of ham needs no pass over these tiles at all.
+template <int THREADS, bool SYM, bool FMODE, class GFetch>
 __device__ __forceinline__ double contract_tile(const TileArgs& A, const TileIdx P, const TileIdx Q, GFetch&& Gval,
                                                 int tid, unsigned long long (&cnt)[CNT_N])
 {
@@ -309,7 +325,23 @@ __device__ __forceinline__ double contract_tile(const TileArgs& A, const TileIdx
             }
             if (shortcut && vd) cnt[CNT_SHORTCUT]++;
             if (A.debug) printf("ENTRY (%d %d|%d %d) val %.12f W %.12f vsig %d\n", a, b, c, d, val, A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d), (int)vsig);
-            if (vsig) wsum += val * (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d));
+            if (vsig) {
+                if constexpr (FMODE) {
+                    const double* __restrict__ Q = A.Pa;
+                    const double* __restrict__ R = A.Pb;
+                    const double qab = Q[a * nso + b], qcd = Q[c * nso + d], qad = Q[a * nso + d], qcb = Q[c * nso + b];
+                    const double rab = R[a * nso + b], rcd = R[c * nso + d], rad = R[a * nso + d], rcb = R[c * nso + b];
+                    wsum += val * (__dmul_rn(qab + rab, qcd + rcd) - __dmul_rn(qad, qcb) - __dmul_rn(rad, rcb));
+                    const double h = 0.5 * val;
+                    atomicAdd(&A.Fmat[a * nso + b], h * (qcd + rcd));
+                    atomicAdd(&A.Fmat[c * nso + d], h * (qab + rab));
+                    atomicAdd(&A.Fmat[a * nso + d], -h * qcb);
+                    atomicAdd(&A.Fmat[c * nso + b], -h * qad);
+                } else {
+                    wsum += val * (A.r1 ? w_rank1(A, nso, a, b, c, d)
+                                        : (A.ndp ? w_general(A.cof, A.ndp, A.cof_stride, nso, a, b, c, d) : w_term(A.Pa, A.Pb, nso, a, b, c, d)));
+                }
+            }
         }
         epart += 0.5 * wsum;
     }
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(pt_threads(PART), 1) k_ptile(const TileArgs A)
             const int npP = P.np;
             const TileIdx Pi{P.np, P.pair_beg}, Qi{s_Q[qi].np, s_Q[qi].pair_beg};
             auto gv = [&](int p, int q) { return G_s[q * npP + p]; };
-            double epart = A.sym ? contract_tile<PT_THREADS, true>(A, Pi, Qi, gv, tid, cnt) : contract_tile<PT_THREADS, false>(A, Pi, Qi, gv, tid, cnt);
+            double epart = A.sym ? contract_tile<PT_THREADS, true, false>(A, Pi, Qi, gv, tid, cnt) : contract_tile<PT_THREADS, false, false>(A, Pi, Qi, gv, tid, cnt);
             if (A.mode == 1) {
                 for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
                 if (lane == 0) s_red[warp][qi] = epart;
@@ -543,7 +575,9 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_contract(const TileArgs A, co
             const int pc = perm[P.pair_beg + p], qc = perm[Q.pair_beg + q];
             return swp ? src[pc * Q.np + qc] : src[qc * P.np + pc];
         };
-        double epart = A.sym ? contract_tile<32, true>(A, P, Q, gv, lane, cnt) : contract_tile<32, false>(A, P, Q, gv, lane, cnt);
+        double epart;
+        if (A.Fmat) epart = contract_tile<32, false, true>(A, P, Q, gv, lane, cnt);      // first_order_opt: W0 energy + F accumulators
+        else epart = A.sym ? contract_tile<32, true, false>(A, P, Q, gv, lane, cnt) : contract_tile<32, false, false>(A, P, Q, gv, lane, cnt);
         for (int o = 16; o > 0; o >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, o);
         if (lane == 0) A.tileE[tile_base + it] = epart * A.c0;
     }
