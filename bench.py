@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the VSVB energy hot path (BASELINE.json metric: contracted shell quartets / s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--waters M] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--sweep 16,32,64,128] [--impl ours|reference]
 
-One step = one pass of the hot path: guess_energy (one vsvb_energy evaluation: one-electron
-part, spin-block inverses, Schwarz pass, fused ERI + contraction pass) of a synthetic
-(H2O)_M cluster, 6-31G, five DOCC orbitals per monomer (SURVEY.md section 8d, config 5;
-tolerances `10 20 10`, see DESIGN.md "Tolerances").  Default M = 256, the cluster BASELINE.json's
-north_star names (768 atoms, 3328 AOs, 1280 doubly occupied orbitals); it fits one GPU.  The unit counted is the reference's:
-one contracted AO shell quartet evaluated and digested = one simint_compute_eri call of the
-reference algorithm (/root/reference/src/valence.F90:3398); the count comes from the engine's
-bit-exact screening counters, so recomputation the GPU formulation avoids still counts once per
-reference call.  `unique_ao_quartets_per_s` reports what the GPU actually generates.
+One step = one pass of the hot path through the library's public call: geometry in from (pinned) host memory,
+guess_energy (one vsvb_energy evaluation: AO one-electron matrices, spin-block inverses, pair tables, Schwarz pass,
+fused ERI + contraction pass), energy out to the host.  Workloads:
+    w256 (default)  synthetic (H2O)_256, 6-31G, five DOCC orbitals per monomer -- the cluster BASELINE.json's north_star
+                    names (768 atoms, 3328 AOs, 1280 doubly occupied orbitals); tolerances `10 20 10`
+    w<N>            the same generator at N molecules
+    lif128          the reconstructed examples/lif128 (4x4x8 LiF lattice, 384 DOCC orbitals), tolerances 9 20 8
+    h2o, c3h8, cu+.3d94s1   the reference's example inputs verbatim (configs 1-3 of BASELINE.json)
+The unit counted is the reference's: one contracted AO shell quartet evaluated and digested = one simint_compute_eri
+call of the reference algorithm (/root/reference/src/valence.F90:3398); the count comes from the engine's bit-exact
+screening counters, so recomputation the GPU formulation avoids still counts once per reference call.
+`primitive_quartets_per_step` is what the GPU actually evaluates.
+
+`parity` compares the step's energy and counters with the fast CPU oracle's committed result for the same input
+(tests/golden/fast__*.json) when there is one.
 
 Metric 2 (`energy_plus_first_order`): wall time of one guess energy plus the first_order_opt matrices (ham, ovl) of
-orbital 1 on the same cluster, through the sharded C-ABI calls.
+orbital 1 on the same input.
 
-N > 1 (torchrun): the tile list is sharded block-cyclically over ranks with work stealing
-inside each GPU; one NCCL all-reduce of the packed accumulators per step; "scaling": "strong"
-(the same cluster is split over more GPUs).
+N > 1 (torchrun): one process per GPU; the ranks form an NCCL communicator INSIDE the library (vb_nccl.cpp), the tile
+list is split by bra blocks, the table shares are all-gathered over NVLink and ONE all-reduce sums the packed
+accumulators per step; "scaling": "strong" (the same input is split over more GPUs).
 """
 from __future__ import annotations
 
@@ -36,15 +42,41 @@ sys.path.insert(0, ROOT)
 
 METRIC = "contracted_shell_quartets_per_s"
 UNIT = "shell quartets/s"
+EXAMPLES = {"h2o": "examples__h2o", "c3h8": "examples__c3h8", "cu+.3d94s1": "examples__cu+.3d94s1"}
 
 
-def make_input(waters: int) -> str:
+def workload_input(name: str):
+    """(ValenceInput, description, fixture case or None)"""
     from valence_b200 import inputs
-    inp = inputs.water_cluster(waters, tol=(10, 20, 10))
-    fd, path = tempfile.mkstemp(prefix=f"h2o_{waters}_", suffix=".inp")
+    if name.startswith("w") and name[1:].isdigit():
+        n = int(name[1:])
+        return inputs.water_cluster(n, tol=(10, 20, 10)), f"(H2O)_{n} 6-31G VSVB guess energy, tolerances 10 20 10", name
+    if name == "lif128":
+        return inputs.lif_cluster(tol=(9, 20, 8)), "LiF 4x4x8 lattice (reconstructed examples/lif128) VSVB guess energy, tolerances 9 20 8", "lif128"
+    if name in EXAMPLES:
+        with open(os.path.join(ROOT, "tests", "golden", EXAMPLES[name] + ".json")) as fh:
+            d = json.load(fh)
+        return inputs.ValenceInput.from_json(d["input"]), f"examples/{name} (reference input verbatim) VSVB guess energy", None
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_input(name: str):
+    from valence_b200 import inputs
+    inp, desc, case = workload_input(name)
+    fd, path = tempfile.mkstemp(prefix=f"vb_{name.replace('/', '_')}_", suffix=".inp")
     with os.fdopen(fd, "w") as fh:
         fh.write(inputs.write(inp))
-    return path
+    return path, inp, desc, case
+
+
+def fixture(case):
+    if not case:
+        return None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", f"fast__{case}.json")) as fh:
+            return json.load(fh)
+    except OSError:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -79,20 +111,27 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def traffic_from_profiles(waters: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the energy-pass launch of k_ptile for this cluster size, from the
-    committed ncu capture (profiles/r1_k_ptile_dram_H2O<M>.csv); None when no capture of this size exists."""
-    path = os.path.join(ROOT, "profiles", f"r1_k_ptile_dram_H2O{waters}.csv")
+def traffic_from_profiles(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the class-pass launches for this workload, summed over the launches of
+    one energy pass, from the committed ncu capture (profiles/r2_pclass_dram_<workload>.csv); None when there is none."""
+    path = os.path.join(ROOT, "profiles", f"r2_pclass_dram_{workload}.csv")
     try:
         tot = 0.0
         with open(path) as fh:
             for line in fh:
                 f = [x.strip().strip('"') for x in line.split(",")]
-                if len(f) >= 3 and f[0].startswith("dram__bytes_") and f[0].endswith(".sum"):
-                    tot += float(f[1])
+                if len(f) >= 3 and f[1].startswith("dram__bytes_") and f[1].endswith(".sum"):
+                    tot += float(f[2])
         return tot or None
     except OSError:
         return None
+
+
+def cpu_sample_label(seconds: float, cores: int) -> str:
+    return (f"{seconds:.0f} s of the reference's own task list on the same input -- this rank's share of schwarz_ints "
+            f"(valence.F90:1489-1523) and then of the 2e loop (:1163-1433), literal C restatement, no AO memoisation, no integral "
+            f"cache, round-robin over {cores} processes as the reference's MPI ranks; for the large clusters the sample ends inside "
+            f"schwarz_ints, i.e. it times int2e shell-quartet loops only and no n^3 Givens determinant of the 2e loop")
 
 
 def run_reference(args) -> None:
@@ -102,7 +141,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     from oracle import oracle
-    path = make_input(args.waters)
+    path, inp, desc, case = make_input(args.workload)
     cores = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
     vals = []
@@ -116,13 +155,25 @@ def run_reference(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"(H2O)_{args.waters} 6-31G VSVB guess energy, tolerances 10 20 10", "waters": args.waters},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{per_step:.0f} s per step of the reference task list (schwarz_ints then the 2e loop), "
-                                       f"round-robin over {cores} processes, no integral cache"},
+            "config": {"workload": desc, "name": args.workload},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_label(per_step, cores) + " (per step)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     os.unlink(path)
+
+
+def timed_steps(eng, x_host, steps, warmup, barrier):
+    for _ in range(warmup):
+        eng.set_coords(x_host.numpy())
+        eng.energy()
+    barrier()
+    t0 = time.perf_counter()
+    res = []
+    for _ in range(steps):
+        eng.set_coords(x_host.numpy())
+        res.append(eng.energy())
+    barrier()
+    return res, time.perf_counter() - t0
 
 
 def run_ours(args) -> None:
@@ -134,42 +185,16 @@ def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        # all ranks of the node build their host tables at the same time: share the cores instead of oversubscribing them
-        # (the tables do not depend on the thread count: tests/host/test_setup_host.cpp)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))     # only for the timing barriers / max over ranks
+        # all ranks of the node build their share of the host tables at the same time: share the cores
         os.environ.setdefault("VB_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // world)))
     torch.cuda.set_device(local)
-    path = make_input(args.waters)
-    eng = api.Engine(path, device=local)
-    natom = eng.natom
-    # host-side inputs of one step: the geometry the reference API receives (valence_api.F90:37)
-    from valence_b200 import inputs as vin
-    x_host = torch.tensor(vin.parse_file(path).coords, dtype=torch.float64).flatten().pin_memory()
 
     def barrier():
         torch.cuda.synchronize(local)
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(local)
-
-    def step():
-        eng.set_coords(x_host.numpy())
-        return eng.energy_distributed(rank, world)
-
-    peak = api.measure_fp64_peak(local)
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    results = [step() for _ in range(args.steps)]
-    barrier()
-    wall = time.perf_counter() - t0
-    if sampler:
-        sampler.stop_flag.set()
-        sampler.join(timeout=3)
 
     def red(v, op):
         if world == 1:
@@ -179,85 +204,126 @@ def run_ours(args) -> None:
         return float(t.item())
 
     R = dist.ReduceOp if world > 1 else None
-    wall = red(wall, R.MAX if R else None)
-    # Metric 2: guess energy + one first_order_opt accumulator build (ham, ovl of orbital 1) on the same
-    # cluster, tiles sharded over the ranks, one all-reduce of the accumulators and one of ham.  The (ib,jb) loop reuses
-    # the integrals of all tiles that do not touch the substituted orbital from an HBM cache.
+    MAX, SUM = (R.MAX, R.SUM) if R else (None, None)
+    peak = api.measure_fp64_peak(local)
+
+    def measure(name, steps, warmup, sample_clocks):
+        """Time `steps` steps of workload `name`; returns the per-workload record (rank 0) and the engine."""
+        path, inp, desc, case = make_input(name)
+        eng = api.Engine(path, device=local)
+        if world > 1:
+            eng.attach_comm(rank, world)                 # NCCL inside the library: energy() is collective from here on
+        x_host = torch.tensor(inp.coords, dtype=torch.float64).flatten().pin_memory()
+        sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
+        if sampler:
+            # warm-up happens inside timed_steps before its barrier; the sampler covers warm-up + timed region
+            sampler.start()
+        results, wall = timed_steps(eng, x_host, steps, warmup, barrier)
+        if sampler:
+            sampler.stop_flag.set()
+            sampler.join(timeout=3)
+        wall = red(wall, MAX)
+        dev_ms = red(sum(r["t_1e_ms"] + r["t_density_ms"] + r["t_diag_ms"] + r["t_tiles_ms"] for r in results) / steps, MAX)
+        tile_ms = red(sum(r["t_tiles_ms"] for r in results) / steps, MAX)
+        flops_rank = sum(r["flops_model"] for r in results) / steps
+        tile_ms_rank = sum(r["t_tiles_ms"] for r in results) / steps
+        launches = red(float(sum(r["launches"] for r in results)), SUM)
+        primq = red(sum(r["n_prim_quartets"] for r in results) / steps, SUM)
+        farq = red(sum(r["n_ao_quartets"] for r in results) / steps, SUM)
+        last = results[-1]
+        refq = last["ref_shell_quartets"]                # all-reduced inside the library: the whole job's count
+        e2e_ms = 1e3 * wall / steps
+        achieved = flops_rank / (tile_ms_rank * 1e-3) / 1e12 if tile_ms_rank > 0 else 0.0
+        rec = {"name": name, "workload": desc, "natom": eng.natom, "electrons": eng.nelec, "ms_per_step": dev_ms, "wall_ms_per_step": e2e_ms,
+               "tile_pass_ms_per_step": tile_ms, "value": refq / (dev_ms * 1e-3), "e2e_value": refq / (e2e_ms * 1e-3),
+               "energy_hartree": last["energy"], "reference_algorithm_shell_quartets_per_step": refq,
+               "primitive_quartets_per_step": primq, "far_field_primitive_quartets_per_step": farq,
+               "h2d_bytes_per_step": int(last.get("h2d_bytes", 0)) or 24 * eng.natom, "d2h_bytes_per_step": int(last.get("d2h_bytes", 0)) or 8,
+               "gpu_launches": int(launches), "roofline_achieved_tflops": achieved, "roofline_frac": achieved / peak if peak else None,
+               "clocks": sampler.summary() if sampler else None}
+        fx = fixture(case)
+        if fx is not None:
+            cnt = last["counters"]
+            keys = ("schwarz_erep", "schwarz_exch", "int2e_calls", "shell_quartets_2e", "shortcut", "value_erep", "value_exch")
+            rec["parity"] = {"oracle": "oracle/vo_fast.c, committed as tests/golden/fast__%s.json" % case, "oracle_energy": fx["energy"],
+                             "dE_hartree": last["energy"] - fx["energy"], "counters_identical": all(cnt[k] == fx["counters"][k] for k in keys),
+                             "oracle_cpu_seconds": fx.get("seconds"), "oracle_threads": fx.get("threads")}
+        return rec, eng, path, inp
+
+    rec, eng, path, inp = measure(args.workload, args.steps, args.warmup, True)
+
+    # Metric 2 (SURVEY.md 8d): guess energy + one first_order_opt accumulator build (ham, ovl of orbital 1) on the same input.
     grad = None
-    os.environ.setdefault("VB_FO_REQUIRE_CACHE", "1")      # never fall back to 36 full tile passes inside the bench
-    if args.grad_waters != 0:
-        gw = args.waters if args.grad_waters < 0 else args.grad_waters
-        ge, gp = eng, None
-        if gw != args.waters:
-            gp = make_input(gw)
-            ge = api.Engine(gp, device=local)
-            ge.energy_distributed(rank, world)
+    os.environ.setdefault("VB_FO_REQUIRE_CACHE", "1")      # never fall back to norbas^2/2 full tile passes inside the bench
+    if not args.no_grad:
         barrier()
         t0g = time.perf_counter()
         try:
-            rg = ge.energy_distributed(rank, world)
-            Hg, Sg, st = ge.first_order_distributed(1, rank, world)
+            rg = eng.energy()
+            Hg, Sg, st = eng.first_order(1)
             barrier()
-            tg = red(time.perf_counter() - t0g, R.MAX if R else None)
+            tg = red(time.perf_counter() - t0g, MAX)
             import numpy as np
-            cw = np.array([w for _, w in vin.water_cluster(gw, tol=(10, 20, 10)).orbitals[0].terms])
-            grad = {"waters": gw, "ms": 1e3 * tg, "orbital": 1, "matrix_order": int(Hg.shape[0]),
-                    "first_order_kernel_ms": red(st["t_tiles_ms"], R.MAX if R else None),
-                    "kernel_launches": int(st["launches"]),
+            cw = np.array([w for _, w in inp.orbitals[0].terms])
+            grad = {"ms": 1e3 * tg, "orbital": 1, "matrix_order": int(Hg.shape[0]),
+                    "first_order_kernel_ms": red(st["t_tiles_ms"], MAX), "kernel_launches": int(st["launches"]),
+                    "method": "rank-one form: one Fock-like matrix pass over the tiles free of the subject orbital + the subject tiles per element",
                     "rayleigh_quotient_minus_energy": float(cw @ Hg @ cw / (cw @ Sg @ cw)) + rg["enucrep"] - rg["energy"]}
         except RuntimeError as ex:      # metric 2 must never cost the headline line
-            grad = {"waters": gw, "error": str(ex)[:200]}
-        if gp is not None:
-            ge.close(); os.unlink(gp)
-    dev_ms = sum(r["t_1e_ms"] + r["t_density_ms"] + r["t_diag_ms"] + r["t_tiles_ms"] for r in results) / args.steps
-    dev_ms = red(dev_ms, R.MAX if R else None)
-    tile_ms = red(sum(r["t_tiles_ms"] for r in results) / args.steps, R.MAX if R else None)
-    flops = red(sum(r["flops_model"] for r in results) / args.steps, R.SUM if R else None)
-    flops_rank = sum(r["flops_model"] for r in results) / args.steps
-    tile_ms_rank = sum(r["t_tiles_ms"] for r in results) / args.steps
-    launches = red(float(sum(r["launches"] for r in results)), R.SUM if R else None)
-    primq = red(sum(r["n_prim_quartets"] for r in results) / args.steps, R.SUM if R else None)
-    last = results[-1]
-    ref_quartets = last["ref_shell_quartets"]          # all-reduced: the whole job's count
+            grad = {"error": str(ex)[:200]}
+    eng.close()
+
+    # scaling sweep over cluster sizes (config 5): short runs, same call path
+    sweep = []
+    for n in args.sweep:
+        r2, e2, p2, _ = measure(f"w{n}", 2, 1, False)
+        e2.close()
+        os.unlink(p2)
+        if rank == 0:
+            sweep.append({k: r2[k] for k in ("name", "ms_per_step", "wall_ms_per_step", "tile_pass_ms_per_step", "value", "e2e_value", "energy_hartree",
+                                             "primitive_quartets_per_step", "roofline_achieved_tflops", "roofline_frac") if k in r2} | ({"parity": r2["parity"]} if "parity" in r2 else {}))
+
     if rank == 0:
-        e2e_ms = 1e3 * wall / args.steps
-        achieved = flops_rank / (tile_ms_rank * 1e-3) / 1e12 if tile_ms_rank > 0 else 0.0
         line = {
-            "metric": METRIC, "value": ref_quartets / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"(H2O)_{args.waters} 6-31G VSVB guess energy, tolerances 10 20 10", "waters": args.waters,
-                       "orbitals": 5 * args.waters, "electrons": 10 * args.waters,
-                       "l2": "every step regenerates and re-uploads its tables (>= L2 only for large clusters); "
-                             "integral data never leaves the SM, so the timed kernel has no warm-cache advantage",
-                       "parallelism": f"tile list block-cyclic over {world} GPU(s) + work stealing, 1 NCCL all-reduce/step"},
-            "energy_hartree": last["energy"],
-            "reference_algorithm_shell_quartets_per_step": ref_quartets,
-            "primitive_quartets_per_step": primq,
-            "wall_ms_per_step": e2e_ms,
-            "tile_kernel_ms_per_step": tile_ms,
-            "e2e": {"value": ref_quartets / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(last.get("h2d_bytes", 0)) or 24 * natom,
-                    "d2h_bytes_per_step": int(last.get("d2h_bytes", 0)) or 8,
-                    "note": "valence_api-style call: geometry in from (pinned) host memory, energy out to host; all basis / "
-                            "pair tables are rebuilt on the host and copied to the device inside the timed region"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic_from_profiles(args.waters), "kernel": "k_ptile<0> (fused primitive ERI + DMMA density transforms + cofactor contraction)",
+            "config": {"workload": rec["workload"], "name": args.workload, "atoms": rec["natom"], "electrons": rec["electrons"],
+                       "l2": "every step rebuilds and re-uploads its tables (0.6 GB for (H2O)_256, > L2) and streams 38 GB of "
+                             "orbital-level integral blocks through HBM/L2: no warm-cache advantage between steps",
+                       "parallelism": f"{world} GPU(s): tile list split by bra blocks, table shares all-gathered over NVLink, 1 NCCL all-reduce/step (in-library)"},
+            "energy_hartree": rec["energy_hartree"],
+            "reference_algorithm_shell_quartets_per_step": rec["reference_algorithm_shell_quartets_per_step"],
+            "primitive_quartets_per_step": rec["primitive_quartets_per_step"],
+            "far_field_primitive_quartets_per_step": rec["far_field_primitive_quartets_per_step"],
+            "wall_ms_per_step": rec["wall_ms_per_step"],
+            "tile_pass_ms_per_step": rec["tile_pass_ms_per_step"],
+            "e2e": {"value": rec["e2e_value"], "unit": UNIT, "ms_per_step": rec["wall_ms_per_step"],
+                    "h2d_bytes_per_step": rec["h2d_bytes_per_step"], "d2h_bytes_per_step": rec["d2h_bytes_per_step"],
+                    "note": "valence_api-style call: geometry in from (pinned) host memory, energy out to host; all basis / pair tables "
+                            "are rebuilt on the host and copied to the device inside the timed region"},
+            "gpu_launches": rec["gpu_launches"],
+            "roofline": {"bound": "fp64", "achieved": rec["roofline_achieved_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": rec["roofline_frac"],
+                         "traffic": traffic_from_profiles(args.workload),
+                         "kernel": "tile pass = k_pclass<TB,TK> x 9 integral classes (fused primitive ERI + DMMA density transforms, FP64 reductions "
+                                   "of the orbital-level blocks at L2) + k_contract_items (screening + cofactor contraction)",
                          "peak_source": "measured here: DFMA micro-benchmark vb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
-                         "flops": "algorithmic: executed primitive quartets per class x per-class operation count (DESIGN.md)"},
-            "clocks": sampler.summary() if sampler else None,
+                         "flops": "algorithmic, as executed: primitive quartets per class from in-kernel counters x the class's operation count, "
+                                  "quartets in the asymptotic regime (T >= 40) at their shorter count; the DMMA transform flops are not counted (DESIGN.md)"},
+            "clocks": rec["clocks"],
         }
+        if "parity" in rec:
+            line["parity"] = rec["parity"]
         if grad is not None:
             line["energy_plus_first_order"] = grad
+        if sweep:
+            line["sweep"] = sweep
         if args.cpu_baseline_seconds > 0 and world == 1:
             from oracle import oracle
             cb = oracle.cpu_baseline(path, seconds=args.cpu_baseline_seconds)
             line["cpu_baseline"] = {"value": cb["quartets_per_s"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
-                                    "sample": f"{cb['seconds']:.1f} s of the reference task list (schwarz_ints then the 2e loop) on the same "
-                                              f"workload, round-robin over {cb['cores']} processes, no integral cache"}
+                                    "sample": cpu_sample_label(cb["seconds"], cb["cores"])}
         print(json.dumps(line), flush=True)
-    eng.close()
     os.unlink(path)
     if world > 1:
         dist.destroy_process_group()
@@ -268,12 +334,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--waters", type=int, default=int(os.environ.get("VB_BENCH_WATERS", "256")))
+    ap.add_argument("--workload", default=os.environ.get("VB_BENCH_WORKLOAD", "w256"))
+    ap.add_argument("--waters", type=int, default=0, help="shorthand for --workload w<N>")
+    ap.add_argument("--sweep", default=os.environ.get("VB_BENCH_SWEEP", "16,32,64,128"),
+                    help="cluster sizes of the scaling sweep reported in `sweep` ('' = none)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
-    ap.add_argument("--grad-waters", type=int, default=-1,
-                    help="cluster size of the energy + first_order_opt timing (metric 2); -1 = the bench cluster, 0 = skip")
+    ap.add_argument("--no-grad", action="store_true", help="skip metric 2 (energy + first_order_opt matrices)")
+    ap.add_argument("--grad-waters", type=int, default=-1, help="(kept for compatibility) 0 = skip metric 2")
     args = ap.parse_args()
+    if args.waters:
+        args.workload = f"w{args.waters}"
+    if args.grad_waters == 0:
+        args.no_grad = True
+    args.sweep = [int(x) for x in str(args.sweep).split(",") if x.strip()]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/valence_b200.h but not exported"
 
 
+def test_fortran_binding_source_matches_header():
+    """fortran/valence_b200.f90 (the ISO_C_BINDING module a Fortran host compiles) binds only symbols the header declares,
+    and the result type lists the same members in the same order as the C struct."""
+    f90 = open(os.path.join(ROOT, "fortran", "valence_b200.f90")).read()
+    bound = set(re.findall(r'bind\(c,\s*name="([a-z_0-9]+)"\)', f90))
+    declared = set(declared_symbols())
+    assert bound and bound <= declared, sorted(bound - declared)
+    for must in ("vb_engine_create", "vb_engine_energy", "vb_engine_first_order", "vb_engine_attach_comm", "vb_engine_run"):
+        assert must in bound
+    hdr = open(os.path.join(ROOT, "include", "valence_b200.h")).read()
+    cstruct = hdr[hdr.index("typedef struct vb_energy_result {"):hdr.index("} vb_energy_result;")]
+    cstruct = re.sub(r"/\*.*?\*/", "", cstruct, flags=re.S)
+    c_members = [m for decl in re.findall(r"(?:double|long long|int)\s+([^;]+);", cstruct) for m in re.split(r",\s*", re.sub(r"\[.*?\]", "", decl).strip())]
+    ftype = f90[f90.index("type, bind(c) :: vb_energy_result"):f90.index("end type vb_energy_result")]
+    ftype = re.sub(r"!.*", "", ftype)
+    f_members = [m for decl in re.findall(r"::\s*(.+)", ftype)[1:] for m in re.split(r",\s*", re.sub(r"\(.*?\)", "", decl).strip())]
+    assert [m.strip() for m in c_members] == [m.strip() for m in f_members]
+
+
 def test_engine_fails_loudly_without_gpu(write_input):
     """No CPU fallback: creating an engine without a CUDA device must raise."""
     import torch

@@ -85,11 +85,15 @@ double now_ms()
 }
 
 // algorithmic FP64 operation count of one primitive quartet of class (tb | tk); FMA = 2
-double flops_prim_quartet(int tb, int tk)
+// far != 0: the quartet is in the asymptotic regime T >= 40 (one reciprocal square root instead of the table look-up and
+// Taylor series; (ss|ss) also skips the general geometry): what the class kernels execute for it
+double flops_prim_quartet(int tb, int tk, int far = 0)
 {
     const int LA = pt_la(tb), EA = pt_E(tb), LC = pt_la(tk), EC = pt_E(tk), M = EA + EC;
+    if (far && M == 0) return 27.0;                   // |PQ|^2, p q, test, rsqrt (9), K_a K_b sqrt(pi)/2, accumulate
     double f = 45.0;                                  // geometry, T, prefactor (1 rsqrt, 1 div)
-    f += 16.0 + (M > 0 ? 25.0 + 3.0 * M : 0.0);       // Boys: 8-term Taylor (+ exp and downward recursion)
+    if (far) f += 10.0 + 3.0 * M;                     // F_0 = sqrt(pi/T)/2, upward recursion
+    else f += 16.0 + (M > 0 ? 25.0 + 3.0 * M : 0.0);  // Boys: 8-term Taylor (+ exp and downward recursion)
     f += M + 1;                                       // prefactor scaling
     const int NE = ncum(EA), NF = ncum(EC);
     for (int e = 1; e < NE; ++e) {
@@ -864,18 +868,16 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         std::vector<unsigned long long> pq;
         pq_counters.download(pq, st);
         double fl = 0.0;
-        long long npq = 0;
+        long long npq = 0, nfarq = 0;
         for (int a = 0; a < NPTYPE; ++a)
             for (int b = 0; b < NPTYPE; ++b) {
-                fl += (double)pq[a * NPTYPE + b] * flops_prim_quartet(a, b);
+                if (!gen && (a >= 3 || b >= 3)) continue;      // s/p runs: the upper slots hold the far-field counts of the class kernels
+                const unsigned long long far = (!gen && a < 3 && b < 3) ? std::min(pq[PQ_FAR + a * 3 + b], pq[a * NPTYPE + b]) : 0ull;
+                fl += (double)(pq[a * NPTYPE + b] - far) * flops_prim_quartet(a, b) + (double)far * flops_prim_quartet(a, b, 1);
                 npq += (long long)pq[a * NPTYPE + b];
+                nfarq += (long long)far;
             }
-        out->flops_model += fl; out->n_prim_quartets += npq;
-        if (std::getenv("VB_DEBUG_PQ") && pq[27])
-            std::printf("class (0|0): tasks %llu, empty %llu, bra quads run %llu, skipped %llu\n", pq[27], pq[28], pq[29], pq[30]);
-        if (std::getenv("VB_DEBUG_PQ"))
-            for (int c = 0; c < 9; ++c)
-                if (pq[18 + c]) std::printf("class (%d|%d): lane slots %llu, quartets %llu, lane efficiency %.3f\n", c / 3, c % 3, pq[18 + c], pq[(c / 3) * NPTYPE + c % 3], (double)pq[(c / 3) * NPTYPE + c % 3] / (double)pq[18 + c]);
+        out->flops_model += fl; out->n_prim_quartets += npq; out->n_ao_quartets += nfarq;   // n_ao_quartets carries the far-field count
         if (std::getenv("VB_DEBUG_PQ"))
             for (int a = 0; a < NPTYPE; ++a)
                 for (int b = 0; b < NPTYPE; ++b)
@@ -1196,9 +1198,10 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     auto add_pq = [&]() {
         std::vector<unsigned long long> pq;
         pq_counters.download(pq, st);
-        for (int a = 0; a < NPTYPE; ++a)
-            for (int b = 0; b < NPTYPE; ++b) {
-                acc->flops_model += (double)pq[a * NPTYPE + b] * flops_prim_quartet(a, b);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                const unsigned long long far = std::min(pq[PQ_FAR + a * 3 + b], pq[a * NPTYPE + b]);
+                acc->flops_model += (double)(pq[a * NPTYPE + b] - far) * flops_prim_quartet(a, b) + (double)far * flops_prim_quartet(a, b, 1);
                 acc->n_prim_quartets += (long long)pq[a * NPTYPE + b];
             }
     };

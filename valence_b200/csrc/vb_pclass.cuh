@@ -18,6 +18,8 @@
 
 namespace vb {
 
+constexpr int PQ_FAR = 18;   // pq_counters[PQ_FAR + tb*3 + tk]: quartets of class (tb|tk) evaluated with the asymptotic Boys values
+
 struct ClassCfg {           // shared-memory capacities of one class launch (host: max over the pair groups)
     int d_cap;              // doubles for the staged bra densities of pair type TB (+2 slack for the alignment shift)
     int sp_cap, pp_cap;     // bra shell pairs / primitive pairs of type TB
@@ -120,7 +122,7 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
 #pragma unroll
             for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
     }
-    unsigned long long nq_task = 0ull;
+    unsigned long long nq_task = 0ull, nfar_task = 0ull;
     auto octet_group = [&](const int oct) -> bool {     // false: nothing left further down the (sorted) ket list
     const int k0 = 8 * KB * oct;
     if (k0 >= nk) return false;
@@ -141,23 +143,14 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int j = 0; j < 4; ++j) { X[kb][f][j][0] = 0.0; X[kb][f][j][1] = 0.0; }
-    unsigned nq = 0;                                    // primitive quartets evaluated by this lane
-#ifdef VB_EXP_EFF
-    unsigned ntrip = 0, nquad_run = 0, nquad_skip = 0;
-#endif
+    unsigned nq = 0, nfar = 0;                          // primitive quartets evaluated by this lane; those in the asymptotic regime
     for (int q0 = 0; q0 < nsp; q0 += 4) {
         // shell pairs are sorted by contraction length, not by weight: test the quad's own bound
         const bool sact = q0 + t < nsp;
         const SPRec sp = spss[q0 + (sact ? t : 0)];
         if (!__any_sync(0xffffffffu, sact && sp.wmax * wk >= A.tau)) {
-#ifdef VB_EXP_EFF
-            ++nquad_skip;
-#endif
             continue;
         }
-#ifdef VB_EXP_EFF
-        ++nquad_run;
-#endif
         const int cnt = (sact && sp.wmax * wl[0] >= A.tau) ? sp.pp_cnt : 0;
         const PrimPair* __restrict__ bl = bpps + (sp.pp_beg - pp_base);
         double acc[KB][NE * NF];
@@ -171,9 +164,6 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
             const PrimPair a = bl[ip < cnt ? ip : 0];
             const bool act = ip < cnt && a.w * wl[0] >= A.tau;
             if (!__any_sync(0xffffffffu, act)) break;
-#ifdef VB_EXP_EFF
-            ntrip += KB;
-#endif
             // All lanes and all KB kets in the asymptotic regime (true for most trips of a large cluster): straight-line
             // code without a table look-up, so the KB chains interleave; otherwise the general routine per ket.
             constexpr int M = pt_E(TB) + pt_E(TK);
@@ -194,7 +184,9 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
                     const double u = a.p + b[kb].p;
                     const double dx = a.Px - b[kb].Px, dy = a.Py - b[kb].Py, dz = a.Pz - b[kb].Pz;
                     const double sq = a.p * b[kb].p * (dx * dx + dy * dy + dz * dz);
-                    far = far && (!actk[kb] || sq >= BOYS_S_TMAX * u);
+                    const bool fk = sq >= BOYS_S_TMAX * u;
+                    far = far && (!actk[kb] || fk);
+                    nfar += (actk[kb] && fk) ? 1u : 0u;
                     sv[kb] = actk[kb] ? sq : 1.0;
                 }
                 if (__all_sync(0xffffffffu, far)) {
@@ -212,7 +204,9 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
                     quartet_geom_fast(ak[kb], b[kb], geo[kb], T[kb], pref[kb]);
-                    far = far && (!actk[kb] || T[kb] >= BOYS_S_TMAX);
+                    const bool fk = T[kb] >= BOYS_S_TMAX;
+                    far = far && (!actk[kb] || fk);
+                    nfar += (actk[kb] && fk) ? 1u : 0u;
                 }
                 if (__all_sync(0xffffffffu, far)) {
 #pragma unroll
@@ -237,18 +231,9 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
         }
         if (ip > 0) feed_dmma_kb<TB, TK, KB>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
     }
-#ifdef VB_EXP_EFF
-    if (lane == 0) {                                   // experiment builds: lane slots, tasks, empty tasks, quads run / skipped
-        atomicAdd(&A.pq_counters[18 + TB * 3 + TK], 32ull * ntrip);
-        if (TB == 0 && TK == 0) {
-            atomicAdd(&A.pq_counters[27], 1ull); atomicAdd(&A.pq_counters[28], ntrip ? 0ull : 1ull);
-            atomicAdd(&A.pq_counters[29], (unsigned long long)nquad_run); atomicAdd(&A.pq_counters[30], (unsigned long long)nquad_skip);
-        }
-    }
-#endif
-    for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(0xffffffffu, nq, o);
+    for (int o = 16; o > 0; o >>= 1) { nq += __shfl_xor_sync(0xffffffffu, nq, o); nfar += __shfl_xor_sync(0xffffffffu, nfar, o); }
     if (!nq) return false;                             // the ket list is sorted by magnitude: nothing further down either
-    nq_task += nq;
+    nq_task += nq; nfar_task += nfar;
     if constexpr (KO == 1) {                           // single-octet tasks: C only lives from here
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -296,7 +281,7 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
             if (!octet_group(oct)) break;
     }
     if (!nq_task) return;
-    if (lane == 0) atomicAdd(s_pq, nq_task);
+    if (lane == 0) { atomicAdd(&s_pq[0], nq_task); atomicAdd(&s_pq[1], nfar_task); }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int q = 8 * m + g;
@@ -353,10 +338,10 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
     }
     __shared__ int s_item, s_unit;
     __shared__ int s_cum[PT_MAXQ + 1];
-    __shared__ unsigned long long s_pq;
+    __shared__ unsigned long long s_pq[2];        // primitive quartets evaluated / of those in the asymptotic regime
     __shared__ PGDesc s_P, s_Q[PT_MAXQ];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_pq = 0ull;
+    if (tid < 2) s_pq[tid] = 0ull;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
@@ -419,11 +404,11 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
             const int oct = (u - s_cum[qi]) * KO;
             const PGDesc& Q = s_Q[qi];
             double* Gglob = A.gbuf + ((size_t)item.z + qi - A.gslot_base) * A.g_cap;
-            pclass_task<TB, TK, KB, KO>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, &s_pq);
+            pclass_task<TB, TK, KB, KO>(A, nsp, P.np, P.pp_beg[TB], e_beg, Q, oct, bpp_s, sps_s, Dp_s + shift, A.dmat + Q.d_off, boys_sm, scratch, Gglob, lane, s_pq);
         }
     }
     __syncthreads();
-    if (tid == 0 && s_pq) atomicAdd(&A.pq_counters[TB * NPTYPE + TK], s_pq);
+    if (tid == 0 && s_pq[0]) { atomicAdd(&A.pq_counters[TB * NPTYPE + TK], s_pq[0]); atomicAdd(&A.pq_counters[PQ_FAR + TB * 3 + TK], s_pq[1]); }
 }
 
 // Contraction of the finished tiles of a chunk of work items with the cofactor densities: one tile per warp,
