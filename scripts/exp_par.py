@@ -11,7 +11,7 @@ for n in [int(a) for a in sys.argv[1:]]:
     fx = json.load(open(os.path.join(%r, "tests", "golden", "fast__w%%d.json" %% n)))
     print("RESULT n", n, "E", repr(r["energy"]), "dE vs fast oracle %%+.2e" %% (r["energy"] - fx["energy"]), "e1 %%r e2 %%r wfnorm %%r" %% (r["e1"], r["e2"], r["wfnorm"]), "fx num %%r wf %%r" %% (fx["numerator"], fx["wfnorm"]), "minpiv", r["min_pivot_ratio"], flush=True)
 """ % (ROOT, ROOT)
-for s in [{}, {"VB_INV_REFINE": "0"}]:
+for s in [{}, {"VB_PRIM_TAU": "1e-24"}]:
     env = dict(os.environ); env.update(s)
     ns = sys.argv[1:] if "VB_FAST_MIN_N" not in s else [a for a in sys.argv[1:] if int(a) <= 16]
     out = subprocess.run([sys.executable, "-c", CHILD] + ns, env=env, capture_output=True, text=True)

@@ -47,11 +47,13 @@ def test_energy_and_counts_match_oracle_and_golden(name, write_input):
     inp, _ = load_golden(name)
     r, ro = gpu_and_oracle(path)
     assert abs(r["enucrep"] - ro["enucrep"]) < 1e-12
-    # the reference's Givens determinants skip rotations below dtol (givens.F90:245); the GPU's are
-    # exact, so 1e-10 parity is defined for dtol <= 1e-16 (DESIGN.md "Tolerances")
-    tol = 1e-10 if inp.ntol_d >= 16 else 1e-7
+    # the reference's Givens determinants skip rotations below dtol (givens.F90:245); the GPU's are exact, so 1e-10 parity
+    # is defined for dtol <= 1e-16 (DESIGN.md "Tolerances").  On the eight shipped inputs with a looser dtol the skip never
+    # bites beyond 1.2e-10 (exact-determinant energy vs the reference's golden value): held to 1e-9,
+    # ten times tighter than the reference's own acceptance threshold (1e-8, testing/testing.py:23)
+    tol = 1e-10 if inp.ntol_d >= 16 else 1e-9
     assert abs(r["energy"] - ro["energy"]) < tol
-    assert abs(r["wfnorm"] / ro["wfnorm"] - 1.0) < (1e-11 if inp.ntol_d >= 16 else 1e-7)
+    assert abs(r["wfnorm"] / ro["wfnorm"] - 1.0) < (1e-11 if inp.ntol_d >= 16 else 1e-9)
     assert abs(r["energy"] - gold["guess_energy"]) < max(tol, 2e-10)   # reference tolerance: 1e-8
     for k in EXACT:
         assert r["counters"][k] == ro["counters"][k], k
@@ -233,7 +235,7 @@ def test_spin_coupled_energies_match_oracle(name, write_input):
     path, gold = write_input(name)
     inp, _ = load_golden(name)
     r, ro = gpu_and_oracle(path)
-    tol = 1e-10 if inp.ntol_d >= 16 else 1e-7
+    tol = 1e-10 if inp.ntol_d >= 16 else 1e-9
     assert abs(r["energy"] - ro["energy"]) < tol
     assert abs(r["energy"] - gold["guess_energy"]) < max(tol, 2e-10)
     for k in EXACT:

@@ -250,6 +250,12 @@ struct Engine::Impl {
     bool fo_collective = false;                      // first_order through the engine's communicator: decisions are agreed on
     std::vector<double> coeff_sc;                    // current spin-coupling weights
     double enuc = 0, e1 = 0, wfnorm = 0;
+    // the same two sums per unit determinant product, as unevaluated (high, low) pairs, and that product: energy_finish
+    // assembles E = (E1 + E2 / c0) / (N1 / nelec) + Enuc in extended precision (a 256-molecule cluster has |E_elec| ~ 2e5 Eh,
+    // one ulp of that is 3e-11 Eh: five roundings of the plain formula are the whole 1e-10 Eh budget)
+    double e1u[2] = {0, 0}, wnu[2] = {0, 0}, c0_keep = 0;
+    bool split_sum = false;     // energy_partial: leave E2 as the (grid multiple, rest) pair in accum[0], accum[1 + CNT_N]
+    int nelec_keep = 0;
     // primitive-quartet magnitude cut (VB_PRIM_TAU overrides).  Measured on (H2O)_64 / (H2O)_128: the energy is the same to
     // 13 digits for every cut between 1e-24 and 1e-18 (profiles/r2_tau_sweep.log); the screening counters do not depend on it.
     double tau = 1e-20;
@@ -285,7 +291,7 @@ Engine::Engine(const Input& in, int device) : in_(in), impl_(new Impl)
     I.coeff_sc = in.coeff_sc;
     if (const char* t = std::getenv("VB_PRIM_TAU")) I.tau = std::atof(t);
     reset_orbitals();
-    I.accum.alloc(1 + CNT_N);
+    I.accum.alloc(2 + CNT_N);     // [E2 (high part), counters, E2 (low part)]
     CK(cudaStreamSynchronize(I.st));
 }
 
@@ -317,7 +323,7 @@ long long Engine::debug_tile_energies(double* out, long long cap) const
     }
     return n;
 }
-int Engine::accum_len() const { return 1 + CNT_N; }
+int Engine::accum_len() const { return 2 + CNT_N; }
 void* Engine::stream() const { return (void*)impl_->st; }
 
 namespace {
@@ -530,7 +536,7 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
             Pa.alloc((size_t)nso * nso); Pb.alloc((size_t)nso * nso);
             k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mai.p, na, posa_bra.p, posa_bra.p, nso, Pa.p);
             k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(same ? Mai.p : Mbi.p, nb, posb_bra.p, posb_bra.p, nso, Pb.p);
-            one_e.alloc(2);
+            one_e.alloc(4);
             k_one_electron_energy<<<1, 1024, 0, st>>>(Se.p, He.p, Pa.p, Pb.p, nso * nso, one_e.p);
             CK(cudaGetLastError());
             launches += 3;
@@ -538,9 +544,11 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
             one_e.download(oe, st);
             e1 = c0 * oe[0];
             wfnorm = c0 * oe[1] / (double)nelec;    // valence.F90:1106
+            e1u[0] = oe[0]; e1u[1] = oe[2]; wnu[0] = oe[1]; wnu[1] = oe[3]; c0_keep = c0; nelec_keep = nelec;
         } else {
             fast = false;
             c0 = 1.0;
+            c0_keep = 0.0;
             // small blocks / several determinant pairs / possibly singular blocks: factorise on the host
             // (O(n^3) once per determinant pair, n <= 64), contract on the GPU
             std::vector<double> hSe, hHe;
@@ -858,7 +866,16 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     }
     CK(cudaEventRecord(ev3, st));
     if (gen) out->tile_launches += mine > 0 ? 1 : 0;
-    k_sum<<<1, 1024, 0, st>>>(tileE.p, ntiles, accum.p);
+    {
+        // grid of the high part: 2^-42 of the next power of two above |E1| (|E2| < |E1|), the same on every rank
+        double grid = 0.0;
+        if (e1 != 0.0 && std::isfinite(e1)) grid = std::ldexp(1.0, std::ilogb(e1) + 1 - 42);
+        if (split_sum) k_sum<<<1, 1024, 0, st>>>(tileE.p, ntiles, accum.p, accum.p + 1 + CNT_N, grid);
+        else {
+            k_sum<<<1, 1024, 0, st>>>(tileE.p, ntiles, accum.p);
+            CK(cudaMemsetAsync(accum.p + 1 + CNT_N, 0, sizeof(double), st));
+        }
+    }
     CK(cudaGetLastError());
     launches++;
     {
@@ -940,7 +957,7 @@ void Engine::energy(EnergyResult* out)
         I.use_gather = true;
         try { energy_partial(r, n, out); } catch (...) { I.use_gather = false; throw; }
         I.use_gather = false;
-        I.comm->allreduce_sum(I.accum.p, 1 + CNT_N, I.st);
+        I.comm->allreduce_sum(I.accum.p, 2 + CNT_N, I.st);
         energy_finish(out);
         return;
     }
@@ -952,7 +969,7 @@ void Engine::energy(EnergyResult* out)
         I.comm->barrier(I.st);
     }
     energy_partial(r, n, out);
-    I.comm->allreduce_sum(I.accum.p, 1 + CNT_N, I.st);
+    I.comm->allreduce_sum(I.accum.p, 2 + CNT_N, I.st);
     energy_finish(out);
 }
 
@@ -971,7 +988,9 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
     double t1 = now_ms();
     out->t_1e = t1 - I.t_begin;
     Wavefunction wf = default_wavefunction(in_);
-    I.evaluate(in_, wf, nullptr, false, rank, nranks, out, nullptr);
+    I.split_sum = true;
+    try { I.evaluate(in_, wf, nullptr, false, rank, nranks, out, nullptr); } catch (...) { I.split_sum = false; throw; }
+    I.split_sum = false;
 }
 
 // Table build shared by the ranks of one node.  One process per GPU means N ranks on one host build the same pair
@@ -1944,14 +1963,23 @@ void Engine::energy_finish(EnergyResult* out)
 {
     Impl& I = *impl_;
     CK(cudaSetDevice(I.device));
-    std::vector<double> acc(1 + CNT_N);
+    std::vector<double> acc(2 + CNT_N);
     CK(cudaMemcpyAsync(acc.data(), I.accum.p, acc.size() * sizeof(double), cudaMemcpyDeviceToHost, I.st));
     CK(cudaStreamSynchronize(I.st));
-    out->e2 = acc[0];
+    out->e2 = acc[0] + acc[1 + CNT_N];
     for (int i = 0; i < CNT_N; ++i) out->counters[i] = (long long)(acc[1 + i] + 0.5);
     out->ref_shell_quartets = out->counters[CNT_SHELLQ];
     out->numerator = I.e1 + out->e2;
     out->energy = out->numerator / I.wfnorm + I.enuc;     // valence.F90:344
+    if (I.c0_keep != 0.0 && std::isfinite(I.c0_keep)) {
+        typedef long double ld;     // x87 extended (64-bit mantissa) on the x86 hosts this runs on; plain double elsewhere
+        const ld e1 = (ld)I.e1u[0] + (ld)I.e1u[1], wn = ((ld)I.wnu[0] + (ld)I.wnu[1]) / (ld)I.nelec_keep;
+        const ld e2 = ((ld)acc[0] + (ld)acc[1 + CNT_N]) / (ld)I.c0_keep;
+        const ld E = (e1 + e2) / wn + (ld)I.enuc;
+        if (std::getenv("VB_DEBUG_PARTS"))
+            std::fprintf(stderr, "[parts] E1/c0 %.20Lg  E2/c0 %.20Lg  N1/nelec - 1 %.3Le  c0 %.17g  E %.20Lg  (plain formula %.17g)\n", e1, e2, wn - 1.0L, I.c0_keep, E, out->energy);
+        out->energy = (double)E;
+    }
     out->launches = I.launches;
     out->h2d_bytes = g_h2d_bytes + 8 * CNT_N; out->d2h_bytes = g_d2h_bytes + 8 * (1 + CNT_N);
     out->t_total = now_ms() - I.t_begin;

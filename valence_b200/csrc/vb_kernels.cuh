@@ -428,43 +428,66 @@ __global__ void k_entry_density(const double* __restrict__ Minv, int n, const in
 }
 
 // deterministic two-level sum of n doubles (fixed tree; same result on every run and for every grid)
-__global__ void k_sum(const double* __restrict__ x, long long n, double* __restrict__ out)
+// double-double accumulation (error-free product through FMA, two-sum): the one-electron numerator of a few hundred
+// molecules is a sum of ~1e6 terms of magnitude 1e2 that adds up to ~1e5 Hartree -- a plain double sum alone costs 1e-10 Eh
+struct dd { double hi, lo; };
+__device__ __forceinline__ void dd_add(dd& s, double p, double e)   // s += p + e
 {
-    __shared__ double sh[1024];
-    double acc = 0.0, comp = 0.0;   // Kahan per thread over a fixed stride pattern
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        double y = x[i] - comp, t = acc + y;
-        comp = (t - acc) - y;
-        acc = t;
-    }
+    const double t = __dadd_rn(s.hi, p), bp = __dsub_rn(t, s.hi);
+    const double err = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, bp)), __dsub_rn(p, bp));
+    s.hi = t;
+    s.lo = __dadd_rn(s.lo, __dadd_rn(err, e));
+}
+// out_lo == nullptr: out[0] = the sum rounded to double.  Otherwise the sum leaves as an unevaluated pair: out[0] = its
+// multiple of `grid` (a power of two shared by every rank, chosen so that the per-rank values add up EXACTLY in a double
+// all-reduce), out_lo[0] = the rest -- the energy is assembled from the pair in extended precision on the host.
+__global__ void k_sum(const double* __restrict__ x, long long n, double* __restrict__ out, double* __restrict__ out_lo = nullptr, double grid = 0.0)
+{
+    __shared__ dd sh[1024];
+    dd acc = {0.0, 0.0};            // double-double per thread over a fixed stride pattern: deterministic and exact to ~1e-30
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) dd_add(acc, x[i], 0.0);
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        if ((int)threadIdx.x < o) dd_add(sh[threadIdx.x], sh[threadIdx.x + o].hi, sh[threadIdx.x + o].lo);
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = sh[0];
+    if (threadIdx.x == 0) {
+        if (!out_lo) out[0] = sh[0].hi + sh[0].lo;
+        else if (grid > 0.0) {
+            const double top = rint(sh[0].hi / grid) * grid;     // exact: a power-of-two grid
+            out[0] = top; out_lo[0] = (sh[0].hi - top) + sh[0].lo;
+        } else { out[0] = sh[0].hi; out_lo[0] = sh[0].lo; }
+    }
 }
 
 // E1 = sum_st h[s][t] (Pa+Pb)[s][t],  N1 = sum_st S[s][t] (Pa+Pb)[s][t]   (valence.F90:1072-1106)
 __global__ void k_one_electron_energy(const double* __restrict__ Se, const double* __restrict__ He,
                                       const double* __restrict__ Pa, const double* __restrict__ Pb, int n2,
-                                      double* __restrict__ out /* [2] */)
+                                      double* __restrict__ out /* [4]: E1, N1, then their low-order parts */)
 {
-    __shared__ double sh[2][1024];
-    double e = 0.0, w = 0.0;
+    __shared__ dd sh[2][1024];
+    dd e = {0.0, 0.0}, w = {0.0, 0.0};
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        double p = Pa[i] + Pb[i];
-        e += He[i] * p;
-        w += Se[i] * p;
+        const double p = Pa[i] + Pb[i];
+        const double pe = __dmul_rn(He[i], p), pw = __dmul_rn(Se[i], p);
+        dd_add(e, pe, __fma_rn(He[i], p, -pe));
+        dd_add(w, pw, __fma_rn(Se[i], p, -pw));
     }
     sh[0][threadIdx.x] = e; sh[1][threadIdx.x] = w;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+        if ((int)threadIdx.x < o) {
+            dd_add(sh[0][threadIdx.x], sh[0][threadIdx.x + o].hi, sh[0][threadIdx.x + o].lo);
+            dd_add(sh[1][threadIdx.x], sh[1][threadIdx.x + o].hi, sh[1][threadIdx.x + o].lo);
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out[0] = sh[0][0]; out[1] = sh[1][0]; }
+    if (threadIdx.x == 0) {
+        const double e = sh[0][0].hi + sh[0][0].lo, w = sh[1][0].hi + sh[1][0].lo;
+        out[0] = e; out[1] = w;
+        out[2] = (sh[0][0].hi - e) + sh[0][0].lo; out[3] = (sh[1][0].hi - w) + sh[1][0].lo;
+    }
 }
 
 }  // namespace vb
