@@ -35,6 +35,7 @@ module valence_b200
      integer(c_int) :: launches, diag_launches, tile_launches
      real(c_double) :: min_pivot_ratio
      integer(c_long_long) :: h2d_bytes, d2h_bytes
+     real(c_double) :: flops_transform
   end type vb_energy_result
 
   interface

@@ -71,6 +71,7 @@ typedef struct vb_energy_result {
     int launches, diag_launches, tile_launches;
     double min_pivot_ratio;
     long long h2d_bytes, d2h_bytes;   /* host<->device bytes copied by this call */
+    double flops_transform;           /* FP64 tensor-core flops of the two density transforms of this rank's tile pass */
 } vb_energy_result;
 
 const char* vb_last_error(void);

@@ -44,3 +44,14 @@ def test_tile_list_and_rank_sharding_on_the_host(tmp_path):
                            os.path.join(ROOT, "tests", "host", "test_tilelist_host.cpp"), os.path.join(csrc, "vb_tilelist.cpp")])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_far_field_segment_form_against_the_recurrence(tmp_path):
+    """vb_far.cuh on the CPU: the closed far-field form of (ss|ss) (ps|ss) (ss|ps) (ps|ps) over collinear shell-pair
+    segments equals the Obara-Saika recurrence with the general Boys function (block-relative 5e-15), the
+    segment-level far test never admits a quartet with T < 40, and the integer magnitude cut keeps everything the
+    exact comparison keeps."""
+    exe = tmp_path / "test_far"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "host", "test_far_host.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

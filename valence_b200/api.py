@@ -31,7 +31,7 @@ class CEnergyResult(C.Structure):
                 + [(n, C.c_double) for n in ("t_total_ms", "t_host_setup_ms", "t_1e_ms", "t_density_ms",
                                              "t_diag_ms", "t_tiles_ms")]
                 + [(n, C.c_int) for n in ("launches", "diag_launches", "tile_launches")]
-                + [("min_pivot_ratio", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)])
+                + [("min_pivot_ratio", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("flops_transform", C.c_double)])
 
     def asdict(self) -> dict:
         d = {}

@@ -13,7 +13,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 SOURCES = ["vb_engine.cu", "vb_setup.cpp", "vb_tilelist.cpp", "vb_cofactor.cpp", "vb_input.cpp", "vb_capi.cpp", "vb_nccl.cpp"]
-HEADERS = ["vb_engine.h", "vb_setup.h", "vb_cofactor.h", "vb_input.h", "vb_eri.cuh", "vb_kernels.cuh", "vb_tile.cuh", "vb_ptile.cuh", "vb_pclass.cuh", "vb_nccl.h", "vb_tilelist.h",
+HEADERS = ["vb_engine.h", "vb_setup.h", "vb_cofactor.h", "vb_input.h", "vb_eri.cuh", "vb_kernels.cuh", "vb_tile.cuh", "vb_ptile.cuh", "vb_pclass.cuh", "vb_pseg.cuh", "vb_far.cuh", "vb_nccl.h", "vb_tilelist.h",
            os.path.join("..", "..", "include", "valence_b200.h")]
 
 

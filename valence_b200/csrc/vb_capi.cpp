@@ -32,6 +32,7 @@ void to_c(const vb::EnergyResult& r, vb_energy_result* o)
     o->t_total_ms = r.t_total; o->t_host_setup_ms = r.t_host_setup; o->t_1e_ms = r.t_1e; o->t_density_ms = r.t_density;
     o->t_diag_ms = r.t_diag; o->t_tiles_ms = r.t_tiles; o->launches = r.launches; o->diag_launches = r.diag_launches;
     o->tile_launches = r.tile_launches; o->min_pivot_ratio = r.min_pivot_ratio; o->h2d_bytes = r.h2d_bytes; o->d2h_bytes = r.d2h_bytes;
+    o->flops_transform = r.flops_transform;
 }
 
 template <class F>
@@ -202,7 +203,7 @@ int vb_engine_energy_finish(vb_engine* e, vb_energy_result* out)
         // carry the partial's workload fields through
         r.n_entries = out->n_entries; r.n_groups = out->n_groups; r.n_pairgroups = out->n_pairgroups; r.n_tiles = out->n_tiles;
         r.n_tiles_mine = out->n_tiles_mine; r.n_ao_quartets = out->n_ao_quartets; r.n_prim_quartets = out->n_prim_quartets;
-        r.flops_model = out->flops_model; r.t_host_setup = out->t_host_setup_ms; r.t_1e = out->t_1e_ms; r.t_density = out->t_density_ms;
+        r.flops_model = out->flops_model; r.flops_transform = out->flops_transform; r.t_host_setup = out->t_host_setup_ms; r.t_1e = out->t_1e_ms; r.t_density = out->t_density_ms;
         r.t_diag = out->t_diag_ms; r.t_tiles = out->t_tiles_ms; r.diag_launches = out->diag_launches; r.tile_launches = out->tile_launches;
         r.min_pivot_ratio = out->min_pivot_ratio; r.enucrep = out->enucrep; r.e1 = out->e1; r.wfnorm = out->wfnorm;
         e->eng->energy_finish(&r);

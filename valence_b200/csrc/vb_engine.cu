@@ -20,7 +20,7 @@
 #include "vb_kernels.cuh"
 #include "vb_tilelist.h"
 #include "vb_ptile.cuh"
-#include "vb_pclass.cuh"
+#include "vb_pseg.cuh"
 #include "vb_tile.cuh"
 
 namespace vb {
@@ -119,6 +119,11 @@ struct ClassPlan {
     ClassCfg cfg[3];
     size_t smem[3][3];
     bool ok = true;
+    // segment form of the four light classes (vb_pseg.cuh): far-field tables of this evaluation, or null -> k_pclass for every class
+    const FarPrim* fcp = nullptr;      // aligned with pps
+    const FarPrim* fcpf = nullptr;     // aligned with pps_flat
+    unsigned lthr = 0;
+    size_t smem_seg[2] = {0, 0};
 };
 
 ClassPlan plan_classes(const std::vector<PGDesc>& pgs)
@@ -130,7 +135,7 @@ ClassPlan plan_classes(const std::vector<PGDesc>& pgs)
         for (int t = 0; t < 3; ++t) {
             const int nsp = pg.sp_beg[t + 1] - pg.sp_beg[t], npp = pg.pp_beg[t + 1] - pg.pp_beg[t];
             if (nsp > 0 && npp > 0) bra[t] = true;
-            mx_d[t] = std::max(mx_d[t], nsp * pt_ne(t) * pg.np);
+            mx_d[t] = std::max(mx_d[t], (pg.e_beg[t + 1] - pg.e_beg[t]) * pg.np);
             mx_sp[t] = std::max(mx_sp[t], nsp);
             mx_pp[t] = std::max(mx_pp[t], npp);
         }
@@ -145,8 +150,29 @@ ClassPlan plan_classes(const std::vector<PGDesc>& pgs)
                               (size_t)pl.cfg[tb].sp_cap * sizeof(SPRec) + (size_t)pl.cfg[tb].pp_cap * sizeof(PrimPair);
             if (pl.present[tb][tk] && pl.smem[tb][tk] > PT_SMEM_MAX) pl.ok = false;
         }
+        if (tb < 2)
+            pl.smem_seg[tb] = ((size_t)pl.cfg[tb].d_cap + (size_t)(PS_THREADS / 32) * PT_SCRATCH + BOYS_S_SIZE) * sizeof(double) +
+                              (size_t)pl.cfg[tb].sp_cap * sizeof(SPRec) + ((size_t)pl.cfg[tb].pp_cap + FAR_PAD) * sizeof(FarPrim) +
+                              (size_t)pl.cfg[tb].pp_cap * sizeof(PrimPair);
     }
     return pl;
+}
+
+template <int TB, int TK>
+void launch_seg(const TileArgs& A, const ClassPlan& pl, int nsm, int nitems, cudaStream_t st)
+{
+    const size_t smem = pl.smem_seg[TB];
+    CK(cudaFuncSetAttribute(k_pseg<TB, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pseg<TB, TK>, PS_THREADS, smem));
+    per_sm = std::max(1, per_sm);
+    const int grid = std::max(1, std::min(nsm * per_sm, nitems));
+    SegCfg C;
+    C.d_cap = pl.cfg[TB].d_cap; C.sp_cap = pl.cfg[TB].sp_cap; C.pp_cap = pl.cfg[TB].pp_cap; C.fcp = pl.fcp; C.fcpf = pl.fcpf; C.lthr = pl.lthr;
+    C.skip = 0;
+    if (const char* e = std::getenv("VB_SEG_SKIP")) C.skip = std::atoi(e);
+    k_pseg<TB, TK><<<grid, PS_THREADS, smem, st>>>(A, C);
+    CK(cudaGetLastError());
 }
 
 template <int TB, int TK>
@@ -175,6 +201,15 @@ int run_class_pass(TileArgs A, const ClassPlan& pl, int nsm, long long ntile_slo
         if (!pl.present[tb][tk]) continue;
         CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
         if (ms_class) CK(cudaEventRecord(e0, st));
+        const bool seg = pl.fcp && tb < 2 && tk < 2 && pl.smem_seg[tb] <= PT_SMEM_MAX;
+        if (seg) {
+            switch (tb * 2 + tk) {
+                case 0: launch_seg<0, 0>(A, pl, nsm, A.nitems, st); break;
+                case 1: launch_seg<0, 1>(A, pl, nsm, A.nitems, st); break;
+                case 2: launch_seg<1, 0>(A, pl, nsm, A.nitems, st); break;
+                default: launch_seg<1, 1>(A, pl, nsm, A.nitems, st); break;
+            }
+        } else
         switch (tb * 3 + tk) {
             case 0: launch_class<0, 0>(A, pl, nsm, A.nitems, st); break;
             case 1: launch_class<0, 1>(A, pl, nsm, A.nitems, st); break;
@@ -208,6 +243,7 @@ struct Engine::Impl {
     std::vector<std::vector<double>> coeff;          // current orbital weights (normalised in energy())
     std::vector<double> xyz_angs;
     // device data
+    DBuf<FarPrim> fcp, fcpf;
     DBuf<double> boys, boys_small, gbuf, gred, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, gj_res, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket;
@@ -801,7 +837,21 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     if (const char* e = std::getenv("VB_CLASS_SPLIT")) csplit = csplit && std::atoi(e) != 0;
     ClassPlan cplan;
     if (csplit) { cplan = plan_classes(ts.pgs); csplit = cplan.ok; }
+    // VB_PSEG=1: closed far-field form for the light classes (vb_pseg.cuh).  Measured slower than k_pclass (DESIGN.md section 5:
+    // both are bound by the two DMMA transforms and the latency of short inner loops, not by the integral arithmetic) -- kept as
+    // a documented experiment, off by default
+    bool use_seg = false;
+    if (const char* e = std::getenv("VB_PSEG")) use_seg = csplit && std::atoi(e) != 0;
     CK(cudaEventRecord(ev2, st));
+    if (use_seg && mine > 0) {
+        // far-field tables of every segment / primitive pair of this evaluation (part of the timed tile pass)
+        fcp.alloc(pps.n); fcpf.alloc(pps.n);
+        const long long npp = (long long)pps.n;
+        k_far_tables<<<(unsigned)((npp + 255) / 256), 256, 0, st>>>(pps.p, pps_flat.p, npp, fcp.p, fcpf.p);
+        CK(cudaGetLastError());
+        launches++;
+        cplan.fcp = fcp.p; cplan.fcpf = fcpf.p; cplan.lthr = far_lthr(tau_energy);
+    }
     if (gen) {
         if (mine > 0) launch((int)mine, PART_ALL);
     } else if (mine > 0 && csplit) {
@@ -890,18 +940,21 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
             for (int b = 0; b < NPTYPE; ++b) {
                 if (!gen && (a >= 3 || b >= 3)) continue;      // s/p runs: the upper slots hold the far-field counts of the class kernels
                 const unsigned long long far = (!gen && a < 3 && b < 3) ? std::min(pq[PQ_FAR + a * 3 + b], pq[a * NPTYPE + b]) : 0ull;
-                fl += (double)(pq[a * NPTYPE + b] - far) * flops_prim_quartet(a, b) + (double)far * flops_prim_quartet(a, b, 1);
+                // light classes: the quartets that went through the far-field segment form (vb_far.cuh) at ITS operation count
+                const unsigned long long seg = (!gen && a < 2 && b < 2) ? std::min(pq[PQ_SEGFAR + a * 2 + b], far) : 0ull;
+                fl += (double)(pq[a * NPTYPE + b] - far) * flops_prim_quartet(a, b) + (double)(far - seg) * flops_prim_quartet(a, b, 1) +
+                      (double)seg * far_flops(a, b);
                 npq += (long long)pq[a * NPTYPE + b];
                 nfarq += (long long)far;
             }
         out->flops_model += fl; out->n_prim_quartets += npq; out->n_ao_quartets += nfarq;   // n_ao_quartets carries the far-field count
+        if (!gen) out->flops_transform += 512.0 * (double)pq[PQ_DMMA];
         if (std::getenv("VB_DEBUG_PQ"))
             for (int a = 0; a < NPTYPE; ++a)
                 for (int b = 0; b < NPTYPE; ++b)
                     if (pq[a * NPTYPE + b])
-                        std::printf("class (%d|%d): %llu primitive quartets x %.0f flops = %.2f GF (%.1f%%)\n", a, b, pq[a * NPTYPE + b],
-                                    flops_prim_quartet(a, b), pq[a * NPTYPE + b] * flops_prim_quartet(a, b) * 1e-9,
-                                    100.0 * pq[a * NPTYPE + b] * flops_prim_quartet(a, b) / fl);
+                        std::printf("class (%d|%d): %llu primitive quartets, %llu asymptotic, %llu in far-field segment form\n", a, b, pq[a * NPTYPE + b],
+                                    a < 3 && b < 3 ? pq[PQ_FAR + a * 3 + b] : 0ull, a < 2 && b < 2 ? pq[PQ_SEGFAR + a * 2 + b] : 0ull);
         std::vector<double> cd(CNT_N);
         for (int i = 0; i < CNT_N; ++i) cd[i] = (double)c[i];
         CK(cudaMemcpyAsync(accum.p + 1, cd.data(), CNT_N * sizeof(double), cudaMemcpyHostToDevice, st));

@@ -19,6 +19,7 @@
 namespace vb {
 
 constexpr int PQ_FAR = 18;   // pq_counters[PQ_FAR + tb*3 + tk]: quartets of class (tb|tk) evaluated with the asymptotic Boys values
+constexpr int PQ_DMMA = 31;  // pq_counters[PQ_DMMA]: FP64 tensor-core instructions (m8n8k4, 512 flops each) of the two density transforms
 
 struct ClassCfg {           // shared-memory capacities of one class launch (host: max over the pair groups)
     int d_cap;              // doubles for the staged bra densities of pair type TB (+2 slack for the alignment shift)
@@ -122,7 +123,7 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
 #pragma unroll
             for (int j = 0; j < 4; ++j) { C[m][j][0] = 0.0; C[m][j][1] = 0.0; }
     }
-    unsigned long long nq_task = 0ull, nfar_task = 0ull;
+    unsigned long long nq_task = 0ull, nfar_task = 0ull, ndmma_task = 0ull;
     auto octet_group = [&](const int oct) -> bool {     // false: nothing left further down the (sorted) ket list
     const int k0 = 8 * KB * oct;
     if (k0 >= nk) return false;
@@ -229,11 +230,11 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
                 }
             }
         }
-        if (ip > 0) feed_dmma_kb<TB, TK, KB>(acc, sp.eoff - e_beg, Dp_s, npP, g, X);
+        if (ip > 0) { feed_dmma_kb<TB, TK, KB>(acc, sp.eoff - e_beg, Dp_s, npP, g, X); ndmma_task += NE * NF * 4 * KB; }
     }
     for (int o = 16; o > 0; o >>= 1) { nq += __shfl_xor_sync(0xffffffffu, nq, o); nfar += __shfl_xor_sync(0xffffffffu, nfar, o); }
     if (!nq) return false;                             // the ket list is sorted by magnitude: nothing further down either
-    nq_task += nq; nfar_task += nfar;
+    nq_task += nq; nfar_task += nfar; ndmma_task += NF * KB * 32;
     if constexpr (KO == 1) {                           // single-octet tasks: C only lives from here
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -281,7 +282,7 @@ __device__ __forceinline__ void pclass_task(const TileArgs& A, int nsp, int npP,
             if (!octet_group(oct)) break;
     }
     if (!nq_task) return;
-    if (lane == 0) { atomicAdd(&s_pq[0], nq_task); atomicAdd(&s_pq[1], nfar_task); }
+    if (lane == 0) { atomicAdd(&s_pq[0], nq_task); atomicAdd(&s_pq[1], nfar_task); atomicAdd(&s_pq[2], ndmma_task); }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int q = 8 * m + g;
@@ -338,10 +339,10 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
     }
     __shared__ int s_item, s_unit;
     __shared__ int s_cum[PT_MAXQ + 1];
-    __shared__ unsigned long long s_pq[2];        // primitive quartets evaluated / of those in the asymptotic regime
+    __shared__ unsigned long long s_pq[3];        // primitive quartets evaluated / of those in the asymptotic regime / DMMA instructions
     __shared__ PGDesc s_P, s_Q[PT_MAXQ];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 2) s_pq[tid] = 0ull;
+    if (tid < 3) s_pq[tid] = 0ull;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
@@ -364,14 +365,12 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
         const PGDesc& P = s_P;
         const int nsp = P.sp_beg[TB + 1] - P.sp_beg[TB], nbpp = P.pp_beg[TB + 1] - P.pp_beg[TB];
         if (nsp == 0 || nbpp == 0) continue;
-        int e_beg = 0;                                          // first e-row of pair type TB inside P's density block
-#pragma unroll
-        for (int t = 0; t < TB; ++t) e_beg += (P.sp_beg[t + 1] - P.sp_beg[t]) * pt_ne(t);
+        const int e_beg = P.e_beg[TB];                          // first e-row of pair type TB inside P's density block
         const long long o = P.d_off + (long long)e_beg * P.np;  // TMA wants 16-byte alignment: copy from the even element below
         const int shift = (int)(o & 1);
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const unsigned bd = (unsigned)(((shift + nsp * NE * P.np + 1) & ~1) * sizeof(double));
+            const unsigned bd = (unsigned)(((shift + (P.e_beg[TB + 1] - e_beg) * P.np + 1) & ~1) * sizeof(double));
             const unsigned bb = (unsigned)(nbpp * sizeof(PrimPair));
             const unsigned bs = (unsigned)(nsp * sizeof(SPRec));
             mbar_expect_tx(&s_bar, bd + bb + bs);
@@ -408,7 +407,10 @@ __global__ void __launch_bounds__(pc_threads(TB, TK), pc_minblocks(TB, TK)) k_pc
         }
     }
     __syncthreads();
-    if (tid == 0 && s_pq[0]) { atomicAdd(&A.pq_counters[TB * NPTYPE + TK], s_pq[0]); atomicAdd(&A.pq_counters[PQ_FAR + TB * 3 + TK], s_pq[1]); }
+    if (tid == 0 && s_pq[0]) {
+        atomicAdd(&A.pq_counters[TB * NPTYPE + TK], s_pq[0]); atomicAdd(&A.pq_counters[PQ_FAR + TB * 3 + TK], s_pq[1]);
+        atomicAdd(&A.pq_counters[PQ_DMMA], s_pq[2]);
+    }
 }
 
 // Contraction of the finished tiles of a chunk of work items with the cofactor densities: one tile per warp,

@@ -216,6 +216,9 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
 {
     (void)in;
     TileSetup& ts = *out;
+    int seg_len = 64;         // primitives per s / p shell-pair segment (VB_SEG; 64 leaves the 6-31G shell pairs whole: no
+                              // measurable difference for k_pclass, profiles/r2_segment_sweep.log)
+    if (const char* e = std::getenv("VB_SEG")) seg_len = std::min(64, std::max(1, std::atoi(e)));
     // reset, but keep the storage of the big tables: a TileSetup that is reused across calls is resized in place at
     // the merge (every element is overwritten there), which saves zero-filling and page-faulting ~0.6 GB per call
     ts.groups.clear(); ts.pgs.clear();
@@ -475,13 +478,17 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                         double K = bas.coefs[sa.prim_off + ia] * bas.coefs[sb.prim_off + ib] * ex * SQ2PI54;
                         if (K == 0.0) continue;
                         PrimPair pp;
-                        pp.Px = (a * sa.r[0] + b * sb.r[0]) / p;
-                        pp.Py = (a * sa.r[1] + b * sb.r[1]) / p;
-                        pp.Pz = (a * sa.r[2] + b * sb.r[2]) / p;
+                        // P - A = b/p (B - A) formed from the difference of the centres: P - A as a difference of
+                        // absolute coordinates loses |coordinate| / |P - A| units in the last place (1e-14 relative for an
+                        // atom 40 bohr from the origin); P = A + (P - A) keeps the pair consistent
+                        const double sAB = b / p;
+                        pp.PAx = sAB * (sb.r[0] - sa.r[0]); pp.PAy = sAB * (sb.r[1] - sa.r[1]); pp.PAz = sAB * (sb.r[2] - sa.r[2]);
+                        pp.Px = sa.r[0] + pp.PAx;
+                        pp.Py = sa.r[1] + pp.PAy;
+                        pp.Pz = sa.r[2] + pp.PAz;
                         pp.p = p;
                         pp.ip = 1.0 / p;
                         pp.Kp = K / p;
-                        pp.PAx = pp.Px - sa.r[0]; pp.PAy = pp.Py - sa.r[1]; pp.PAz = pp.Pz - sa.r[2];
                         // Schwarz-type magnitude: the charge cloud sum_e dt[e] [e0| of this primitive pair has
                         // self-repulsion <= w^2, so its share of any (st|uv) is <= w_p w_q.
                         // [ss|ss]_pp = Kp^2 / sqrt(2p); each unit of angular momentum adds a factor
@@ -498,13 +505,22 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
                 if (sp.pp.empty()) continue;
                 // by decreasing weight, stable; a few primitives per shell pair on average: insertion sort (std::stable_sort
                 // allocates a buffer per call)
-                if (sp.pp.size() <= 12) {
-                    for (size_t i = 1; i < sp.pp.size(); ++i) {
+                // s / p shell pairs leave as segments of seg_len primitives (below): order by exponent sum first, tightest
+                // primitives first, so that a segment holds primitives of similar extent (its far-field radius is that of
+                // its most diffuse primitive), then by decreasing weight inside each segment
+                auto by_weight = [&](size_t lo, size_t hi) {
+                    for (size_t i = lo + 1; i < hi; ++i) {
                         const PrimPair x = sp.pp[i];
                         size_t j = i;
-                        for (; j > 0 && x.w > sp.pp[j - 1].w; --j) sp.pp[j] = sp.pp[j - 1];
+                        for (; j > lo && x.w > sp.pp[j - 1].w; --j) sp.pp[j] = sp.pp[j - 1];
                         sp.pp[j] = x;
                     }
+                };
+                if (sp.type <= 1 && sp.pp.size() > (size_t)seg_len) {
+                    std::stable_sort(sp.pp.begin(), sp.pp.end(), [](const PrimPair& x, const PrimPair& y) { return x.p > y.p; });
+                    for (size_t c0 = 0; c0 < sp.pp.size(); c0 += (size_t)seg_len) by_weight(c0, std::min(sp.pp.size(), c0 + (size_t)seg_len));
+                } else if (sp.pp.size() <= 12) {
+                    by_weight(0, sp.pp.size());
                 } else {
                     std::stable_sort(sp.pp.begin(), sp.pp.end(), [](const PrimPair& x, const PrimPair& y) { return x.w > y.w; });
                 }
@@ -530,15 +546,29 @@ void build_tiles(const Input& in, const Basis& bas, const Wavefunction& wf, cons
         out.pps.clear();
         for (size_t k = 0; k < tsp.size(); ++k) {
             const TmpSP& sp = tsp[k];
-            while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)out.pps.size(); ++t_cur; }
+            while (t_cur <= sp.type) { pg.pp_beg[t_cur] = (int)out.pps.size(); pg.e_beg[t_cur] = eoff; ++t_cur; }
             const int nE = pt_ne(sp.type);
-            recs.push_back({sp.type, eoff, (int)out.pps.size(), (int)sp.pp.size(), sp.wmax, 0.0});
+            // s and p shell pairs enter the tables as segments of at most seg_len primitives (all with the pair's e-offset:
+            // the integrals are linear in the primitives).  The segment kernels (vb_pseg.cuh) walk (bra segment, ket segment)
+            // pairs per lane; bounded, similar lengths keep the lanes of a warp in step.  Primitives are sorted by magnitude,
+            // so a segment's first weight is its largest.
+            {
+                // (splitting the one-to-four pp shell pairs of a pair group over the four bra lanes of a quad was measured as
+                // well: 10-25 % slower for the pp classes -- every extra segment is another tensor-core feed)
+                const int cnt = (int)sp.pp.size(), base = (int)out.pps.size();
+                const int S = sp.type <= 1 ? seg_len : cnt;
+                for (int c0 = 0; c0 < cnt; c0 += S) {
+                    double ipmax = 0.0;
+                    for (int i = c0; i < std::min(cnt, c0 + S); ++i) ipmax = std::max(ipmax, sp.pp[i].ip);
+                    recs.push_back({sp.type, eoff, base + c0, std::min(S, cnt - c0), sp.pp[c0].w, ipmax});
+                }
+            }
             pg.kwmax[sp.type] = std::max(pg.kwmax[sp.type], sp.wmax);
             for (PrimPair pp : sp.pp) { pp.eoff = eoff; pp.pad = 0; pp.wseg = sp.wmax; out.pps.push_back(pp); }
             std::copy(sp.dt.begin(), sp.dt.end(), D + (size_t)eoff * np);
             eoff += nE;
         }
-        while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)out.pps.size(); ++t_cur; }
+        while (t_cur <= NPTYPE) { pg.pp_beg[t_cur] = (int)out.pps.size(); pg.e_beg[t_cur] = eoff; ++t_cur; }
         // per type, most expensive shell pairs first (they are dealt round-robin to the warps)
         std::stable_sort(recs.begin(), recs.end(), [](const SPRec& a, const SPRec& b) {
             return a.type != b.type ? a.type < b.type : a.pp_cnt > b.pp_cnt;

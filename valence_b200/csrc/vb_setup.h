@@ -42,11 +42,12 @@ struct SPRec {          // one oriented shell pair of a pair group (whole contra
     int eoff;           // first [e0| component of this shell pair inside the group's e-space
     int pp_beg, pp_cnt; // range in the primitive-pair array
     double wmax;        // largest primitive weight of the shell pair
-    double pad;         // 32 bytes: staged with cp.async.bulk
+    double pad;         // s / p segments: largest 1/p of the segment (sort key of the list); 32 bytes: staged with cp.async.bulk
 };
 struct PGDesc {
     int sp_beg[NPTYPE + 1];     // shell pairs sorted by type
     int pp_beg[NPTYPE + 1];     // primitive pairs sorted by type, then shell pair (ket lanes walk these)
+    int e_beg[NPTYPE + 1];      // first e-row of each pair type inside the density block (rows of a type are contiguous)
     long long d_off;            // offset of the folded density block [ne][np]
     int ne, np;                 // # e-components, # orbital pairs
     int pair_beg;               // offset into the pair list (s,t)
