@@ -72,6 +72,23 @@ def test_water_clusters_match_oracle(n, rotate, write_input):
         assert r["counters"][k] == ro["counters"][k], k
 
 
+@pytest.mark.parametrize("n", [1, 4, 8])
+def test_alkanes_match_fast_oracle(n, write_input):
+    """n-alkanes from the vtools guess-orbital library (inputs.alkane): two-atom orbital basis sets, bonds in every direction."""
+    from valence_b200 import api, inputs
+    from oracle.oracle import Oracle
+    path, _ = write_input(inputs.alkane(n))
+    eng = api.Engine(path)
+    r = eng.energy()
+    eng.close()
+    o = Oracle(path)
+    ro = o.fast_guess_energy()
+    o.close()
+    assert abs(r["energy"] - ro["energy"]) < 1e-10
+    for k in EXACT + VALUE:
+        assert r["counters"][k] == ro["counters"][k], k
+
+
 def test_screening_counters_match_reference_task_loop_on_16_waters(write_input):
     """(H2O)_16 is beyond the full oracle (O(n^3) determinants per task), but the reference's task
     bookkeeping only needs the Schwarz table: the oracle's count-only pass (real schwarz_ints, then

@@ -76,3 +76,42 @@ def test_lif128_reconstruction_matches_the_surviving_part_of_the_reference_file(
     # round trip through the writer / parser
     again = inputs.parse(inputs.write(inp))
     assert again.ndocc == 384 and again.coords[113] == inp.coords[113]
+
+
+def test_alkane_generator_from_the_vtools_guess_orbitals(write_input):
+    """n-alkanes from vtools/631g (C.basis, H.basis, C_1 / C-C_1-1 / C-H_1-1 prototype orbitals rotated onto
+    the bonds).  Counts, geometry (bond lengths, tetrahedral angles), determinism, a round trip through the writer, and the
+    energies of the literal and the fast oracle for methane and ethane: they agree with each other, and the prototype
+    orbitals land within 10 mEh of the reference's own optimised-orbital energies for the same molecules
+    (testing/testing.py:120 ethane guess energy -79.1652117)."""
+    import numpy as np
+    from valence_b200 import inputs
+    from oracle.oracle import Oracle
+    for n in (1, 2, 5):
+        inp = inputs.alkane(n)
+        assert (inp.natom, inp.ndocc, inp.nelec, inp.npair, inp.nunpd) == (3 * n + 2, 4 * n + 1, 8 * n + 2, 0, 0)
+        X = np.array(inp.coords)
+        d = np.linalg.norm(X[:, None, :] - X[None, :, :], axis=-1)
+        for i in range(n - 1):
+            assert abs(d[i, i + 1] - 1.54) < 1e-12
+        for o in inp.orbitals:
+            if len(o.atoms) == 2 and inp.atom_t[o.atoms[1] - 1] == 2:
+                assert abs(d[o.atoms[0] - 1, o.atoms[1] - 1] - 1.09) < 1e-12
+        # every carbon has four neighbours at tetrahedral angles
+        for i in range(n):
+            nb = [j for j in range(inp.natom) if j != i and d[i, j] < 1.6]
+            assert len(nb) == 4
+            for a in range(4):
+                for b in range(a):
+                    u, v = X[nb[a]] - X[i], X[nb[b]] - X[i]
+                    assert abs(u @ v / np.linalg.norm(u) / np.linalg.norm(v) + 1.0 / 3.0) < 1e-9
+        assert inputs.write(inputs.alkane(n)) == inputs.write(inp)
+        assert inputs.parse(inputs.write(inp)).ndocc == inp.ndocc
+    expect = {1: -40.17271092719702, 2: -79.17282996450531}
+    for n, e in expect.items():
+        path, _ = write_input(inputs.alkane(n))
+        o = Oracle(path)
+        rl, rf = o.guess_energy(), o.fast_guess_energy()
+        o.close()
+        assert abs(rl["energy"] - rf["energy"]) < 1e-10 and abs(rf["energy"] - e) < 1e-9
+    assert abs(expect[2] + 79.1652117037620258) < 0.01

@@ -426,6 +426,86 @@ def lif_cluster(nx: int = 4, ny: int = 4, nz: int = 8, spacing: float = 2.015,
     return inp.fix_counts()
 
 
+# n-alkanes from the guess-orbital library of vtools: numeric content of
+# /root/reference/vtools/631g/C.basis, H.basis (6-31G) and of the prototype orbitals C_1.gorb (1s core), C-C_1-1.gorb
+# (sigma bond from C2H6) and C-H_1-1.gorb (sigma bond from C2H6), which are tabulated for a bond along +z
+# (vtools/631g/README-631g): AO index within the two-atom basis set, weight.  vtools rotates them onto every bond of the
+# molecule with openbabel's help; here the chain is built directly (all-trans, tetrahedral angles).
+_C_631G = AtomType(6.0, [
+    Shell(0, [3047.5249, 457.36951, 103.94869, 29.210155, 9.286663, 3.163927],
+          [0.0018347, 0.0140373, 0.0688426, 0.2321844, 0.4679413, 0.362312]),
+    Shell(0, [7.8682724, 1.8812885, 0.5442493], [-0.1193324, -0.1608542, 1.1434564]),
+    Shell(1, [7.8682724, 1.8812885, 0.5442493], [0.0689991, 0.316424, 0.7443083]),
+    Shell(0, [0.1687144], [1.0]),
+    Shell(1, [0.1687144], [1.0]),
+])
+_GORB_C_CORE = [(1, 1.0)]
+# (AO, weight): carbon AOs 1 s, 2 s, 3-5 p, 6 s, 7-9 p; second atom follows (C: 10-18, H: 10-11); p weights are the z entries
+_GORB_CC = {"s": [(2, 0.249), (6, 0.112), (11, 0.249), (15, 0.112)], "pz": [(3, 0.312), (7, 0.168), (12, -0.312), (16, -0.168)]}
+_GORB_CH = {"s": [(2, 0.256), (6, 0.130), (10, 0.318), (11, 0.225)], "pz": [(3, 0.336), (7, 0.184)]}
+
+
+def _bond_orbital(proto: dict, u: np.ndarray) -> List[Tuple[int, float]]:
+    """Prototype sigma orbital (bond along +z) rotated onto the unit vector u: s weights unchanged, a p_z weight w becomes
+    the p vector w u (first AO of the p shell given in the table)."""
+    terms = list(proto["s"])
+    for first, w in proto["pz"]:
+        for k in range(3):
+            if abs(w * u[k]) > 1e-14:
+                terms.append((first + k, float(w * u[k])))
+    return sorted(terms)
+
+
+def alkane(n: int, tol: Tuple[int, int, int] = (10, 20, 10), r_cc: float = 1.54, r_ch: float = 1.09) -> ValenceInput:
+    """All-trans n-alkane C_n H_(2n+2), 6-31G, one DOCC orbital per core and per bond (VSHF-type wavefunction like
+    examples/c3h8): 4n + 1 doubly occupied orbitals with one- and two-atom orbital basis sets."""
+    if n < 1:
+        raise ValueError("alkane: n >= 1")
+    th = np.arccos(-1.0 / 3.0)                         # tetrahedral angle
+    sx, cz = np.sin(th / 2.0), np.cos(th / 2.0)
+    C = [np.array([i * r_cc * sx, 0.0, (0.5 if i % 2 else -0.5) * r_cc * cz]) for i in range(n)]
+    coords: List[np.ndarray] = list(C)
+    atom_t = [1] * n
+    bonds_ch: List[Tuple[int, int]] = []               # (carbon, hydrogen), 0-based atoms
+
+    def add_h(ic: int, d: np.ndarray):
+        coords.append(C[ic] + r_ch * d / np.linalg.norm(d))
+        atom_t.append(2)
+        bonds_ch.append((ic, len(coords) - 1))
+
+    for i in range(n):
+        nb = [C[j] - C[i] for j in (i - 1, i + 1) if 0 <= j < n]
+        nb = [v / np.linalg.norm(v) for v in nb]
+        if len(nb) == 2:                               # methylene: two H in the plane perpendicular to the backbone
+            b = -(nb[0] + nb[1]); b /= np.linalg.norm(b)
+            nrm = np.cross(nb[0], nb[1]); nrm /= np.linalg.norm(nrm)
+            for sgn in (1.0, -1.0):
+                add_h(i, np.cos(th / 2.0) * b + sgn * np.sin(th / 2.0) * nrm)
+        else:                                          # methyl (or methane): the remaining tetrahedral directions
+            a = nb[0] if nb else np.array([0.0, 0.0, 1.0])
+            e0 = np.cross(a, np.array([0.0, 1.0, 0.0]))
+            e0 /= np.linalg.norm(e0)
+            e1 = np.cross(a, e0)
+            for k in range(3):
+                ph = 2.0 * np.pi * k / 3.0
+                add_h(i, -a / 3.0 + np.sqrt(8.0) / 3.0 * (np.cos(ph) * e0 + np.sin(ph) * e1))
+            if not nb:
+                add_h(i, a)
+    docc: List[Orbital] = []
+    for i in range(n):
+        docc.append(Orbital([i + 1], list(_GORB_C_CORE)))
+    for i in range(n - 1):
+        u = (C[i + 1] - C[i]) / np.linalg.norm(C[i + 1] - C[i])
+        docc.append(Orbital([i + 1, i + 2], _bond_orbital(_GORB_CC, u)))
+    for ic, ih in bonds_ch:
+        u = (coords[ih] - C[ic]) / r_ch
+        docc.append(Orbital([ic + 1, ih + 1], _bond_orbital(_GORB_CH, u)))
+    inp = ValenceInput(0, 0, 0, 0, len(docc), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                       tol[0], tol[1], tol[2], 0, 0, 0, 0.0, 0.0, [], atom_t, [[float(v) for v in x] for x in coords],
+                       [copy.deepcopy(_C_631G), copy.deepcopy(_H_631G)], [1.0], [], [], docc)
+    return inp.fix_counts()
+
+
 def dump_json(inp: ValenceInput, path: str, **extra) -> None:
     with open(path, "w") as fh:
         json.dump({"input": inp.to_json(), **extra}, fh, indent=0, separators=(",", ":"))
