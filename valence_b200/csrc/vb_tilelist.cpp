@@ -17,7 +17,12 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
                     std::vector<TilePair>* tl, std::vector<std::pair<long long, int>>* runs, int rank, int nranks)
 {
     tl->clear(); runs->clear();
-    const int PB = nranks > 1 ? 64 : 128, QC = 1024;
+    // bra block: 128 pair groups on one GPU (L2 residency of the block's tables); the ranks of a multi-GPU run own whole blocks,
+    // so theirs are smaller -- the snake deal evens out the triangular growth, the block count the cost differences between
+    // strong and weak pair groups (VB_TILE_PB overrides)
+    int PB = nranks > 1 ? 64 : 128;
+    if (const char* e = std::getenv("VB_TILE_PB")) PB = std::max(1, std::atoi(e));
+    const int QC = 1024;
     auto owner = [&](int blk) { const int k = blk % nranks; return ((blk / nranks) & 1) ? nranks - 1 - k : k; };
     const int na = (int)avec.size(), nb = (int)bvec.size();
     const int nchunks = (nb + QC - 1) / QC;
