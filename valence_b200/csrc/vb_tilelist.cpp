@@ -20,7 +20,7 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
     // bra block: 128 pair groups on one GPU (L2 residency of the block's tables); the ranks of a multi-GPU run own whole blocks,
     // so theirs are smaller -- the snake deal evens out the triangular growth, the block count the cost differences between
     // strong and weak pair groups (VB_TILE_PB overrides)
-    int PB = nranks > 1 ? 64 : 128;
+    int PB = nranks > 1 ? 32 : 128;       // 8 x B200, (H2O)_256: tile pass 586 ms with blocks of 64, 550 with 32, 548 with 16, 582 with 8
     if (const char* e = std::getenv("VB_TILE_PB")) PB = std::max(1, std::atoi(e));
     const int QC = 1024;
     auto owner = [&](int blk) { const int k = blk % nranks; return ((blk / nranks) & 1) ? nranks - 1 - k : k; };
