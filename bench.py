@@ -286,6 +286,55 @@ def run_ours(args) -> None:
             sweep.append({k: r2[k] for k in ("name", "ms_per_step", "wall_ms_per_step", "tile_pass_ms_per_step", "value", "e2e_value", "energy_hartree",
                                              "primitive_quartets_per_step", "roofline_achieved_tflops", "roofline_frac") if k in r2} | ({"parity": r2["parity"]} if "parity" in r2 else {}))
 
+    # the other stated configurations (BASELINE.json configs 1-4) through the same call path: short runs, one GPU
+    configs = []
+    if world == 1 and args.sweep:
+        for cname in ("h2o", "c3h8", "cu+.3d94s1", "lif128"):
+            try:
+                rc, ec, pc, _ = measure(cname, 2, 1, False)
+                ec.close()
+                ent = {k: rc[k] for k in ("name", "workload", "ms_per_step", "wall_ms_per_step", "tile_pass_ms_per_step", "value", "e2e_value", "energy_hartree",
+                                          "reference_algorithm_shell_quartets_per_step", "primitive_quartets_per_step", "roofline_achieved_tflops",
+                                          "roofline_frac") if k in rc}
+                if "parity" in rc:
+                    ent["parity"] = rc["parity"]
+                if cname in EXAMPLES:
+                    with open(os.path.join(ROOT, "tests", "golden", EXAMPLES[cname] + ".json")) as fh:
+                        ent["reference_golden_guess_energy"] = json.load(fh)["golden"]["guess_energy"]
+                if cname in ("h2o", "cu+.3d94s1"):       # the literal restatement of the reference runs these to completion in seconds
+                    from oracle.oracle import Oracle
+                    o = Oracle(pc)
+                    t0 = time.perf_counter()
+                    ro = o.guess_energy()
+                    dtc = time.perf_counter() - t0
+                    o.close()
+                    ent["cpu_literal_oracle"] = {"seconds": dtc, "cores": 1, "energy_hartree": ro["energy"],
+                                                 "shell_quartets_per_s": ro["counters"]["shell_quartets_2e"] / dtc if dtc > 0 else None}
+                configs.append(ent)
+                os.unlink(pc)
+            except Exception as ex:      # a side block must never cost the headline line
+                configs.append({"name": cname, "error": str(ex)[:200]})
+
+    # config 5's spin-coupled variant: the two OH bonds of the first two molecules of (H2O)_32 as spin-coupled pairs (one GPU)
+    scv = None
+    if world == 1 and args.sweep:
+        from valence_b200 import inputs
+        fd, psc = tempfile.mkstemp(prefix="vb_w32sc2_", suffix=".inp")
+        with os.fdopen(fd, "w") as fh:
+            fh.write(inputs.write(inputs.water_cluster(32, tol=(10, 20, 10), sc_molecules=2)))
+        try:
+            esc = api.Engine(psc, device=local)
+            esc.energy()
+            t0 = time.perf_counter()
+            rs = esc.energy()
+            scv = {"workload": "(H2O)_32 6-31G, OH bonds of the first 2 molecules as spin-coupled pairs: npair 4, 256 determinant pairs, "
+                               "spin blocks of 160 inverted on the GPU per pair", "wall_ms": 1e3 * (time.perf_counter() - t0),
+                   "energy_hartree": rs["energy"], "kernel_launches": int(rs["launches"])}
+            esc.close()
+        except RuntimeError as ex:
+            scv = {"error": str(ex)[:200]}
+        os.unlink(psc)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -327,6 +376,10 @@ def run_ours(args) -> None:
             line["energy_plus_first_order"] = grad
         if sweep:
             line["sweep"] = sweep
+        if scv is not None:
+            line["spin_coupled_variant"] = scv
+        if configs:
+            line["configs"] = configs
         if args.cpu_baseline_seconds > 0 and world == 1:
             from oracle import oracle
             cb = oracle.cpu_baseline(path, seconds=args.cpu_baseline_seconds)

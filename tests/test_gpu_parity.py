@@ -272,6 +272,50 @@ FIRST_ORDER = [("examples__h2o", 1), ("examples__h2o", 4), ("examples__li", 1), 
                ("examples__ch4", 2), ("examples__h2o.SC", 3), ("examples__lih.SCval", 1), ("examples__fe3+", 3)]
 
 
+@pytest.mark.parametrize("n,sc", [(2, 1), (2, 2), (3, 1)])
+def test_spin_coupled_determinant_pairs_on_the_gpu_match_oracle(n, sc, write_input, monkeypatch):
+    """Config 5's spin-coupled variant: the determinant pairs of a spin-coupled wavefunction with large blocks are inverted on the
+    GPU (Engine::Impl::sc_cofactors_gpu).  Forced here for small clusters (VB_FAST_MIN_N=0) so that the literal oracle can check
+    it: 4 / 256 / 4 determinant pairs (density_sc, dbra, dket: valence.F90:1612-1870)."""
+    from valence_b200 import inputs
+    monkeypatch.setenv("VB_FAST_MIN_N", "0")
+    path, _ = write_input(inputs.water_cluster(n, tol=(10, 20, 10), sc_molecules=sc))
+    r, ro = gpu_and_oracle(path)
+    assert abs(r["energy"] - ro["energy"]) < 1e-10
+    assert abs(r["wfnorm"] / ro["wfnorm"] - 1.0) < 1e-11
+    for k in EXACT:
+        assert r["counters"][k] == ro["counters"][k], k
+
+
+def test_spin_coupled_pairs_inside_large_clusters(write_input, monkeypatch):
+    """(H2O)_8 with two coupled molecules: host factorisation (blocks of 40) and GPU determinant pairs agree to 1e-10 Eh.
+    (H2O)_16 / (H2O)_32 with the same two coupled molecules (blocks of 80 / 160, 256 determinant pairs: GPU path by default) run in
+    seconds, reproducibly, and the energy lowering against the all-DOCC cluster -- a property of the two coupled molecules -- is
+    the same within 1e-5 Eh at every cluster size."""
+    from valence_b200 import api, inputs
+
+    def energy(n, sc):
+        path, _ = write_input(inputs.water_cluster(n, tol=(10, 20, 10), sc_molecules=sc), f"w{n}_sc{sc}.inp")
+        eng = api.Engine(path)
+        r = eng.energy()
+        eng.close()
+        return r
+
+    host = energy(8, 2)
+    monkeypatch.setenv("VB_FAST_MIN_N", "0")
+    gpu = energy(8, 2)
+    monkeypatch.delenv("VB_FAST_MIN_N")
+    assert abs(host["energy"] - gpu["energy"]) < 1e-10 and abs(host["wfnorm"] / gpu["wfnorm"] - 1.0) < 1e-10
+    for k in EXACT:
+        assert host["counters"][k] == gpu["counters"][k], k
+    lowering = {}
+    for n in (8, 16, 32):
+        lowering[n] = energy(n, 2)["energy"] - energy(n, 0)["energy"]
+    assert abs(energy(32, 2)["energy"] - energy(32, 2)["energy"]) < 1e-10
+    assert -4e-3 < lowering[8] < -2.5e-3
+    assert abs(lowering[16] - lowering[8]) < 1e-5 and abs(lowering[32] - lowering[8]) < 1e-5
+
+
 @pytest.mark.parametrize("name,iorb", FIRST_ORDER)
 def test_first_order_matrices_match_oracle(name, iorb, write_input):
     """The "orbital gradient" accumulators of first_order_opt (valence.F90:527-764):
@@ -458,6 +502,47 @@ def test_c3h8_orbital_optimisation_sweep_is_variational(write_input):
     # the shipped orbitals are already optimised: the sweep lowers the energy by ~2e-8 Eh (never raises it)
     assert r["total_energy"] <= r["guess_energy"] + 1e-10
     assert r["total_energy"] > r["guess_energy"] - 1e-4
+
+
+def test_c3h8_optimised_energy_is_the_energy_of_the_written_orbitals(write_input, tmp_path):
+    """Config 2 with a value pinned independently: the reference-compatible CLI runs one sweep on examples/c3h8, writes `orbitals`
+    (xm_output format, 8 decimals); the energy the run reports must be the energy of exactly those orbitals as evaluated by the
+    fast CPU oracle (a different integral scheme, no shared code), and no higher than the guess energy."""
+    import dataclasses
+    import os
+    import subprocess
+    from valence_b200 import build, inputs
+    from oracle.oracle import Oracle
+    inp, gold = load_golden("examples__c3h8")
+    opt = dataclasses.replace(inp, nset=1, orbset=[(1, 13)], ntol_e_min=4, ntol_e_max=4, max_iter=1)
+    path, _ = write_input(opt, "c3h8_opt.inp")
+    out = subprocess.run([build.CLI, path], capture_output=True, text=True, cwd=str(tmp_path), timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    vals = {}
+    for line in out.stdout.splitlines():
+        f = line.split()
+        if len(f) >= 3 and f[0] == "guess" and f[1] == "energy":
+            vals["guess"] = float(f[2])
+    # one sweep does not converge, so stdout carries no `total energy` line (valence.F90:2879-2881); the `orbitals` file saved after
+    # the sweep does (xm_output, xm_module.F90:556)
+    text = (tmp_path / "orbitals").read_text()
+    vals["total"] = float(text.split("total energy in atomic units")[1].split()[0])
+    assert abs(vals["guess"] - gold["guess_energy"]) < 1e-9 and vals["total"] <= vals["guess"] + 1e-10
+    toks = text.split("total energy")[0].split()
+    pos, orbs = 0, []
+    while pos < len(toks):
+        nat = int(toks[pos]); atoms = [int(t) for t in toks[pos + 1:pos + 1 + nat]]; nt = int(toks[pos + 1 + nat]); pos += 2 + nat
+        terms = [(int(toks[pos + 2 * k]), float(toks[pos + 2 * k + 1])) for k in range(nt)]
+        pos += 2 * nt
+        orbs.append(inputs.Orbital(atoms, terms))
+    assert len(orbs) == len(inp.orbitals) and all(a.atoms == b.atoms and [t[0] for t in a.terms] == [t[0] for t in b.terms] for a, b in zip(orbs, inp.orbitals))
+    again = dataclasses.replace(inp, orbitals=orbs)
+    p2, _ = write_input(again, "c3h8_written.inp")
+    o = Oracle(p2)
+    rf = o.fast_guess_energy()
+    o.close()
+    # weights are written with 8 decimals; the energy is stationary in them to first order
+    assert abs(rf["energy"] - vals["total"]) < 2e-8, (rf["energy"], vals)
 
 
 def test_lif_cluster_matches_oracle_and_full_lif128_runs(write_input):

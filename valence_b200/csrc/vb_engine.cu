@@ -280,6 +280,8 @@ struct Engine::Impl {
     // GPU inverse + determinant of Se[ent][ent] (Gauss-Jordan, then one double-double refinement step); res_dev[0] = det,
     // res_dev[1] = smallest / largest pivot
     void gpu_inverse(int nso, const std::vector<int>& ent, DBuf<int>& ent_dev, DBuf<double>& M, DBuf<double>& Minv, double* res_dev);
+    void sc_cofactors_gpu(const Input& in, const Wavefunction& wf, EnergyResult* out, int* ndp_out);
+    DBuf<int> sc_idx;                                 // spin-coupled determinant pairs on the GPU: entry lists / positions of one pair
     DBuf<double> Fmat, r1x, r1y, Qd, Rd, Ni;       // first_order_opt in rank-one form
     DBuf<int> en_dev, eo_dev, posn_dev, poso_dev;
     bool use_gather = false;                         // energy(): table shares are exchanged on the device (all-gather)
@@ -585,6 +587,12 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
             fast = false;
             c0 = 1.0;
             c0_keep = 0.0;
+            if (in.npair > 0 && std::max(na, nb) > fast_min) {
+                // spin-coupled pairs in a large wavefunction: every determinant pair's blocks inverted on the GPU
+                sc_cofactors_gpu(in, wf, out, &ndp);
+                *fast_out = false; *c0_out = 1.0; *ndp_out = ndp;
+                return;
+            }
             // small blocks / several determinant pairs / possibly singular blocks: factorise on the host
             // (O(n^3) once per determinant pair, n <= 64), contract on the GPU
             std::vector<double> hSe, hHe;
@@ -602,6 +610,113 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
     *fast_out = fast; *c0_out = c0; *ndp_out = ndp;
 }
 
+
+// Cofactor data of a spin-coupled wavefunction with large determinants, built on the GPU.  Same enumeration and the same packed
+// layout as build_cofactors (vb_cofactor.cpp; density_sc / dbra / dket of the reference, valence.F90:1576-1588, 1648-1870): for every
+// (bra coupling, ket coupling, bra spin assignment, ket spin assignment) the alpha and beta overlap blocks are gathered from the
+// entry-level overlaps, inverted by the cooperative Gauss-Jordan kernel (+ one double-double refinement step) and scattered to
+// entry level straight into the pair's slot of `cof`; the one-electron sums of the pair are reduced on the device.  Blocks must
+// be non-singular (the host path treats null spaces exactly, for blocks up to 64).  Leaves e1, wfnorm in the object.
+void Engine::Impl::sc_cofactors_gpu(const Input& in, const Wavefunction& wf, EnergyResult* out, int* ndp_out)
+{
+    const int nso = wf.nso, nelec = (int)wf.bra.size();
+    std::vector<int> entry_of_slot(nelec);
+    for (int s = 0; s < nso; ++s)
+        for (int k = 0; k < wf.nslots(s); ++k) entry_of_slot[wf.slot(s, k)] = s;
+    const int npair = in.npair, nunpd = in.nunpd, ndocc = in.ndocc;
+    const int nsc = std::max(1, in.nspinc);
+    const std::vector<double>& csc = coeff_sc.empty() ? in.coeff_sc : coeff_sc;
+    const size_t stride = cof_stride(nso);
+    const long long nmask = 1LL << npair;
+    const long long ncoup = only_isc >= 0 ? 1 : (long long)nsc * nsc;
+    const long long ndp_tot = ncoup * nmask * nmask;
+    if (ndp_tot > 65536 || (double)ndp_tot * stride * 8.0 > 64e9) throw std::runtime_error("valence_b200: too many determinant pairs for the GPU cofactor path");
+    cof.alloc((size_t)ndp_tot * stride);
+    cof.zero(st);
+    std::vector<int> a_fixed, b_fixed;     // set_up_unpaired_docc, valence.F90:2461-2480 (0-based slots)
+    for (int i = 0; i < nunpd; ++i) a_fixed.push_back(2 * npair + i);
+    for (int d = 0; d < ndocc; ++d) { a_fixed.push_back(2 * npair + nunpd + 2 * d); b_fixed.push_back(2 * npair + nunpd + 2 * d + 1); }
+    const int na = npair + (int)a_fixed.size(), nb = npair + (int)b_fixed.size();
+    Ma.alloc((size_t)na * na + 1); Mai.alloc((size_t)na * na + 1); Mb.alloc((size_t)nb * nb + 1); Mbi.alloc((size_t)nb * nb + 1);
+    gj_res.alloc((size_t)std::max(na, nb) * std::max(na, nb));
+    gj_ws.alloc(2 * (size_t)std::max(na, nb)); piv.alloc(2 * (size_t)std::max(na, nb) + 2);
+    gjout.alloc(4); one_e.alloc(4);
+    sc_idx.alloc(2 * (size_t)(na + nb) + 4 * (size_t)nso);
+    long double e1s = 0.0L, wns = 0.0L;
+    double minratio = 1.0;
+    int d = 0;
+    auto invert = [&](DBuf<double>& M, DBuf<double>& Minv, const int* rows, const int* cols, int n, double* res) {
+        if (n == 0) { const double one[2] = {1.0, 1.0}; CK(cudaMemcpyAsync(res, one, sizeof one, cudaMemcpyHostToDevice, st)); return; }
+        k_gather_block<<<(n * n + 255) / 256, 256, 0, st>>>(Se.p, nso, rows, cols, n, M.p);
+        int grid = std::max(1, std::min(nsm, n / 4));
+        double* Ap = M.p; double* Ip = Minv.p; double* wsp = gj_ws.p; int* iwp = piv.p; int nn = n;
+        void* args[] = {&Ap, &nn, &Ip, &wsp, &iwp, &res};
+        CK(cudaLaunchCooperativeKernel((void*)k_gj_inverse_grid, dim3(grid), dim3(1024), args, 0, st));
+        k_gather_block<<<(n * n + 255) / 256, 256, 0, st>>>(Se.p, nso, rows, cols, n, M.p);
+        const dim3 g((n + RF_T - 1) / RF_T, (n + RF_T - 1) / RF_T), b(RF_T, RF_T);
+        k_inv_residual_dd<<<g, b, 0, st>>>(M.p, Minv.p, n, gj_res.p);
+        k_inv_update<<<g, b, 0, st>>>(Minv.p, gj_res.p, n, M.p);       // refined inverse lands in M
+        CK(cudaGetLastError());
+        launches += 5;
+    };
+    for (int isc = 0; isc < nsc; ++isc)
+        for (int jsc = 0; jsc < nsc; ++jsc) {
+            if (only_isc >= 0 && (isc != only_isc || jsc != only_jsc)) continue;
+            for (long long bm = 0; bm < nmask; ++bm)
+                for (long long km = 0; km < nmask; ++km, ++d) {
+                    std::vector<int> abra, bbra, aket, bket;
+                    for (int k = 0; k < npair; ++k) {
+                        int b1 = in.pair(isc, k, 0) - 1, b2 = in.pair(isc, k, 1) - 1;
+                        int k1 = in.pair(jsc, k, 0) - 1, k2 = in.pair(jsc, k, 1) - 1;
+                        if ((bm >> k) & 1) std::swap(b1, b2);
+                        if ((km >> k) & 1) std::swap(k1, k2);
+                        abra.push_back(b1); bbra.push_back(b2); aket.push_back(k1); bket.push_back(k2);
+                    }
+                    abra.insert(abra.end(), a_fixed.begin(), a_fixed.end()); aket.insert(aket.end(), a_fixed.begin(), a_fixed.end());
+                    bbra.insert(bbra.end(), b_fixed.begin(), b_fixed.end()); bket.insert(bket.end(), b_fixed.begin(), b_fixed.end());
+                    // one upload: [ea_bra na][ea_ket na][eb_bra nb][eb_ket nb][posa_bra nso][posa_ket nso][posb_bra nso][posb_ket nso]
+                    std::vector<int> h(2 * (size_t)(na + nb) + 4 * (size_t)nso, -1);
+                    int* ea_b = h.data(); int* ea_k = ea_b + na; int* eb_b = ea_k + na; int* eb_k = eb_b + nb;
+                    int* pa_b = eb_k + nb; int* pa_k = pa_b + nso; int* pb_b = pa_k + nso; int* pb_k = pb_b + nso;
+                    for (int r = 0; r < na; ++r) { ea_b[r] = entry_of_slot[abra[r]]; ea_k[r] = entry_of_slot[aket[r]]; pa_b[ea_b[r]] = r; pa_k[ea_k[r]] = r; }
+                    for (int r = 0; r < nb; ++r) { eb_b[r] = entry_of_slot[bbra[r]]; eb_k[r] = entry_of_slot[bket[r]]; pb_b[eb_b[r]] = r; pb_k[eb_k[r]] = r; }
+                    CK(cudaMemcpyAsync(sc_idx.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+                    g_h2d_bytes += (long long)(h.size() * sizeof(int));
+                    const int* D0 = sc_idx.p;
+                    invert(Ma, Mai, D0, D0 + na, na, gjout.p);
+                    invert(Mb, Mbi, D0 + 2 * na, D0 + 2 * na + nb, nb, gjout.p + 2);
+                    double* slot = cof.p + (size_t)d * stride;
+                    double* Ga = slot + COF_HEADER;
+                    double* Gb = Ga + (size_t)nso * nso;
+                    const int* P0 = D0 + 2 * (na + nb);
+                    if (na) k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Ma.p, na, P0, P0 + nso, nso, Ga);
+                    if (nb) k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mb.p, nb, P0 + 2 * nso, P0 + 3 * nso, nso, Gb);
+                    k_one_electron_energy<<<1, 1024, 0, st>>>(Se.p, He.p, Ga, Gb, nso * nso, one_e.p);
+                    CK(cudaGetLastError());
+                    launches += 3;
+                    double g4[4], oe[4];
+                    CK(cudaMemcpyAsync(g4, gjout.p, sizeof g4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpyAsync(oe, one_e.p, sizeof oe, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));      // also keeps the host index vector alive until it is copied
+                    g_d2h_bytes += 64;
+                    const double ra = na ? g4[1] : 1.0, rb = nb ? g4[3] : 1.0;
+                    minratio = std::min(minratio, std::min(ra, rb));
+                    if (!(g4[0] != 0.0) || !(g4[2] != 0.0) || std::min(ra, rb) < 1e-13)
+                        throw std::runtime_error("valence_b200: singular spin block in a spin-coupled wavefunction too large for the host factorisation");
+                    const double w = only_isc >= 0 ? 1.0 : ((npair > 0 && in.nspinc > 0) ? csc[isc] * csc[jsc] : 1.0);
+                    const double hdr[COF_HEADER] = {w, g4[0], 1.0, 0.0, 0.0, 0.0, g4[2], 1.0, 0.0, 0.0, 0.0, 0.0};
+                    CK(cudaMemcpyAsync(slot, hdr, sizeof hdr, cudaMemcpyHostToDevice, st));
+                    CK(cudaStreamSynchronize(st));
+                    const long double dd0 = (long double)w * g4[0] * g4[2];
+                    e1s += dd0 * ((long double)oe[0] + oe[2]);
+                    wns += dd0 * ((long double)oe[1] + oe[3]);
+                }
+        }
+    e1 = (double)e1s;
+    wfnorm = (double)(wns / (long double)nelec);
+    out->min_pivot_ratio = minratio;
+    *ndp_out = d;
+}
 
 void Engine::Impl::gpu_inverse(int nso, const std::vector<int>& ent, DBuf<int>& ent_dev, DBuf<double>& M, DBuf<double>& Minv, double* res_dev)
 {

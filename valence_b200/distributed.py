@@ -1,15 +1,16 @@
-"""Multi-GPU plumbing of the energy path: one process per GPU, the tile list of the fused
-ERI + contraction pass is sharded block-cyclically over ranks (tile k -> rank k mod N, work
-stealing inside each GPU), and ONE all-reduce sums the packed accumulators
-[E2, screening counters...] -- the replacement of the reference's four MPI all-reduces per
-energy (xm_equalize / xm_equalize_scalar, /root/reference/src/xm_module.F90:853-910)."""
+"""Multi-GPU plumbing of the energy path for hosts that do the reduction themselves with torch.distributed
+(api.Engine.energy_distributed / first_order_distributed without an in-library communicator): one process per GPU, the
+work items of the tile pass are dealt over the ranks (work stealing inside each GPU), and ONE all-reduce sums the packed
+accumulators [E2 (grid multiple), screening counters..., E2 (rest)] -- the replacement of the reference's four MPI
+all-reduces per energy (xm_equalize / xm_equalize_scalar, /root/reference/src/xm_module.F90:853-910).  With
+Engine.attach_comm the library does all of this itself over NCCL (csrc/vb_nccl.cpp)."""
 from __future__ import annotations
 
 from typing import List
 
 
 def shard(ntiles: int, rank: int, nranks: int) -> range:
-    """Tiles owned by `rank` (mirrors TileArgs.tile_first / tile_stride in csrc/vb_tile.cuh)."""
+    """Work items owned by `rank` when items are dealt round-robin (make_items, csrc/vb_tilelist.cpp)."""
     return range(rank, ntiles, nranks)
 
 
