@@ -748,6 +748,87 @@ static void f_block(const f_pg *P, const f_pg *Q, double thr, double *E, long lo
     free(Hh);
 }
 
+/* the same two routines with every accumulation (primitive sums, both density transformations) in extended precision:
+ * VO_FAST_XACC=1.  A block of a 256-molecule cluster sums ~1e5 terms; in plain double that costs ~1e-15 relative per block,
+ * which is what separates the fixture from the GPU engine's (double-double assembled) energy at that size. */
+static void f_eri_sp_x(const f_sp *A, const f_sp *B, double thr, long double *I, long long *npq)
+{
+    const int nab = A->nab, ncd = B->nab, nhA = A->nh, nhB = B->nh, L = A->Lp + B->Lp;
+    const double c25 = 34.98683665524972497;    /* 2 pi^2.5 */
+    double R[FL_NH8], M[FL_NH4 * FL_NH4];
+    long double tmp[36 * FL_NH4];
+    for (int i = 0; i < A->npp; ++i) {
+        const f_pp *a = &A->pp[i];
+        if (a->w * B->wmax < thr) break;
+        const double *Ea = A->E + (size_t)i * nab * nhA;
+        for (int j = 0; j < B->npp; ++j) {
+            const f_pp *b = &B->pp[j];
+            if (a->w * b->w < thr) break;
+            const double *Eb = B->E + (size_t)j * ncd * nhB;
+            double p = a->p, q = b->p, alpha = p * q / (p + q);
+            double PQ[3] = {a->P[0] - b->P[0], a->P[1] - b->P[1], a->P[2] - b->P[2]};
+            double pref = c25 / (p * q * sqrt(p + q));
+            ++*npq;
+            f_hermite_R(L, alpha, PQ, R);
+            if (L == 0) { I[0] += (long double)pref * Ea[0] * Eb[0] * R[0]; continue; }
+            for (int h = 0; h < nhA; ++h)
+                for (int r = 0; r < nhB; ++r) M[h * nhB + r] = fh_sgn[r] * R[fh_sum[h][r]];
+            for (int ab = 0; ab < nab; ++ab)
+                for (int r = 0; r < nhB; ++r) {
+                    long double s = 0.0L;
+                    for (int h = 0; h < nhA; ++h) s += (long double)Ea[ab * nhA + h] * M[h * nhB + r];
+                    tmp[ab * nhB + r] = s;
+                }
+            for (int ab = 0; ab < nab; ++ab)
+                for (int cd = 0; cd < ncd; ++cd) {
+                    long double s = 0.0L;
+                    for (int r = 0; r < nhB; ++r) s += tmp[ab * nhB + r] * Eb[cd * nhB + r];
+                    I[ab * ncd + cd] += (long double)pref * s;
+                }
+        }
+    }
+}
+
+static void f_block_x(const f_pg *P, const f_pg *Q, double thr, double *E, long long *npq)
+{
+    const int npP = P->np, npQ = Q->np;
+    long double I[36 * 36], *Hh = (long double *)malloc(sizeof(long double) * 36 * (size_t)npQ);
+    long double *El = (long double *)malloc(sizeof(long double) * ((size_t)npP * npQ + 1));
+    for (int k = 0; k < npP * npQ; ++k) El[k] = 0.0L;
+    for (int x = 0; x < P->nsp; ++x) {
+        const f_sp *A = &P->sp[x];
+        if (Q->nsp == 0 || A->wmax * Q->sp[0].wmax < thr) break;
+        for (int k = 0; k < A->nab * npQ; ++k) Hh[k] = 0.0;
+        for (int y = 0; y < Q->nsp; ++y) {
+            const f_sp *B = &Q->sp[y];
+            if (A->wmax * B->wmax < thr) break;
+            for (int k = 0; k < A->nab * B->nab; ++k) I[k] = 0.0;
+            f_eri_sp_x(A, B, thr, I, npq);
+            for (int ab = 0; ab < A->nab; ++ab)
+                for (int cd = 0; cd < B->nab; ++cd) {
+                    long double v = I[ab * B->nab + cd];
+                    if (v == 0.0L) continue;
+                    const double *d = B->D + (size_t)cd * npQ;
+                    long double *hrow = Hh + (size_t)ab * npQ;
+                    for (int q = 0; q < npQ; ++q) hrow[q] += v * d[q];
+                }
+        }
+        for (int ab = 0; ab < A->nab; ++ab) {
+            const long double *hrow = Hh + (size_t)ab * npQ;
+            const double *d = A->D + (size_t)ab * npP;
+            for (int p = 0; p < npP; ++p) {
+                if (d[p] == 0.0) continue;
+                long double *e = El + (size_t)p * npQ;
+                for (int q = 0; q < npQ; ++q) e[q] += d[p] * hrow[q];
+            }
+        }
+    }
+    for (int k = 0; k < npP * npQ; ++k) E[k] = (double)El[k];
+    free(Hh); free(El);
+}
+
+static int f_xacc = 0;      /* VO_FAST_XACC: extended-precision block sums */
+
 /* ---- the reference's task bookkeeping for one integral value ------------------------------------------- */
 typedef struct { long double e2; vo_counters cnt; } f_acc;   /* extended-precision accumulation of the task sum */
 
@@ -929,7 +1010,7 @@ static void f_schwarz_one(void *ctx, long long k, int tid)
     if (!F->sym && P->h > P->g) return;
     double *E = DARR((size_t)P->np * P->np);
     long long npq = 0;
-    f_block(P, P, 1e-32, E, &npq);
+    if (f_xacc) f_block_x(P, P, 1e-32, E, &npq); else f_block(P, P, 1e-32, E, &npq);
     for (int p = 0; p < P->np; ++p) {
         int s = P->ps[p], t = P->pt[p];
         if (s >= t) c->schwarz[indx(s, t)] = sqrt(E[(size_t)p * P->np + p]);
@@ -968,7 +1049,7 @@ static void f_blk_one(void *ctx, long long k, int tid)
     if (cacheable && F->cache[J->blk[k]]) Eu = F->cache[J->blk[k]];
     else {
         long long npq = 0;
-        f_block(P, Q, F->thr, E, &npq);
+        if (f_xacc) f_block_x(P, Q, F->thr, E, &npq); else f_block(P, Q, F->thr, E, &npq);
         J->npq[tid] += npq;
         if (cacheable) { double *keep = DARR((size_t)P->np * Q->np); memcpy(keep, E, sizeof(double) * (size_t)P->np * Q->np); F->cache[J->blk[k]] = keep; }
     }
@@ -1040,6 +1121,7 @@ int vo_fast_guess_energy(vo_ctx *c, int nthreads, double thr, vo_fast_result *ou
     memset(out, 0, sizeof *out);
     if (c->npair > 0) return -1;
     f_nthreads = nthreads;
+    f_xacc = getenv("VO_FAST_XACC") != NULL && atoi(getenv("VO_FAST_XACC")) != 0;
     double t0 = mono_now();
     setup_energy(c);
     memset(&c->cnt, 0, sizeof c->cnt);

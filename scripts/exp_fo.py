@@ -25,7 +25,7 @@ for n, iorb in [(int(a.split(":")[0]), int(a.split(":")[1])) for a in sys.argv[1
         env = dict(os.environ); env.update(s)
         f = f"/tmp/fo_{n}_{iorb}_{len(s)}.npy"
         out = subprocess.run([sys.executable, "-c", CHILD, str(n), str(iorb), f], env=env, capture_output=True, text=True)
-        print("==", n, iorb, s, "\n".join(l for l in out.stdout.splitlines() if l.startswith("RESULT")), flush=True)
+        print("==", n, iorb, s, "\n".join(l for l in out.stdout.splitlines() if l.startswith(("RESULT", "[fo]", "[time]"))), flush=True)
         if out.returncode != 0: print(out.stderr[-1500:])
         else: outs.append(np.load(f))
     if len(outs) == 2:

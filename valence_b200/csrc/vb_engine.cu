@@ -748,14 +748,14 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
                             int rank, int nranks, EnergyResult* out, std::vector<double>* sch_out)
 {
     const int nso = wf.nso;
-    double t1 = now_ms();
+    double t1 = now_ms(), t_cof = 0.0;
     bool fast = false;
     double c0 = 1.0;
     int ndp = 0;
-    cofactor_stage(in, wf, diag_only, out, &fast, &c0, &ndp);
-    double t2 = now_ms();
 
     // ---- pair groups, shell-pair tables, folded densities ---------------------------------------------
+    // (host cores) built WHILE the GPU forms the entry-level matrices, inverts the spin blocks and reduces the one-electron
+    // sums (cofactor_stage below): the two do not depend on each other
     // magnitude cuts: the Schwarz (diagonal) pass must resolve (st|st) down to itol^2, the energy pass
     // needs the integrals to ~itol; never looser than the configured tau
     const double tau_diag = std::min(tau, 0.01 * itol * itol), tau_energy = std::min(tau, 0.01 * itol);
@@ -770,7 +770,15 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     }
     const bool gather = use_gather && comm && comm->nranks() > 1 && !gen && !shard_pending;
     if (gather) { topts.shard_mode = 3; topts.shard_rank = comm->rank(); topts.shard_nranks = comm->nranks(); }
-    build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts, topts);
+    {
+        std::exception_ptr bt_err;
+        std::thread bt([&] { try { build_tiles(in, bas, wf, orbs2e, tau_diag, !gen, &ts, topts); } catch (...) { bt_err = std::current_exception(); } });
+        try { cofactor_stage(in, wf, diag_only, out, &fast, &c0, &ndp); } catch (...) { bt.join(); throw; }
+        t_cof = now_ms() - t1;
+        bt.join();
+        if (bt_err) std::rethrow_exception(bt_err);
+    }
+    const double t2 = t1 + t_cof;      // end of the device-side cofactor stage; what is left of the table build counts as host set-up
     if (gather) {
         // Every rank has built the pair groups it owns (blocks of 16, round-robin) with local offsets.  The shares meet on
         // the DEVICE: sizes by one small all-reduce, then each table is all-gathered over NVLink into a layout with one
