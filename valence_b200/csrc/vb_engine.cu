@@ -268,6 +268,7 @@ struct Engine::Impl {
     bool first_order_cached(const Input& in, const Wavefunction& wf, int es, int iorb, const std::vector<double>& sch, int rank, int nranks,
                             std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* acc);
     TileSetup ts_keep;                               // host tables of the last evaluation (storage kept)
+    TileSetup ts_fo_keep;                             // first_order_opt: tables of the unsubstituted lists
     // table build shared by the ranks of a node (Engine::shard_tables): consumed by the next energy_partial
     bool shard_pending = false, prepared = false;
     int shard_rank = 0, shard_nranks = 1;
@@ -292,6 +293,7 @@ struct Engine::Impl {
     // assembles E = (E1 + E2 / c0) / (N1 / nelec) + Enuc in extended precision (a 256-molecule cluster has |E_elec| ~ 2e5 Eh,
     // one ulp of that is 3e-11 Eh: five roundings of the plain formula are the whole 1e-10 Eh budget)
     double e1u[2] = {0, 0}, wnu[2] = {0, 0}, c0_keep = 0;
+    bool pb_same = false;       // closed shell: Pb holds the same numbers as Pa (the contraction then reads Pa only)
     bool split_sum = false;     // energy_partial: leave E2 as the (grid multiple, rest) pair in accum[0], accum[1 + CNT_N]
     int nelec_keep = 0;
     // primitive-quartet magnitude cut (VB_PRIM_TAU overrides).  Measured on (H2O)_64 / (H2O)_128: the energy is the same to
@@ -574,6 +576,7 @@ void Engine::Impl::cofactor_stage(const Input& in, const Wavefunction& wf, bool 
             Pa.alloc((size_t)nso * nso); Pb.alloc((size_t)nso * nso);
             k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(Mai.p, na, posa_bra.p, posa_bra.p, nso, Pa.p);
             k_entry_density<<<(nso * nso + 255) / 256, 256, 0, st>>>(same ? Mai.p : Mbi.p, nb, posb_bra.p, posb_bra.p, nso, Pb.p);
+            pb_same = same && na == nb;      // same entry lists, hence the same positions
             one_e.alloc(4);
             k_one_electron_energy<<<1, 1024, 0, st>>>(Se.p, He.p, Pa.p, Pb.p, nso * nso, one_e.p);
             CK(cudaGetLastError());
@@ -870,7 +873,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.pgs = pgs.p; A.pg_pairs = pg_pairs.p; A.sps = sps.p; A.pps = pps.p; A.pps_flat = pps_flat.p; A.tau = tau_diag;
     A.pq_counters = pq_counters.p; A.dmat = dmat.p;
     A.boys = boys.p; A.counter = counter.p; A.nso = nso; A.nnd = wf.nnd; A.sym = wf.sym ? 1 : 0; A.subject = wf.subject;
-    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.g_cap = g_cap; A.boys_small = boys_small.p; A.boys_cap = boys_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
+    A.dq_cap = dq_cap2; A.hs_cap = hs_cap; A.hs_ld = hs_ld; A.g_cap = g_cap; A.boys_small = boys_small.p; A.boys_cap = boys_cap; A.pp_cap = pp_cap; A.sp_cap = sp_cap; A.itol = itol; A.Pa = Pa.p; A.Pb = (fast && pb_same) ? Pa.p : Pb.p; A.c0 = fast ? c0 : 1.0; A.nsh_bra = nsh_bra.p; A.nsh_ket = nsh_ket.p;
     A.cof = cof.p; A.ndp = ndp; A.cof_stride = (long long)cof_stride(nso);
     A.counters = counters.p; A.gen_scratch = gen_scratch.p;
     A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;
@@ -1272,7 +1275,7 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     // ---- all tables of the unsubstituted lists; the free part stays resident ---------------------------------
     TileOpts fo;
     fo.isolate = es; fo.wcut = wall;
-    TileSetup tsF;
+    TileSetup& tsF = ts_fo_keep;     // storage reused across calls, like ts_keep of the energy pass
     build_tiles(in, bas, wb, orbs2e, tau_diag, true, &tsF, fo);
     const int nfree = tsF.n_free_pg, npgF = (int)tsF.pgs.size();
     if (nfree == 0) return false;

@@ -50,6 +50,11 @@ __device__ __forceinline__ int tri_index(int a, int c) { return a * (a + 1) / 2 
 // W(s,t,u,v) = P[s,t] P[u,v] - sum_sigma P^s[s,v] P^s[u,t]   (times c0 outside)
 __device__ __forceinline__ double w_term(const double* __restrict__ Pa, const double* __restrict__ Pb, int nso, int s, int t, int u, int v)
 {
+    if (Pa == Pb) {     // closed shell: one density for both spins (the host passes the same pointer) -- half the gathers, same arithmetic
+        const double ast = Pa[s * nso + t], auv = Pa[u * nso + v], asv = Pa[s * nso + v], aut = Pa[u * nso + t];
+        const double x = __dmul_rn(asv, aut);
+        return __dmul_rn(ast + ast, auv + auv) - x - x;
+    }
     double ast = Pa[s * nso + t], bst = Pb[s * nso + t], auv = Pa[u * nso + v], buv = Pb[u * nso + v];
     double asv = Pa[s * nso + v], bsv = Pb[s * nso + v], aut = Pa[u * nso + t], but = Pb[u * nso + t];
     return __dmul_rn(ast + bst, auv + buv) - __dmul_rn(asv, aut) - __dmul_rn(bsv, but);
