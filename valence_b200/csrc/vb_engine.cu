@@ -929,6 +929,25 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
         }
         pg.smax = m;
     }
+    if (std::getenv("VB_DEBUG_PAIRS")) {
+        // how many orbital pairs of a pair group can ever pass the Schwarz screen (sch_st * max sch > itol)?
+        double smx = 0.0;
+        for (const PGDesc& pg : ts.pgs) smx = std::max(smx, pg.smax);
+        long long hist[33] = {0}, histw[33] = {0}, tot = 0, live = 0;
+        for (const PGDesc& pg : ts.pgs) {
+            if (pg.np <= 0) continue;
+            int n = 0;
+            for (int p = 0; p < pg.np; ++p) {
+                double v = sch[(size_t)ts.pg_pairs[2 * (pg.pair_beg + p)] * nso + ts.pg_pairs[2 * (pg.pair_beg + p) + 1]];
+                if (v * smx > itol) ++n;
+            }
+            hist[std::min(32, n)]++; tot += pg.np; live += n;
+            (void)histw;
+        }
+        std::printf("[pairs] %lld pair groups, %lld pairs, %lld can pass the Schwarz screen (max sch %.3g); live pairs per group:", (long long)ts.pgs.size(), tot, live, smx);
+        for (int n = 0; n <= 32; ++n) if (hist[n]) std::printf(" %d:%lld", n, hist[n]);
+        std::printf("\n");
+    }
     // ---- tile list: pair-group pairs that can hold a significant integral ----------------------------
     // Tile (a, b), b <= a, exists when smax_a * smax_b > itol.  Order: blocks of PB consecutive bra pair groups
     // against chunks of QC consecutive ket pair groups, so that the tables of one (block, chunk) -- a few tens of
@@ -940,6 +959,24 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     std::vector<std::pair<long long, int>> runs;      // (first tile, # tiles) of every non-empty (a, chunk)
     make_tile_list(ts.pgs, all, all, itol, &tl, &runs, rank, nranks);      // this rank's bra blocks only
     const long long ntiles = (long long)tl.size();
+    if (std::getenv("VB_DEBUG_PAIRS")) {
+        // per tile: orbital pairs of either side that can pass the Schwarz screen against the other side's largest value
+        long long h1[5] = {0, 0, 0, 0, 0}, h2[17] = {0};
+        auto live = [&](const PGDesc& a, double smax_other) {
+            int n = 0;
+            for (int p = 0; p < a.np; ++p)
+                if (sch[(size_t)ts.pg_pairs[2 * (a.pair_beg + p)] * nso + ts.pg_pairs[2 * (a.pair_beg + p) + 1]] * smax_other > itol) ++n;
+            return n;
+        };
+        for (const TilePair& t : tl) {
+            const int nP = live(ts.pgs[t.x], ts.pgs[t.y].smax), nQ = live(ts.pgs[t.y], ts.pgs[t.x].smax);
+            const int jb = (nP + 7) / 8, mb = (nQ + 7) / 8;
+            h1[jb]++; h2[jb * mb]++;
+        }
+        std::printf("[pairs] %lld tiles; column blocks of the first transform (of 4): 0:%lld 1:%lld 2:%lld 3:%lld 4:%lld; blocks of the second (of 16):", ntiles, h1[0], h1[1], h1[2], h1[3], h1[4]);
+        for (int k = 0; k <= 16; ++k) if (h2[k]) std::printf(" %d:%lld", k, h2[k]);
+        std::printf("\n");
+    }
     // work items of the s/p kernel: pieces of <= m tiles of a run (they share the bra pair group); the d-shell
     // kernel takes single tiles.  Only this rank's items are kept (block-cyclic over the ranks; z = slot of the
     // item's first tile in the G hand-over buffer).
@@ -968,6 +1005,11 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     // a documented experiment, off by default
     bool use_seg = false;
     if (const char* e = std::getenv("VB_PSEG")) use_seg = csplit && std::atoi(e) != 0;
+    // (Tried: orbital pairs sorted by Schwarz value on the device and the density transforms of a tile restricted to the pairs that
+    // can pass the reference's Schwarz screen in that tile -- on average 2.6 of 4 column blocks in the first and 7 of 16 blocks in
+    // the second transform over the tiles of (H2O)_256, VB_DEBUG_PAIRS.  No gain in the light classes -- the tiles that carry
+    // the work are the ones that need every block -- and the extra predicates cost the pp classes registers: 4.40 s against
+    // 4.03 s for the pass.  profiles/r2_pair_screen_experiment.log)
     CK(cudaEventRecord(ev2, st));
     if (use_seg && mine > 0) {
         // far-field tables of every segment / primitive pair of this evaluation (part of the timed tile pass)
