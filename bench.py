@@ -357,6 +357,8 @@ def run_ours(args) -> None:
             "gpu_launches": rec["gpu_launches"],
             "roofline": {"bound": "fp64", "achieved": rec["roofline_achieved_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": rec["roofline_frac"],
                          "traffic": traffic_from_profiles(args.workload),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the class + contraction launches of one energy pass, ncu capture of "
+                                           "the same workload committed as profiles/r2_pclass_dram_<workload>.csv (not measured in this run; null when there is none)",
                          "transforms": {"achieved": rec["transform_tflops"], "unit": "TFLOP/s",
                                         "frac_integrals_plus_transforms": (rec["roofline_achieved_tflops"] + rec["transform_tflops"]) / peak if peak else None,
                                         "note": "executed FP64 tensor-core flops (DMMA m8n8k4 = 512 flops, in-kernel instruction count) of the two density "

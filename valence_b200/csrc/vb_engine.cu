@@ -68,6 +68,12 @@ struct DBuf {
         if (!v.empty()) CK(cudaMemcpyAsync(p + off, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
         g_h2d_bytes += (long long)(v.size() * sizeof(T));
     }
+    void upload_at(size_t off, const T* src, size_t cnt, cudaStream_t st)   // straight from the caller's storage (no temporary)
+    {
+        if (off + cnt > cap) throw std::runtime_error("valence_b200: device table overflow");
+        if (cnt) CK(cudaMemcpyAsync(p + off, src, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+        g_h2d_bytes += (long long)(cnt * sizeof(T));
+    }
     void zero(cudaStream_t st) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
     void download(std::vector<T>& v, cudaStream_t st)
     {
@@ -268,7 +274,22 @@ struct Engine::Impl {
     bool first_order_cached(const Input& in, const Wavefunction& wf, int es, int iorb, const std::vector<double>& sch, int rank, int nranks,
                             std::vector<double>* ham, std::vector<double>* ovl, EnergyResult* acc);
     TileSetup ts_keep;                               // host tables of the last evaluation (storage kept)
-    TileSetup ts_fo_keep;                             // first_order_opt: tables of the unsubstituted lists
+    // Schwarz table of the last guess energy, orbital by orbital, and a digest of the state it belongs to (geometry, orbital
+    // weights, screen): first_order_opt needs the same table for its unsubstituted lists (valence.F90:666-667) and takes it from
+    // here instead of repeating the table build and the diagonal pass when nothing has changed in between
+    std::vector<double> sch_cache;
+    int sch_cache_n = 0;
+    unsigned long long sch_cache_key = 0;
+    unsigned long long state_key(const Input& in) const
+    {
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+        mix(xyz_angs.data(), xyz_angs.size() * sizeof(double));
+        for (const std::vector<double>& c : coeff) mix(c.data(), c.size() * sizeof(double));
+        const double t[3] = {(double)in.ntol_i, (double)in.ntol_d, tau};
+        mix(t, sizeof t);
+        return h;
+    }
     // table build shared by the ranks of a node (Engine::shard_tables): consumed by the next energy_partial
     bool shard_pending = false, prepared = false;
     int shard_rank = 0, shard_nranks = 1;
@@ -1210,8 +1231,10 @@ void Engine::energy_partial(int rank, int nranks, EnergyResult* out)
     out->t_1e = t1 - I.t_begin;
     Wavefunction wf = default_wavefunction(in_);
     I.split_sum = true;
-    try { I.evaluate(in_, wf, nullptr, false, rank, nranks, out, nullptr); } catch (...) { I.split_sum = false; throw; }
+    I.sch_cache_key = 0;
+    try { I.evaluate(in_, wf, nullptr, false, rank, nranks, out, &I.sch_cache); } catch (...) { I.split_sum = false; throw; }
     I.split_sum = false;
+    I.sch_cache_n = wf.nso; I.sch_cache_key = I.state_key(in_);     // default lists: entry s is orbital s
 }
 
 // Table build shared by the ranks of one node.  One process per GPU means N ranks on one host build the same pair
@@ -1314,11 +1337,14 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
             wall = std::max(wall, tmp.wmax);
         }
     }
+    const double tmA = now_ms();
     // ---- all tables of the unsubstituted lists; the free part stays resident ---------------------------------
     TileOpts fo;
     fo.isolate = es; fo.wcut = wall;
-    TileSetup& tsF = ts_fo_keep;     // storage reused across calls, like ts_keep of the energy pass
+    TileSetup& tsF = ts_keep;        // the storage of the energy pass's host tables (already paged in; rebuilt by every evaluation anyway)
     build_tiles(in, bas, wb, orbs2e, tau_diag, true, &tsF, fo);
+    const double tmB = now_ms();
+    if (dbg_time) std::printf("[fo] weight bounds %.1f ms, table build %.1f ms\n", tmA - tm0, tmB - tmA);
     const int nfree = tsF.n_free_pg, npgF = (int)tsF.pgs.size();
     if (nfree == 0) return false;
     const size_t fPairs = tsF.n_free_pairs, fSps = tsF.n_free_sps, fPps = tsF.n_free_pps, fD = tsF.n_free_d;
@@ -1347,16 +1373,11 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     pps_flat.alloc(fPps + room * sPps + 1024);
     dmat.alloc(fD + room * sD + 4096);
     {
-        std::vector<int> v(tsF.pg_pairs.begin(), tsF.pg_pairs.begin() + 2 * fPairs);
-        pg_pairs.upload_at(0, v, st);
-        std::vector<SPRec> v2(tsF.sps.begin(), tsF.sps.begin() + fSps);
-        sps.upload_at(0, v2, st);
-        std::vector<PrimPair> v3(tsF.pps.begin(), tsF.pps.begin() + fPps);
-        pps.upload_at(0, v3, st);
-        std::vector<PrimPair> v4(tsF.pps_flat.begin(), tsF.pps_flat.begin() + fPps);
-        pps_flat.upload_at(0, v4, st);
-        std::vector<double> v5(tsF.dmat.begin(), tsF.dmat.begin() + fD);
-        dmat.upload_at(0, v5, st);
+        pg_pairs.upload_at(0, tsF.pg_pairs.data(), 2 * fPairs, st);
+        sps.upload_at(0, tsF.sps.data(), fSps, st);
+        pps.upload_at(0, tsF.pps.data(), fPps, st);
+        pps_flat.upload_at(0, tsF.pps_flat.data(), fPps, st);
+        dmat.upload_at(0, tsF.dmat.data(), fD, st);
         pgs.upload_at(0, hp, st);
         CK(cudaStreamSynchronize(st));
     }
@@ -1388,7 +1409,9 @@ bool Engine::Impl::first_order_cached(const Input& in, const Wavefunction& wf, i
     for (int x = 0; x < nfree; ++x) if (canon[x] == x) cand.push_back(x);
     std::vector<TilePair> tlc;
     std::vector<std::pair<long long, int>> runs;
+    const double tmC = now_ms();
     make_tile_list(hp, cand, cand, itol, &tlc, &runs);
+    if (dbg_time) std::printf("[fo] uploads + mirror map %.1f ms, tile list %.1f ms\n", tmC - tmB, now_ms() - tmC);
     std::vector<WorkItem> itc;
     long long my_tiles = 0;
     make_items(runs, (long long)tlc.size(), nsm, rank, nranks, &itc, &my_tiles);
@@ -1884,7 +1907,18 @@ int Engine::first_order(int iorb, std::vector<double>* ham, std::vector<double>*
     wf.subject = -1;
     // Schwarz table of the unsubstituted lists (valence.F90:666-667); the (ib,jb) loop reuses it
     std::vector<double> sch;
-    I.evaluate(in, wf, nullptr, true, 0, 1, &acc, &sch);
+    bool sch_cached = I.sch_cache_key != 0 && I.sch_cache_n == nnd0 + ndocc && I.sch_cache_key == I.state_key(in) &&
+                      I.sch_cache.size() == (size_t)I.sch_cache_n * I.sch_cache_n;
+    if (const char* e = std::getenv("VB_FO_SCH_CACHE")) sch_cached = sch_cached && std::atoi(e) != 0;
+    if (sch_cached) {
+        // same geometry, weights and screens as the last guess energy: its Schwarz table, re-indexed by the entries of these lists
+        const int n0 = I.sch_cache_n, n1 = wf.nso;
+        sch.resize((size_t)n1 * n1);
+        for (int a = 0; a < n1; ++a)
+            for (int b = 0; b < n1; ++b) sch[(size_t)a * n1 + b] = I.sch_cache[(size_t)wf.bra[wf.slot(a, 0)] * n0 + wf.bra[wf.slot(b, 0)]];
+    } else {
+        I.evaluate(in, wf, nullptr, true, 0, 1, &acc, &sch);
+    }
     ham->assign((size_t)norbas * norbas, 0.0);
     ovl->assign((size_t)norbas * norbas, 0.0);
     const int npass = (in.nunpd > 0 && iorb >= nnd0) ? 2 : 1;   // spin average, valence.F90:709-749
