@@ -250,6 +250,7 @@ struct Engine::Impl {
     std::vector<double> xyz_angs;
     // device data
     DBuf<FarPrim> fcp, fcpf;
+    DBuf<double> hpart;                              // d-shell tile kernel: per-slice shares of the half-transformed tiles
     DBuf<double> boys, boys_small, gbuf, gred, exps, coefs, nuc, S, H, Se, He, Ma, Mb, Mai, Mbi, gj_ws, gj_res, Pa, Pb, gjout, diag, sch, tileE, accum, one_e, dmat, gen_scratch;
     DBuf<DevShell> shells;
     DBuf<int> optr, oao, piv, ea_bra, ea_ket, eb_bra, eb_ket, posa_bra, posa_ket, posb_bra, posb_ket, pg_pairs, nsh_bra, nsh_ket;
@@ -880,7 +881,7 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     counter.alloc(1); counters.alloc(CNT_N); pq_counters.alloc(NPTYPE * NPTYPE);
     if (!gen) { gred.alloc((size_t)nsm * PT_MAXQ * g_cap); A_gred = gred.p; }
     int grid_cap = nsm;
-    if (gen) { grid_cap = std::min(grid_cap, 64); gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD); }
+    if (gen) gen_scratch.alloc((size_t)grid_cap * TILE_THREADS * GEN_PER_THREAD);      // one CTA per SM (3.3 GB of recurrence scratch on 148 SMs)
     if (gen) CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else {
         CK(cudaFuncSetAttribute(k_ptile<PART_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -900,7 +901,31 @@ void Engine::Impl::evaluate(const Input& in, const Wavefunction& wf, const std::
     A.debug = std::getenv("VB_DEBUG_ENTRIES") ? 1 : 0;
     auto launch = [&](int nwork, int part) {
         int grid = std::max(1, std::min(grid_cap, nwork));
-        if (gen) k_tile<true><<<grid, TILE_THREADS, smem, st>>>(A);
+        if (gen) {
+            // d-shell inputs are small (one transition-metal atom: tens of tiles, each needing every AO quartet of the atom): one CTA
+            // per tile leaves most SMs idle and the pass takes as long as its heaviest tile.  The first half transformation of
+            // every tile is therefore split over `hs` CTAs (static slices of the (class, bra shell pair) units, shares summed in
+            // slice order by the contraction launch: bitwise reproducible, so every rank still derives the same Schwarz table).
+            int hs = std::max(1, std::min(64, (4 * nsm + nwork - 1) / std::max(1, nwork)));
+            if (const char* e = std::getenv("VB_GEN_SPLIT")) hs = std::max(1, std::min(64, std::atoi(e)));
+            // a slice takes every US-th unit and every KS-th batch of 32 ket primitives of it (the heaviest unit -- a dd bra
+            // shell pair against every ket primitive -- is otherwise one warp's work for the whole launch)
+            const int KS = std::min(4, hs), US = std::max(1, hs / KS);
+            hs = US * KS;
+            if (hs > 1) {
+                hpart.alloc((size_t)nwork * hs * hs_cap);
+                A.hsplit = hs; A.hksplit = KS; A.hpart = hpart.p;
+                A.hphase = 1;
+                k_tile<true><<<std::max(1, std::min(grid_cap, nwork * hs)), TILE_THREADS, smem, st>>>(A);
+                CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned int), st));
+                A.hphase = 2;
+                k_tile<true><<<grid, TILE_THREADS, smem, st>>>(A);
+                A.hsplit = 1; A.hksplit = 1; A.hphase = 0;
+                launches++;
+            } else {
+                k_tile<true><<<grid, TILE_THREADS, smem, st>>>(A);
+            }
+        }
         else if (part == PART_HEAVY) k_ptile<PART_HEAVY><<<grid, pt_threads(PART_HEAVY), smem, st>>>(A);
         else if (part == PART_LIGHT) k_ptile<PART_LIGHT><<<grid, pt_threads(PART_LIGHT), smem, st>>>(A);
         else k_ptile<PART_ALL><<<grid, pt_threads(PART_ALL), smem, st>>>(A);

@@ -67,6 +67,12 @@ struct TileArgs {
     const int* nsh_ket;
     double* tileE;                   // mode 1: per-tile energy partial (deterministic reduction later)
     unsigned long long* counters;    // CNT_N
+    // k_tile (d shells): the first half transformation of one tile split over hsplit CTAs.  hphase 1: CTA (tile, slice) takes the
+    // units u = slice (mod hsplit) and leaves its share of the half-transformed tile in hpart[(tile * hsplit + slice) * hs_cap];
+    // hphase 2: one CTA per tile sums the shares in slice order (deterministic) and contracts.  hsplit <= 1: one CTA does both.
+    // A slice is (us, ks) with hsplit = US * hksplit: units u = us (mod US), ket batches b = ks (mod hksplit) of every unit.
+    int hsplit, hphase, hksplit;
+    double* hpart;
     double* gfull;                   // mode 2: dense G over ordered pairs
     const int* pair_index;           // mode 2: (s*nso+t) -> dense pair index, or -1
     int npairs_total;

@@ -282,11 +282,24 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
         __syncthreads();
         if (tid == 0) s_tile = (int)atomicAdd(A.counter, 1u);   // work stealing inside this rank's shard
         __syncthreads();
-        const long long tl = (long long)A.tile_first + (long long)s_tile * A.tile_stride;
+        const int hs = A.hsplit > 1 ? A.hsplit : 1;
+        const long long wloc = A.hphase == 1 ? (long long)s_tile / hs : (long long)s_tile;     // this rank's tile number
+        const int slice = A.hphase == 1 ? (int)((long long)s_tile % hs) : 0;
+        const long long tl = (long long)A.tile_first + wloc * A.tile_stride;
         if (tl >= A.ntiles) break;
         const int2 tq = A.tiles[tl];
         const PGDesc P = A.pgs[tq.x];
         const PGDesc Q = A.pgs[tq.y];
+        if (A.hphase == 2) {
+            // the half-transformed tile = sum of the slices' shares, in slice order
+            const double* __restrict__ hp = A.hpart + (size_t)wloc * hs * A.hs_cap;
+            for (int i = tid; i < P.ne * A.hs_ld; i += TILE_THREADS) {
+                double v = 0.0;
+                for (int k = 0; k < hs; ++k) v += hp[(size_t)k * A.hs_cap + i];
+                Hs[i] = v;
+            }
+            __syncthreads();
+        } else {
         // stage the tile's tables with TMA bulk copies (one elected thread issues, all wait on the mbarrier)
         const int nkpp = Q.pp_beg[NPTYPE] - Q.pp_beg[0], nbpp = P.pp_beg[NPTYPE] - P.pp_beg[0];
         const int nspP = P.sp_beg[NPTYPE] - P.sp_beg[0];
@@ -336,8 +349,10 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
         }
         __syncthreads();
         const int nunits = s_cum[NT * NT];
-        const bool dynamic = A.mode != 0;
-        int ustat = warp;
+        const bool dynamic = A.mode != 0 && A.hphase != 1;
+        const int KS = (A.hphase == 1 && A.hksplit > 1) ? A.hksplit : 1, US = hs / KS;      // slice = (us, ks)
+        const int us = slice % US, ks = slice / US;
+        int ustat = us + warp * US;
         for (;;) {
             int u;
             if (dynamic) {
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
                 u = __shfl_sync(0xffffffffu, u, 0);
             } else {
                 u = ustat;
-                ustat += nw;
+                ustat += nw * US;
             }
             if (u >= nunits) break;
             int c = 0;
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
 #pragma unroll
             for (int e = 0; e < HM; ++e) H[e] = 0.0;
             unsigned long long npq = 0ull;
-            for (int base = 0; base < nket; base += 32) {
+            for (int base = 32 * ks; base < nket; base += 32 * KS) {
                 // ket shell pairs are sorted by weight: once a batch is negligible, so are the rest
                 if (!(sp.wmax * kpp[base].wseg >= A.tau)) break;
                 switch (cls) {
@@ -392,6 +407,12 @@ __global__ void __launch_bounds__(TILE_THREADS, GEN ? 1 : VB_MINBLOCKS) k_tile(c
             }
         }
         __syncthreads();
+        if (A.hphase == 1) {
+            double* __restrict__ hp = A.hpart + ((size_t)wloc * hs + slice) * A.hs_cap;
+            for (int i = tid; i < P.ne * A.hs_ld; i += TILE_THREADS) hp[i] = Hs[i];
+            continue;
+        }
+        }   // hphase != 2
 
         // ---- contraction with the cofactor densities --------------------------------------
         double epart = 0.0;
