@@ -19,7 +19,7 @@ int main()
     std::uniform_real_distribution<double> U(-9.0, 1.0);
     for (int npg : {1, 7, 300, 2500}) {
         std::vector<PGDesc> pgs(npg);
-        for (PGDesc& p : pgs) { std::memset(&p, 0, sizeof p); p.smax = std::pow(10.0, U(rng)); }
+        for (PGDesc& p : pgs) { std::memset(&p, 0, sizeof p); p.smax = std::pow(10.0, U(rng)); p.pp_beg[NPTYPE] = 1 + (int)(rng() % 400); }
         const double itol = 1e-10;
         std::vector<int> all(npg), odd, even;
         for (int i = 0; i < npg; ++i) { all[i] = i; (i % 2 ? odd : even).push_back(i); }
@@ -70,6 +70,29 @@ int main()
                 }
                 if (total != (long long)t1.size() || std::any_of(owner.begin(), owner.end(), [](int c) { return c != 1; })) {
                     std::printf("ranks do not partition the tile list (npg %d, %d ranks)\n", npg, nranks); ++bad;
+                }
+            }
+            // rank-owned bra blocks (the form the energy pass uses): the ranks' lists are disjoint, their union is the full list,
+            // and the cost-based deal of the blocks balances the estimated work (primitive pairs x partners' primitive pairs)
+            for (int nranks : {2, 3, 8}) {
+                std::set<std::pair<int, int>> uni;
+                size_t total = 0;
+                std::vector<double> load(nranks, 0.0);
+                for (int rank = 0; rank < nranks; ++rank) {
+                    std::vector<TilePair> tr;
+                    std::vector<std::pair<long long, int>> rr;
+                    make_tile_list(pgs, *cs.a, *cs.b, itol, &tr, &rr, rank, nranks);
+                    total += tr.size();
+                    for (const TilePair& t : tr) {
+                        uni.insert({t.x, t.y});
+                        load[rank] += (double)std::max(1, pgs[t.x].pp_beg[NPTYPE]) * (double)std::max(1, pgs[t.y].pp_beg[NPTYPE]);
+                    }
+                }
+                if (total != t1.size() || uni.size() != t1.size()) { std::printf("rank-owned blocks do not partition the tile list (npg %d, %d ranks)\n", npg, nranks); ++bad; }
+                if (npg >= 2500 && cs.a == &all) {
+                    double mx = 0.0, sum = 0.0;
+                    for (double l : load) { mx = std::max(mx, l); sum += l; }
+                    if (mx > 1.10 * sum / nranks) { std::printf("rank loads out of balance: max %.3g mean %.3g (%d ranks)\n", mx, sum / nranks, nranks); ++bad; }
                 }
             }
         }

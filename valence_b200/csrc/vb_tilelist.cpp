@@ -23,7 +23,6 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
     int PB = nranks > 1 ? 32 : 128;       // 8 x B200, (H2O)_256: tile pass 586 ms with blocks of 64, 550 with 32, 548 with 16, 582 with 8
     if (const char* e = std::getenv("VB_TILE_PB")) PB = std::max(1, std::atoi(e));
     const int QC = 1024;
-    auto owner = [&](int blk) { const int k = blk % nranks; return ((blk / nranks) & 1) ? nranks - 1 - k : k; };
     const int na = (int)avec.size(), nb = (int)bvec.size();
     const int nchunks = (nb + QC - 1) / QC;
     std::vector<int> order(bvec);
@@ -33,6 +32,57 @@ void make_tile_list(const std::vector<PGDesc>& pgs, const std::vector<int>& avec
         std::stable_sort(order.begin() + (size_t)c * QC, order.begin() + std::min<size_t>(nb, (size_t)(c + 1) * QC),
                          [&](int x, int y) { return pgs[x].smax > pgs[y].smax; });
     }
+    const int nblocks_all = (na + PB - 1) / PB;
+    // Owner of every bra block.  One rank: trivial.  Several: the blocks are dealt by estimated cost, heaviest first, each to the
+    // rank with the least work so far (every rank computes the same deal from the same descriptors).  Cost of pair group a =
+    // (its primitive pairs) x (primitive pairs of the partners that pass the Schwarz bound), the partners counted per ket chunk by a
+    // binary search in the chunk's sorted bounds (the chunk that contains a itself pro rata).  A plain snake deal of the blocks left
+    // the 8-GPU tile pass of (H2O)_256 8 % above 1/8 of the single-GPU pass.
+    std::vector<int> owner_of(nblocks_all, 0);
+    if (nranks > 1) {
+        auto npp = [&](int x) { return (double)std::max(1, pgs[x].pp_beg[NPTYPE] - pgs[x].pp_beg[0]); };
+        std::vector<double> pf((size_t)nb + nchunks + 1, 0.0);     // per chunk: prefix sums of the partners' primitive pairs in sorted order
+        std::vector<size_t> pf0(nchunks);
+        for (int c = 0, o = 0; c < nchunks; ++c) {
+            const int c0 = c * QC, c1 = std::min(nb, c0 + QC);
+            pf0[c] = (size_t)o;
+            pf[o++] = 0.0;
+            for (int j = c0; j < c1; ++j, ++o) pf[o] = pf[o - 1] + npp(order[j]);
+        }
+        std::vector<double> bcost(nblocks_all, 0.0);
+        for (int blk = 0; blk < nblocks_all; ++blk) {
+            const int B0 = blk * PB, B1 = std::min(na, B0 + PB);
+            double cost = 0.0;
+            for (int ai = B0; ai < B1; ++ai) {
+                const int a = avec[ai];
+                const double sa = pgs[a].smax;
+                if (!(sa > 0.0)) continue;
+                double part = 0.0;
+                for (int c = 0; c < nchunks; ++c) {
+                    if (cmin[c] > a) break;
+                    const int c0 = c * QC, c1 = std::min(nb, c0 + QC);
+                    int lo = c0, hi = c1;                      // first j with sa * smax <= itol
+                    while (lo < hi) { const int mid = (lo + hi) / 2; if (sa * pgs[order[mid]].smax > itol) lo = mid + 1; else hi = mid; }
+                    double w = pf[pf0[c] + (size_t)(lo - c0)];
+                    if (bvec[c1 - 1] > a) w *= (double)(a - cmin[c] + 1) / (double)(bvec[c1 - 1] - cmin[c] + 1);   // a's own chunk
+                    part += w;
+                }
+                cost += npp(a) * part;
+            }
+            bcost[blk] = cost;
+        }
+        std::vector<int> byc(nblocks_all);
+        for (int i = 0; i < nblocks_all; ++i) byc[i] = i;
+        std::stable_sort(byc.begin(), byc.end(), [&](int x, int y) { return bcost[x] > bcost[y]; });
+        std::vector<double> load(nranks, 0.0);
+        for (int blk : byc) {
+            int best = 0;
+            for (int r = 1; r < nranks; ++r) if (load[r] < load[best]) best = r;
+            owner_of[blk] = best;
+            load[best] += bcost[blk];
+        }
+    }
+    auto owner = [&](int blk) { return owner_of[blk]; };
     // one bra block per task on the host cores; the blocks are concatenated in order, so the list does not depend on
     // the thread count
     const int nblocks = (na + PB - 1) / PB;
