@@ -61,6 +61,54 @@ int main(int argc, char** argv)
         for (int t = 0; t < NPTYPE; ++t)
             for (int k = pg.sp_beg[t] + 1; k < pg.sp_beg[t + 1]; ++k)
                 if (a.sps[k].pp_cnt > a.sps[k - 1].pp_cnt) { std::printf("shell pairs not sorted by length\n"); ++bad; }
+    // P = A + (P - A) holds exactly as stored (P - A is formed from the difference of the centres, vb_setup.cpp), and the folded
+    // density rows of ss / ps shell pairs are outer products over the pair list, D[e][(s,t)] = u_e[s] v_e[t] (every 2 x 2 minor
+    // vanishes): the fact the one-index-at-a-time transforms of DESIGN.md "Next" rest on.  pp rows (HRR-folded d components
+    // mix both centres) are counted, not required.
+    {
+        long long rows = 0, rank1 = 0, pp_rows = 0, pp_rank1 = 0;
+        for (const PGDesc& pg : a.pgs) {
+            if (pg.np <= 0) continue;
+            for (int k = pg.sp_beg[0]; k < pg.sp_beg[NPTYPE]; ++k) {
+                const SPRec& sp = a.sps[k];
+                for (int e = 0; e < pt_ne(sp.type); ++e) {
+                    const double* row = a.dmat.data() + pg.d_off + (size_t)(sp.eoff + e) * pg.np;
+                    double mx = 0.0;
+                    for (int p = 0; p < pg.np; ++p) mx = std::fmax(mx, std::fabs(row[p]));
+                    if (mx == 0.0) continue;
+                    bool ok = true;
+                    for (int p = 0; p < pg.np && ok; ++p)
+                        for (int q = 0; q < p && ok; ++q) {
+                            const int s1 = a.pg_pairs[2 * (pg.pair_beg + p)], t1 = a.pg_pairs[2 * (pg.pair_beg + p) + 1];
+                            const int s2 = a.pg_pairs[2 * (pg.pair_beg + q)], t2 = a.pg_pairs[2 * (pg.pair_beg + q) + 1];
+                            if (s1 == s2 || t1 == t2) continue;
+                            // the two crossed pairs (s1,t2), (s2,t1), if the group holds them
+                            int pc = -1, qc = -1;
+                            for (int r = 0; r < pg.np; ++r) {
+                                const int sr = a.pg_pairs[2 * (pg.pair_beg + r)], tr = a.pg_pairs[2 * (pg.pair_beg + r) + 1];
+                                if (sr == s1 && tr == t2) pc = r;
+                                if (sr == s2 && tr == t1) qc = r;
+                            }
+                            if (pc < 0 || qc < 0) continue;
+                            if (std::fabs(row[p] * row[q] - row[pc] * row[qc]) > 1e-13 * mx * mx) ok = false;
+                        }
+                    if (sp.type <= 1) { ++rows; rank1 += ok; } else { ++pp_rows; pp_rank1 += ok; }
+                }
+            }
+        }
+        std::printf("folded density rows: ss/ps %lld, outer products %lld; pp %lld, outer products %lld\n", rows, rank1, pp_rows, pp_rank1);
+        if (rows == 0 || rank1 != rows) { std::printf("ss / ps density rows are not outer products over the pair list\n"); ++bad; }
+        for (const PrimPair& pp : a.pps) {
+            // A = P - (P - A) must be one of the atom centres to rounding (1e-12 bohr is four orders above the rounding of a 40 bohr coordinate)
+            bool hit = false;
+            for (int at = 0; at < in.natom && !hit; ++at) {
+                const double dx = pp.Px - pp.PAx - in.coords[3 * at] * ANGS2BOHR, dy = pp.Py - pp.PAy - in.coords[3 * at + 1] * ANGS2BOHR,
+                             dz = pp.Pz - pp.PAz - in.coords[3 * at + 2] * ANGS2BOHR;
+                hit = std::fabs(dx) < 1e-12 && std::fabs(dy) < 1e-12 && std::fabs(dz) < 1e-12;
+            }
+            if (!hit) { std::printf("P - (P - A) is not an atom centre\n"); ++bad; break; }
+        }
+    }
     // first_order_opt's integral cache (TileOpts): with one entry isolated the pair groups touching it come last, the
     // "subject only" build reproduces exactly that tail (offsets relative), and the free part mirrors under (g,h)<->(h,g)
     {
