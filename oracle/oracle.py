@@ -128,7 +128,7 @@ class Oracle:
         r = FastResult()
         rc = self.L.vo_fast_guess_energy(self.h, nthreads, thr, C.byref(r))
         if rc != 0:
-            raise RuntimeError("fast oracle: input outside its limits (spin-coupled pairs or singular overlap block)")
+            raise RuntimeError("fast oracle: input outside its limits (singular overlap block, more than 12 spin-coupled pairs)")
         return {"enucrep": r.enucrep, "energy": r.energy, "wfnorm": r.wfnorm, "numerator": r.numerator,
                 "counters": r.cnt.asdict(), "prim_quartets": int(r.prim_quartets), "seconds": r.seconds}
 

@@ -21,7 +21,8 @@
  * No code is shared with valence_b200/ (the product uses Obara-Saika recurrences on the GPU).
  * Validation: tests/test_oracle_fast.py compares this path with the literal one above on every input
  * the literal one finishes (energies to 1e-11, counters exactly).
- * Limits: npair == 0 (no spin-coupled pairs), l <= 2, non-singular overlap blocks.
+ * Spin-coupled wavefunctions (npair > 0): one inverse pair per determinant pair, f_cofactors_sc.
+ * Limits: l <= 2, non-singular overlap blocks; first_order matrices for npair == 0 only.
  */
 #include <pthread.h>
 #include <unistd.h>
@@ -188,6 +189,9 @@ typedef struct {
 typedef struct { int g, h, np; int *ps, *pt; int nsp; f_sp *sp; double smax; } f_pg;
 typedef struct { int n; int *e; int nshB, nshK; int *shB, *shK; double *cB, *cK; /* [entry][shell][6] */ } f_grp;
 
+/* cofactor data of one determinant pair of a spin-coupled wavefunction: weight = c_isc c_jsc det(alpha block) det(beta block) */
+struct f_dp_s { int *posa_b, *posa_k, *posb_b, *posb_k; double *Ai, *Bi; double wt; };
+
 typedef struct {
     vo_ctx *c;
     int nsh, nao; f_shell *sh; int *atom_first;
@@ -198,6 +202,7 @@ typedef struct {
     double *S, *H;                               /* AO level */
     int na, nb; int *posa_b, *posa_k, *posb_b, *posb_k;   /* spin-orbital -> position in alpha / beta lists (1-based, 0 = absent) */
     double *Ai, *Bi; double c0, la_det, lb_det;  /* inverses (row = ket position, col = bra position), det product */
+    int ndp; struct f_dp_s *dp;                  /* spin-coupled wavefunctions: one record per determinant pair (then c0 = 1) */
     int ngrp; f_grp *grp; int *grp_of;
     int npg; f_pg *pg; int *pg_of;               /* pg_of[g * ngrp + h] */
     double thr;
@@ -462,26 +467,102 @@ static int f_cofactors(f_ctx *F)
 
 /* Minv[ket position][bra position] of the alpha / beta block; the inverse of M (rows bra, cols ket) is indexed
  * [ket][bra], and f_invert returns M^-1 row-major, i.e. Minv[k][r] */
-#define F_AI(F, k, r) ((F)->Ai[(size_t)((k) - 1) * (F)->na + ((r) - 1)])
-#define F_BI(F, k, r) ((F)->Bi[(size_t)((k) - 1) * (F)->nb + ((r) - 1)])
 
 /* first-order cofactor / c0 of bra spin-orbital i -> ket spin-orbital k (0 when the spins differ) */
-static double f_c1(const f_ctx *F, int i, int k)
+static double f_c1_one(int na, int nb, const int *posa_b, const int *posa_k, const int *posb_b, const int *posb_k, const double *Ai, const double *Bi, int i, int k)
 {
-    if (F->posa_b[i] && F->posa_k[k]) return F_AI(F, F->posa_k[k], F->posa_b[i]);
-    if (F->posb_b[i] && F->posb_k[k]) return F_BI(F, F->posb_k[k], F->posb_b[i]);
+    if (posa_b[i] && posa_k[k]) return Ai[(size_t)(posa_k[k] - 1) * na + (posa_b[i] - 1)];
+    if (posb_b[i] && posb_k[k]) return Bi[(size_t)(posb_k[k] - 1) * nb + (posb_b[i] - 1)];
     return 0.0;
 }
 /* second-order cofactor / c0 for the pairings i -> k, j -> l (det(), valence.F90:1895-2056, in inverse form) */
+static double f_c2_one(int na, int nb, const int *posa_b, const int *posa_k, const int *posb_b, const int *posb_k, const double *Ai, const double *Bi,
+                       int i, int k, int j, int l)
+{
+#define A_(kk, rr) Ai[(size_t)((kk) - 1) * na + ((rr) - 1)]
+#define B_(kk, rr) Bi[(size_t)((kk) - 1) * nb + ((rr) - 1)]
+    int ia = posa_b[i] && posa_k[k], ib = posb_b[i] && posb_k[k];
+    int ja = posa_b[j] && posa_k[l], jb = posb_b[j] && posb_k[l];
+    if (!(ia || ib) || !(ja || jb)) return 0.0;
+    if (ia && ja) {
+        /* same spin: the crossed pairing needs i -> l and j -> k in the alpha lists as well (always true there) */
+        return A_(posa_k[k], posa_b[i]) * A_(posa_k[l], posa_b[j]) - A_(posa_k[l], posa_b[i]) * A_(posa_k[k], posa_b[j]);
+    }
+    if (ib && jb) return B_(posb_k[k], posb_b[i]) * B_(posb_k[l], posb_b[j]) - B_(posb_k[l], posb_b[i]) * B_(posb_k[k], posb_b[j]);
+    if (ia && jb) return A_(posa_k[k], posa_b[i]) * B_(posb_k[l], posb_b[j]);
+    return B_(posb_k[k], posb_b[i]) * A_(posa_k[l], posa_b[j]);
+#undef A_
+#undef B_
+}
+static double f_c1(const f_ctx *F, int i, int k)
+{
+    if (!F->ndp) return f_c1_one(F->na, F->nb, F->posa_b, F->posa_k, F->posb_b, F->posb_k, F->Ai, F->Bi, i, k);
+    long double s = 0.0L;
+    for (int d = 0; d < F->ndp; ++d) {
+        const struct f_dp_s *D = &F->dp[d];
+        s += (long double)D->wt * f_c1_one(F->na, F->nb, D->posa_b, D->posa_k, D->posb_b, D->posb_k, D->Ai, D->Bi, i, k);
+    }
+    return (double)s;
+}
 static double f_c2(const f_ctx *F, int i, int k, int j, int l)
 {
-    int ia = F->posa_b[i] && F->posa_k[k], ib = F->posb_b[i] && F->posb_k[k];
-    int ja = F->posa_b[j] && F->posa_k[l], jb = F->posb_b[j] && F->posb_k[l];
-    if (!(ia || ib) || !(ja || jb)) return 0.0;
-    if (ia && ja) return F_AI(F, F->posa_k[k], F->posa_b[i]) * F_AI(F, F->posa_k[l], F->posa_b[j]) - F_AI(F, F->posa_k[l], F->posa_b[i]) * F_AI(F, F->posa_k[k], F->posa_b[j]);
-    if (ib && jb) return F_BI(F, F->posb_k[k], F->posb_b[i]) * F_BI(F, F->posb_k[l], F->posb_b[j]) - F_BI(F, F->posb_k[l], F->posb_b[i]) * F_BI(F, F->posb_k[k], F->posb_b[j]);
-    if (ia && jb) return F_AI(F, F->posa_k[k], F->posa_b[i]) * F_BI(F, F->posb_k[l], F->posb_b[j]);
-    return F_BI(F, F->posb_k[k], F->posb_b[i]) * F_AI(F, F->posa_k[l], F->posa_b[j]);
+    if (!F->ndp) return f_c2_one(F->na, F->nb, F->posa_b, F->posa_k, F->posb_b, F->posb_k, F->Ai, F->Bi, i, k, j, l);
+    long double s = 0.0L;
+    for (int d = 0; d < F->ndp; ++d) {
+        const struct f_dp_s *D = &F->dp[d];
+        s += (long double)D->wt * f_c2_one(F->na, F->nb, D->posa_b, D->posa_k, D->posb_b, D->posb_k, D->Ai, D->Bi, i, k, j, l);
+    }
+    return (double)s;
+}
+
+/* Spin-coupled wavefunctions (npair > 0): every determinant pair of density_sc / dbra / dket (valence.F90:1612-1870) -- bra coupling
+ * isc x ket coupling jsc x every subset of pairs with alpha and beta exchanged in the bra x every such subset in the ket -- with its
+ * own alpha / beta blocks (rows = bra spin-orbitals, columns = ket spin-orbitals, build_abket :2524-2586), inverted in extended
+ * precision, weight coeff_sc(isc) coeff_sc(jsc) det(A) det(B) (density(), :1576-1588).  c0 = 1 in this mode. */
+static int f_cofactors_sc(f_ctx *F)
+{
+    vo_ctx *c = F->c;
+    const int npair = c->npair, nsc = c->nspinc, ne = c->nelec;
+    if (nsc < 1 || npair > 12) return 0;
+    set_up_unpaired_docc(c);           /* positions npair+1.. of bra_a / ket_a / bra_b / ket_b: unpaired, DOCC alpha / DOCC beta */
+    const int na = npair + c->nunpd + c->ndocc, nb = npair + c->ndocc;
+    F->na = na; F->nb = nb;
+    const long long nmask = 1LL << npair;
+    F->ndp = 0;
+    F->dp = (struct f_dp_s *)xcalloc((size_t)(nsc * nsc * nmask * nmask) + 1, sizeof(struct f_dp_s));
+    double *A = (double *)xcalloc((size_t)na * na + 1, sizeof(double)), *B = (double *)xcalloc((size_t)nb * nb + 1, sizeof(double));
+    int ok = 1;
+    for (int isc = 1; isc <= nsc && ok; ++isc)
+        for (int jsc = 1; jsc <= nsc && ok; ++jsc)
+            for (long long bm = 0; bm < nmask && ok; ++bm)
+                for (long long km = 0; km < nmask && ok; ++km) {
+                    for (int k = 1; k <= npair; ++k) {
+                        int b1 = PAIRSC(c, k, 1, isc), b2 = PAIRSC(c, k, 2, isc), k1 = PAIRSC(c, k, 1, jsc), k2 = PAIRSC(c, k, 2, jsc);
+                        if ((bm >> (k - 1)) & 1) { int t = b1; b1 = b2; b2 = t; }
+                        if ((km >> (k - 1)) & 1) { int t = k1; k1 = k2; k2 = t; }
+                        c->bra_a[k] = b1; c->bra_b[k] = b2; c->ket_a[k] = k1; c->ket_b[k] = k2;
+                    }
+                    struct f_dp_s *D = &F->dp[F->ndp];
+                    D->posa_b = IARR(ne); D->posa_k = IARR(ne); D->posb_b = IARR(ne); D->posb_k = IARR(ne);
+                    for (int i = 1; i <= na; ++i) { D->posa_b[c->bra_a[i]] = i; D->posa_k[c->ket_a[i]] = i; }
+                    for (int i = 1; i <= nb; ++i) { D->posb_b[c->bra_b[i]] = i; D->posb_k[c->ket_b[i]] = i; }
+                    for (int r = 1; r <= na; ++r)
+                        for (int k = 1; k <= na; ++k)
+                            A[(size_t)(r - 1) * na + (k - 1)] = F->Se[(size_t)(f_entry_of_slot(F, c->bra_a[r]) - 1) * F->nso + (f_entry_of_slot(F, c->ket_a[k]) - 1)];
+                    for (int r = 1; r <= nb; ++r)
+                        for (int k = 1; k <= nb; ++k)
+                            B[(size_t)(r - 1) * nb + (k - 1)] = F->Se[(size_t)(f_entry_of_slot(F, c->bra_b[r]) - 1) * F->nso + (f_entry_of_slot(F, c->ket_b[k]) - 1)];
+                    D->Ai = (double *)xcalloc((size_t)na * na + 1, sizeof(double)); D->Bi = (double *)xcalloc((size_t)nb * nb + 1, sizeof(double));
+                    double da = 1.0, db = 1.0, ra = 1.0, rb = 1.0;
+                    if (na > 0) ok = ok && f_invert(na, A, D->Ai, &da, &ra);
+                    if (nb > 0) ok = ok && f_invert(nb, B, D->Bi, &db, &rb);
+                    if (!ok || ra < 1e-12 || rb < 1e-12) ok = 0;
+                    D->wt = c->coeff_sc[isc] * c->coeff_sc[jsc] * da * db;
+                    ++F->ndp;
+                }
+    free(A); free(B);
+    F->c0 = 1.0; F->la_det = F->lb_det = 1.0;
+    return ok;
 }
 
 /* ---- entry groups, pair groups, shell-pair tables ---------------------------------------------------- */
@@ -937,6 +1018,10 @@ static void f_release_lists(f_ctx *F)
     free(F->Se); free(F->He); F->Se = F->He = NULL;
     free(F->posa_b); free(F->posa_k); free(F->posb_b); free(F->posb_k); F->posa_b = F->posa_k = F->posb_b = F->posb_k = NULL;
     free(F->Ai); free(F->Bi); F->Ai = F->Bi = NULL;
+    if (F->dp) {
+        for (int d = 0; d < F->ndp; ++d) { free(F->dp[d].posa_b); free(F->dp[d].posa_k); free(F->dp[d].posb_b); free(F->dp[d].posb_k); free(F->dp[d].Ai); free(F->dp[d].Bi); }
+        free(F->dp); F->dp = NULL; F->ndp = 0;
+    }
     free(F->eB); free(F->eK); F->eB = F->eK = NULL;
 }
 
@@ -1062,7 +1147,7 @@ static void f_blk_one(void *ctx, long long k, int tid)
 static int f_vsvb_energy(f_ctx *F, double *energy_out, double *wfnorm_out, long long *npq_out)
 {
     vo_ctx *c = F->c;
-    if (!f_cofactors(F)) return -1;
+    if (!(c->npair > 0 ? f_cofactors_sc(F) : f_cofactors(F))) return -1;
     const int nnd = F->nnd, nelec = c->nelec, nso = F->nso;
     /* 1e part (:1072-1106) */
     long double e1 = 0.0L, wn = 0.0L;
@@ -1119,7 +1204,6 @@ typedef struct { double enucrep, energy, wfnorm, numerator; vo_counters cnt; lon
 int vo_fast_guess_energy(vo_ctx *c, int nthreads, double thr, vo_fast_result *out)
 {
     memset(out, 0, sizeof *out);
-    if (c->npair > 0) return -1;
     f_nthreads = nthreads;
     f_xacc = getenv("VO_FAST_XACC") != NULL && atoi(getenv("VO_FAST_XACC")) != 0;
     double t0 = mono_now();

@@ -25,7 +25,7 @@ def _make(case):
     return m.CASES[base](), (m.FO_CASES[case][1] if case in m.FO_CASES else None)
 
 
-ENERGY_CASES = [c for c in fast_fixture_names() if "_fo" not in c]
+ENERGY_CASES = [c for c in fast_fixture_names() if "_fo" not in c and "sc" not in c]     # spin-coupled fixtures: test_gpu_parity.py
 FO_CASES = [c for c in fast_fixture_names() if "_fo" in c]
 
 

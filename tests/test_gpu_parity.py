@@ -586,3 +586,21 @@ def test_translation_invariance_on_32_waters(write_input):
     # = 1.8e-12 at 128 molecules, profiles/r2_translation_invariance.log); round 1 needed 5e-9 here
     assert abs(r1["energy"] - r0["energy"]) < 2e-11
     assert abs(r1["enucrep"] - r0["enucrep"]) < 1e-11
+
+
+@pytest.mark.parametrize("case,n", [("w16sc2", 16), ("w32sc2", 32)])
+def test_spin_coupled_clusters_match_fast_oracle_fixture(case, n, write_input):
+    """Config 5's spin-coupled variant at scale, pinned independently: (H2O)_16 / (H2O)_32 with the OH bonds of the first two molecules
+    as spin-coupled pairs (npair 4, 256 determinant pairs, spin blocks of 80 / 160 inverted on the GPU per pair) against the fast CPU
+    oracle's committed result (oracle/vo_fast.c: f_cofactors_sc, validated against the literal restatement in
+    tests/test_oracle_fast.py; tests/golden/fast__w*sc2.json)."""
+    from conftest import fast_fixture
+    from valence_b200 import api, inputs
+    fx = fast_fixture(case)
+    path, _ = write_input(inputs.water_cluster(n, tol=(10, 20, 10), sc_molecules=2), case + ".inp")
+    eng = api.Engine(path)
+    r = eng.energy()
+    eng.close()
+    assert abs(r["energy"] - fx["energy"]) < 1e-10, (r["energy"], fx["energy"])
+    assert abs(r["wfnorm"] / fx["wfnorm"] - 1.0) < 1e-10
+
