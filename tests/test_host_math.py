@@ -55,3 +55,86 @@ def test_far_field_segment_form_against_the_recurrence(tmp_path):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "host", "test_far_host.cpp")])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def _input_tokens(inp):
+    """The token line tests/host/test_input_host.cpp prints, from the Python data model."""
+    t = [inp.natom, inp.natom_t, inp.npair, inp.nunpd, inp.ndocc, inp.totlen, inp.xpmax, inp.nspinc, inp.num_sh, inp.num_pr, inp.nang,
+         inp.ndf, inp.nset, inp.nxorb, inp.mxctr, inp.ntol_c, inp.ntol_d, inp.ntol_i, inp.ntol_e_min, inp.ntol_e_max, inp.max_iter,
+         inp.ptbnmax, inp.feather, 2 * len(inp.orbset)]
+    t += [v for pr in inp.orbset for v in pr]
+    t += list(inp.atom_t)
+    t += [x for c in inp.coords for x in c]
+    for ty in inp.types:
+        t += [ty.charge, len(ty.shells)]
+        for s in ty.shells:
+            t += [s.l, len(s.exps)]
+            for e, c in zip(s.exps, s.coefs):
+                t += [e, c]
+    t += [len(inp.coeff_sc)] + list(inp.coeff_sc)
+    flat = [v for cpl in inp.pair_sc for pr in cpl for v in pr]
+    t += [len(flat)] + flat
+    t += [2 * len(inp.xorb)] + [v for pr in inp.xorb for v in pr]
+    t += [len(inp.orbitals)]
+    for o in inp.orbitals:
+        t += [len(o.atoms)] + list(o.atoms) + [len(o.terms)]
+        for xp, c in o.terms:
+            t += [xp, c]
+    nelec = 2 * inp.npair + 2 * inp.ndocc + inp.nunpd
+    t += [nelec, 2 * inp.npair + inp.ndocc + inp.nunpd + inp.ndf, inp.npair + inp.nunpd + inp.ndocc, inp.npair + inp.ndocc,
+          2 * inp.npair + inp.nunpd]
+    return t
+
+
+def test_input_reader_reads_every_reference_input_like_the_data_model(tmp_path):
+    """vb_input.cpp on the CPU: all reference inputs of tests/golden (examples/ and testing/ of the reference, written back by
+    inputs.write) and the synthetic generators parse to exactly the values of the Python data model, value by value; truncated
+    files are refused with an error, not read short (xm_module.F90:41-287 stops on a short read)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import golden_names, load_golden
+    from valence_b200 import inputs
+    cases = [(n, load_golden(n)[0]) for n in golden_names()]
+    cases += [("w3sc", inputs.water_cluster(3, sc_molecules=1)), ("lif", inputs.lif_cluster(2, 2, 2)), ("c4h10", inputs.alkane(4))]
+    paths = []
+    for n, inp in cases:
+        p = tmp_path / (n + ".inp")
+        p.write_text(inputs.write(inp))
+        paths.append(str(p))
+    text = inputs.write(cases[0][1])
+    for k, frac in enumerate((0.3, 0.6, 0.9)):
+        p = tmp_path / f"cut{k}.inp"
+        p.write_text(text[:int(len(text) * frac)])
+        paths.append(str(p))
+    exe = tmp_path / "test_input"
+    csrc = os.path.join(ROOT, "valence_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", csrc, "-o", str(exe), os.path.join(ROOT, "tests", "host", "test_input_host.cpp"),
+                           os.path.join(csrc, "vb_input.cpp")])
+    out = subprocess.run([str(exe)] + paths, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr
+    lines = out.stdout.splitlines()
+    assert len(lines) == len(paths)
+    for (n, inp), line in zip(cases, lines):
+        tok = line.split()
+        assert tok[0] == "OK", (n, line[:200])
+        want = _input_tokens(inp)
+        assert len(tok) - 1 == len(want), (n, len(tok) - 1, len(want))
+        for k, (a, b) in enumerate(zip(tok[1:], want)):
+            assert float(a) == float(b), (n, k, a, b)
+    for line in lines[len(cases):]:
+        assert line.startswith("ERROR"), line[:200]
+
+
+def test_packed_cofactor_sets_against_determinants_of_minors(tmp_path):
+    """vb_cofactor.cpp on the CPU: for closed-shell, open-shell and spin-coupled wavefunctions (up to 576 determinant pairs, three
+    couplings) the packed data of every determinant pair reproduces det M and its first and second derivatives with respect to the
+    matrix elements -- LU determinants of the explicit minors -- to 1e-13 of the block's scale, including blocks with a one- or
+    two-dimensional null space (where the reference's Givens determinants are finite and an inverse is not) and rank deficit 3
+    (everything vanishes); weights c_i c_j; the one-electron numerator and the norm; the single-coupling-pair mode of spin_opt."""
+    exe = tmp_path / "test_cofactor"
+    csrc = os.path.join(ROOT, "valence_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", csrc, "-o", str(exe), os.path.join(ROOT, "tests", "host", "test_cofactor_host.cpp"),
+                           os.path.join(csrc, "vb_cofactor.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-3000:] + out.stderr
