@@ -206,6 +206,9 @@ def run_ours(args) -> None:
 
     R = dist.ReduceOp if world > 1 else None
     MAX, SUM = (R.MAX, R.SUM) if R else (None, None)
+    # job-unique part of the library's NCCL rendezvous keys: rank 0's pid and start time, agreed through the all-reduce
+    comm_seq = [0]
+    job_token = "%d_%d" % (int(red(float(os.getpid()) if rank == 0 else 0.0, SUM)), int(red(float(int(time.time())) if rank == 0 else 0.0, SUM)))
     peak = api.measure_fp64_peak(local)
 
     def measure(name, steps, warmup, sample_clocks):
@@ -213,7 +216,9 @@ def run_ours(args) -> None:
         path, inp, desc, case = make_input(name)
         eng = api.Engine(path, device=local)
         if world > 1:
-            eng.attach_comm(rank, world)                 # NCCL inside the library: energy() is collective from here on
+            # NCCL inside the library: energy() is collective from here on.  One rendezvous key per engine and job.
+            comm_seq[0] += 1
+            eng.attach_comm(rank, world, f"bench{job_token}_{comm_seq[0]}")
         x_host = torch.tensor(inp.coords, dtype=torch.float64).flatten().pin_memory()
         sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
         if sampler:

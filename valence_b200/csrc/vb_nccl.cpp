@@ -4,6 +4,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -89,7 +90,10 @@ Comm::Comm(int rank, int nranks, const std::string& key) : rank_(rank), nranks_(
 {
     if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("valence_b200: bad rank / size");
     Api& a = api();
-    id_file_ = "/dev/shm/valence_b200_nccl_" + key;
+    // One rendezvous file per communicator of the process: the ranks of a job create their communicators in the same order, so a
+    // rank that runs ahead can never pick up the record of the previous communicator (which stays until rank 0 has closed it).
+    static std::atomic<unsigned> n_created{0};
+    id_file_ = "/dev/shm/valence_b200_nccl_" + key + "." + std::to_string(n_created.fetch_add(1));
     UniqueId id;
     std::memset(&id, 0, sizeof id);
     struct Rec { long long stamp; UniqueId id; } rec;
