@@ -406,8 +406,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("VB_BENCH_WORKLOAD", "w256"))
     ap.add_argument("--waters", type=int, default=0, help="shorthand for --workload w<N>")
-    ap.add_argument("--sweep", default=os.environ.get("VB_BENCH_SWEEP", "16,32,64,128"),
-                    help="cluster sizes of the scaling sweep reported in `sweep` ('' = none)")
+    ap.add_argument("--sweep", default=os.environ.get("VB_BENCH_SWEEP"),
+                    help="cluster sizes of the scaling sweep reported in `sweep` ('' = none); default 16,32,64,128 on one GPU, none on "
+                         "several (the sweep and the other stated configurations are single-GPU lines; the N-GPU line is the headline workload)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-grad", action="store_true", help="skip metric 2 (energy + first_order_opt matrices)")
@@ -417,6 +418,8 @@ def main():
         args.workload = f"w{args.waters}"
     if args.grad_waters == 0:
         args.no_grad = True
+    if args.sweep is None:
+        args.sweep = "16,32,64,128" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else ""
     args.sweep = [int(x) for x in str(args.sweep).split(",") if x.strip()]
     if args.impl == "reference":
         run_reference(args)
