@@ -138,3 +138,16 @@ def test_packed_cofactor_sets_against_determinants_of_minors(tmp_path):
                            os.path.join(csrc, "vb_cofactor.cpp")])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-3000:] + out.stderr
+
+
+def test_launcher_detection_of_the_nccl_layer(tmp_path):
+    """vb_nccl.cpp on the CPU: rank / size / local rank from torchrun, Open MPI, PMI and Slurm variables, the single-process
+    default, the rendezvous key (VB_NCCL_KEY | MASTER_PORT | parent pid), refusal of an impossible rank."""
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = tmp_path / "test_launch_env"
+    csrc = os.path.join(ROOT, "valence_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", csrc, "-I", os.path.join(cuda, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "host", "test_launch_env_host.cpp"), os.path.join(csrc, "vb_nccl.cpp"),
+                           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-ldl", "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout + out.stderr
