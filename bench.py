@@ -368,9 +368,10 @@ def run_ours(args) -> None:
                             "are rebuilt on the host and copied to the device inside the timed region"},
             "gpu_launches": rec["gpu_launches"],
             "roofline": {"bound": "fp64", "achieved": rec["roofline_achieved_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": rec["roofline_frac"],
-                         "traffic": traffic_from_profiles(args.workload),
+                         "traffic": traffic_from_profiles(args.workload) if world == 1 else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the class + contraction launches of one energy pass, ncu capture of "
-                                           "the same workload committed as profiles/r2_pclass_dram_<workload>.csv (not measured in this run; null when there is none)",
+                                           "the same workload on ONE GPU committed as profiles/r2_pclass_dram_<workload>.csv (not measured in this run; null "
+                                           "when there is none and on several GPUs, where a rank's launches move its share only)",
                          "transforms": {"achieved": rec["transform_tflops"], "unit": "TFLOP/s",
                                         "frac_integrals_plus_transforms": (rec["roofline_achieved_tflops"] + rec["transform_tflops"]) / peak if peak else None,
                                         "note": "executed FP64 tensor-core flops (DMMA m8n8k4 = 512 flops, in-kernel instruction count) of the two density "
