@@ -1,5 +1,5 @@
 """The reference arm of bench.py on the CPU (the arm the driver times beside the GPU arm): JSON-line contract, rank-0-only
-behaviour under a multi-rank launch.  The GPU arm's line is checked on the GPU box (tests/test_gpu_parity.py)."""
+behaviour under a multi-rank launch.  The GPU arm needs the device; its lines from the B200 runs are committed under profiles/ (r2_bench_*.json)."""
 import json
 import os
 import subprocess
